@@ -1,0 +1,214 @@
+/*
+ * pgb200.h — C-ABI of the B200 graph-filter propagation engine (libpgb200.so).
+ *
+ * This is the drop-in boundary for pygrank's iterative node-ranking hot path.  The
+ * reference is pure Python; its plugin surface for this path is the backend module
+ * contract /root/reference/pygrank/core/backend/specification.py:5-117 (conv, degrees,
+ * scipy_sparse_to_backend, graph_dropout, sum, abs, ...) bound by
+ * /root/reference/pygrank/core/backend/__init__.py:40-84.  A backend module
+ * (pygrank_b200/backend.py) implements that contract by calling the entry points below
+ * through ctypes; INTEGRATION.md shows the binding a pygrank maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; memory is owned
+ *     by the caller (PyTorch tensors); nothing is allocated or freed behind the ABI;
+ *   - every entry point returns 0 on success, non-zero on failure, and leaves a message
+ *     retrievable with pgb_last_error() (the Python shim raises Exception(msg), the
+ *     error style of the reference, e.g. core/backend/__init__.py:42,83);
+ *   - `stream` is a cudaStream_t passed as an opaque pointer (0 = default stream); all
+ *     work is enqueued on it and no entry point synchronises unless stated;
+ *   - dtype: PGB_F32 or PGB_F64 is the arithmetic/storage type of node vectors; all
+ *     grid-level reductions accumulate in fp64 in both modes;
+ *   - index types: int32 column indices and int32 row pointers (nnz < 2^31 per device;
+ *     larger graphs are row-partitioned across devices before they reach this ABI).
+ */
+#ifndef PGB200_H
+#define PGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGB_ABI_VERSION 1
+
+enum { PGB_F32 = 0, PGB_F64 = 1 };
+
+/* pgb_csr_build flags */
+enum {
+    PGB_BUILD_SYMMETRIZE = 1,      /* also insert (col,row) for every (row,col)            */
+    PGB_BUILD_DROP_SELF_LOOPS = 2, /* discard row == col                                    */
+    PGB_BUILD_BINARY = 4           /* duplicates collapse to weight 1 (else weights summed) */
+};
+
+/* scale kinds for pgb_make_scales: S[S != 0] = 1/S (preprocessing.py:111) after an
+ * optional sqrt (preprocessing.py:115,132) */
+enum { PGB_SCALE_ONE = 0, PGB_SCALE_RECIP = 1, PGB_SCALE_RSQRT = 2 };
+
+/* error measures of ConvergenceManager (convergence.py:96-101; measures/supervised.py) */
+enum {
+    PGB_ERR_MABS = 0, /* sum|prev-cur| / n   (Mabs, supervised.py:101-106; default) */
+    PGB_ERR_L1 = 1,   /* sum|prev-cur|       (L1,   supervised.py:125-130)          */
+    PGB_ERR_MSQ = 2,  /* sum (prev-cur)^2/n  (MSQ,  supervised.py:117-122)          */
+    PGB_ERR_ITERS = 3 /* error_type == "iters": never converges early (convergence.py:97-98) */
+};
+
+/* stop reasons written to pgb_state_i32[PGB_SI_STOP] */
+enum { PGB_RUNNING = 0, PGB_CONVERGED = 1, PGB_MAX_ITERS = 2 };
+
+/* Pull-CSR of the propagation operator: row i lists the sources j with a_ji != 0, so that
+ * conv(x, M)_i = (x @ M)_i = R_i * sum_j a_ji * (L_j * x_j)   (numpy.py:64-65 with the
+ * factorised normalisation of preprocessing.py:109-138).  `values` holds the RAW weights
+ * a_ji in the vector dtype, or NULL for an unweighted graph (all a_ji == 1).
+ * `tile_row` is the merge-path partition written by pgb_mergepath_partition. */
+typedef struct pgb_csr {
+    int64_t n;               /* nodes                                     */
+    int64_t nnz;             /* stored entries                            */
+    const int32_t *indptr;   /* [n+1]                                     */
+    const int32_t *indices;  /* [nnz] ascending within a row              */
+    const void *values;      /* [nnz] raw weights (dtype) or NULL         */
+    const int32_t *tile_row; /* [n_tiles+1]                               */
+    int32_t n_tiles;
+    int32_t tile_items;      /* must equal pgb_tile_items()               */
+} pgb_csr;
+
+/* Cross-tile workspace of one running filter: rows that straddle merge-path tiles are
+ * completed by the last tile to arrive.  Zero-filled by the caller once; self-resetting. */
+typedef struct pgb_span_ws {
+    double *acc;        /* [n_tiles * ncols]  */
+    uint32_t *cnt;      /* [n_tiles]          */
+} pgb_span_ws;
+
+/* Device-resident iteration state (mirror of ConvergenceManager, convergence.py:24-101). */
+enum { /* indices into state_f64[PGB_STATE_F64_LEN] */
+    PGB_SF_ALPHA = 0, /* multiplier of the propagated term in the next normaliser        */
+    PGB_SF_BIAS = 1,  /* sum of the affine term (e.g. (1-alpha)*sum(p))                  */
+    PGB_SF_INVS = 2,  /* 1/sum(ranks) the CURRENT launch divides by (use_quotient)       */
+    PGB_SF_TACC = 3,  /* accumulator: sum_i ranks_i * c_i of the current launch          */
+    PGB_SF_EACC = 4,  /* accumulator: error numerator of the current launch              */
+    PGB_SF_TOL = 5,   /* max(tol, epsilon) or 0 for tol=None (convergence.py:101)        */
+    PGB_SF_MEAN = 6,  /* divisor of the error (n for Mabs/MSQ, 1 for L1)                 */
+    PGB_SF_LASTERR = 7,
+    PGB_SF_NORM = 8,  /* sum|personalization| (abstract_filters.py:52)                   */
+    PGB_SF_PSUM = 9,  /* sum(personalization)                                            */
+    PGB_STATE_F64_LEN = 16
+};
+enum { /* indices into state_i32[PGB_STATE_I32_LEN] */
+    PGB_SI_TICKET = 0,
+    PGB_SI_STEPS = 1,     /* _step calls completed                                        */
+    PGB_SI_STOP = 2,      /* PGB_RUNNING / PGB_CONVERGED / PGB_MAX_ITERS                  */
+    PGB_SI_ITERATION = 3, /* ConvergenceManager.iteration when the loop stopped           */
+    PGB_SI_MAX_ITERS = 4,
+    PGB_SI_END_MODULO = 5,
+    PGB_SI_ERR_MODE = 6,
+    PGB_SI_QUOTIENT = 7,  /* use_quotient (abstract_filters.py:133-134)                   */
+    PGB_STATE_I32_LEN = 16
+};
+
+int pgb_abi_version(void);
+const char *pgb_last_error(void);
+int pgb_tile_items(void);       /* merge-path items (rows + entries) per tile            */
+int pgb_device_sm_count(int device);
+
+/* ---- synthetic graphs (bench/tests; no reference counterpart, graphs are downloaded in
+ *      /root/reference/pygrank/benchmarks/download.py:62-72) ------------------------------ */
+int pgb_rmat_edges(int scale, int64_t first_edge, int64_t num_edges, uint64_t seed,
+                   uint32_t t1, uint32_t t2, uint32_t t3, int32_t *src, int32_t *dst, void *stream);
+int pgb_ba_edges(int64_t n, int m, int64_t first_slot, int64_t num_slots, uint64_t seed,
+                 int32_t *src, int32_t *dst, void *stream);
+
+/* ---- K1: graph -> CSR (replaces nx.to_scipy_sparse_array / coo.tocsr,
+ *      /root/reference/pygrank/core/utils/preprocessing.py:103 and fastgraph/fastgraph.py:73-78) */
+size_t pgb_csr_build_workspace_bytes(int64_t n, int64_t nnz_in, int flags, int weighted);
+/* COO (row, col[, val]) -> canonical CSR (ascending columns, duplicates merged).
+ * out_indices/out_values need capacity nnz_in * (SYMMETRIZE ? 2 : 1).  *out_nnz_host is
+ * written after an internal stream synchronise. */
+int pgb_csr_build(int64_t n, int64_t nnz_in, const int32_t *row, const int32_t *col, const double *val,
+                  int flags, void *workspace, size_t workspace_bytes, int32_t *out_indptr,
+                  int32_t *out_indices, double *out_values, int64_t *out_nnz_host, void *stream);
+/* rows[k] = i for indptr[i] <= k < indptr[i+1] (CSR -> COO row expansion) */
+int pgb_csr_expand_rows(int64_t n, int64_t nnz, const int32_t *indptr, int32_t *rows, void *stream);
+/* perm = node ids sorted by descending degree (stable); iperm[perm[i]] = i */
+size_t pgb_degree_order_workspace_bytes(int64_t n);
+int pgb_degree_order(int64_t n, const int32_t *indptr, void *workspace, size_t workspace_bytes,
+                     int32_t *perm, int32_t *iperm, void *stream);
+int pgb_relabel_coo(int64_t nnz, const int32_t *iperm, int32_t *row, int32_t *col, void *stream);
+int pgb_mergepath_partition(int64_t n, int64_t nnz, const int32_t *indptr, int32_t n_tiles,
+                            int32_t *tile_row, void *stream);
+
+/* ---- K1/K7: degrees and normalisation (preprocessing.py:104-138; numpy.py:76-77) ----- */
+/* out[i] = sum of values (or entry count when values == NULL) of row i, fp64 */
+int pgb_csr_row_sums(int64_t n, const int32_t *indptr, const double *values, double *out, void *stream);
+/* out = kind(S) with zeros kept zero: S[S != 0] = 1/S[S != 0], after sqrt for RSQRT */
+int pgb_make_scales(int64_t n, const double *sums, int kind, double *out, void *stream);
+/* data[k] = (left[i] * a_ik) * right[col k] — the normalised CSR exactly as scipy's two
+ * diagonal products round it (preprocessing.py:113,138); values == NULL means a_ik = 1 */
+int pgb_csr_normalized_values(int64_t n, const int32_t *indptr, const int32_t *indices, const double *values,
+                              const double *left, const double *right, double *out_data, void *stream);
+/* numpy-compatible pairwise row sums of explicit data (np.add.reduceat as called by
+ * scipy's CSR sum(axis=1), numpy.py:76-77); reverse != 0 walks each row backwards (the
+ * storage order left by one diagonal product, i.e. "col" normalisation) */
+int pgb_csr_row_sums_numpy(int64_t n, const int32_t *indptr, const double *data, int reverse, double *out,
+                           void *stream);
+
+/* ---- K2/K4/K5: fused propagation steps ------------------------------------------------ */
+/* Plain conv (numpy.py:64-65): y_i = rscale_i * sum_j a_ji z_j, optionally y_i = x_i - that
+ * (laplacian, preprocessing.py:122).  z is the PRE-SCALED input (L .* x, see pgb_scale).
+ * out_perm != NULL scatters y_i to out[out_perm[i]]. */
+int pgb_spmv(const pgb_csr *g, int dtype, const void *z, const void *rscale, const void *x_for_laplacian,
+             const int32_t *out_perm, void *out, pgb_span_ws ws, void *stream);
+
+/* Affine recursion in the scaled domain z = ranks / sq (PageRank adhoc.py:34-36 and
+ * AbsorbingWalks adhoc.py:166-169 with RecursiveGraphFilter._step's quotient,
+ * abstract_filters.py:126-136, and the Mabs check, convergence.py:96-101, fused):
+ *     z'_i = (alpha * w_i * sum_j a_ji z_j + q_i) * invS
+ *     err += sq_i * |z'_i - z_i|   (or its square)      T += z'_i * c_i
+ * w / sq may be NULL for symmetric unweighted graphs: w_i = 1/deg_i, sq_i = sqrt(deg_i)
+ * are then derived from the row pointers (deg 0 -> w = 0, sq = 1).
+ * Enqueues `num_launches` steps alternating zbuf0/zbuf1 (step k reads buf[(k-1)&1], writes
+ * buf[k&1], k = first_step..); a step whose state says STOP != RUNNING exits untouched.
+ * finalize != 0: the last CTA of each launch updates the state (single GPU); 0: caller
+ * all-reduces the accumulators and calls pgb_state_finalize (row-partitioned multi-GPU). */
+int pgb_affine_steps(const pgb_csr *g, int dtype, double alpha, const void *w, const void *sq, const void *c,
+                     const void *q, void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64,
+                     int32_t *state_i32, double *err_hist, pgb_span_ws ws, int first_step, int num_launches,
+                     int finalize, void *stream);
+
+/* Closed-form (polynomial) filter step (ClosedFormGraphFilter._step, abstract_filters.py:248-256,
+ * taylor recursion :225-228, power advance :241-246), in the scaled domain zp = power / sq:
+ *     ranks_i += coef[k] * sq_i * zp_i ;  err += |delta ranks_i| ;  zp'_i = w_i * sum_j a_ji zp_j
+ * coef is a device array indexed by step (coef[k] for k >= 1). */
+int pgb_poly_steps(const pgb_csr *g, int dtype, const void *w, const void *sq, const double *coef,
+                   void *ranks, void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64,
+                   int32_t *state_i32, double *err_hist, pgb_span_ws ws, int first_step, int num_launches,
+                   int finalize, void *stream);
+
+/* One-thread state update for the deferred (multi-GPU) mode. */
+int pgb_state_finalize(double *state_f64, int32_t *state_i32, double *err_hist, void *stream);
+
+/* ---- vector helpers around the fused steps (K6) ----------------------------------------- */
+/* out[i] = a[src] * b[src] * scale with src = perm ? perm[i] : i   (b may be NULL) */
+int pgb_scale(int64_t n, int dtype, const void *a, const void *b, double scale, const int32_t *perm,
+              void *out, void *stream);
+/* out[dst] = a[i] * b[i] * (*dev_scale or 1) * scale with dst = perm ? perm[i] : i */
+int pgb_unscale(int64_t n, int dtype, const void *a, const void *b, const double *dev_scale, double scale,
+                const int32_t *perm, void *out, void *stream);
+/* sums[0] += sum|x_i|, sums[1] += sum x_i, sums[2] += sum x_i*y_i (y may be NULL); fp64 */
+int pgb_reduce3(int64_t n, int dtype, const void *x, const void *y, double *sums, void *stream);
+/* Start of GraphFilter.rank (abstract_filters.py:52-56) in the engine's domain: with
+ * norm = state[NORM] (set from pgb_reduce3) and src = perm ? perm[i] : i,
+ *     pn = p[src]/norm ; z0[out_offset+i] = (warm ? warm[src] : pn) / sq_i ;
+ *     q_i = (coefvec ? coefvec[i] : coef) * pn / sq_i          (q may be NULL)
+ * and accumulates state[TACC] += z0_i*c_i (c may be NULL), state[BIAS] += q_i*sq_i. */
+int pgb_affine_init(int64_t n, int dtype, const void *p, const void *warm, const void *sq, const void *c,
+                    double coef, const void *coefvec, const int32_t *perm, int64_t out_offset, void *z0, void *q,
+                    double *state_f64, void *stream);
+/* invS for the first step from the accumulated T / BIAS (one thread). */
+int pgb_affine_init_finish(double *state_f64, int32_t *state_i32, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGB200_H */

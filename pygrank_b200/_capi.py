@@ -1,0 +1,127 @@
+"""ctypes binding of libpgb200.so (the C-ABI declared in include/pgb200.h).
+
+The library is the product: if it is missing or a call fails this module raises — there is
+no CPU or PyTorch fallback anywhere in the package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpgb200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+PGB_F32, PGB_F64 = 0, 1
+BUILD_SYMMETRIZE, BUILD_DROP_SELF_LOOPS, BUILD_BINARY = 1, 2, 4
+SCALE_ONE, SCALE_RECIP, SCALE_RSQRT = 0, 1, 2
+ERR_MABS, ERR_L1, ERR_MSQ, ERR_ITERS = 0, 1, 2, 3
+RUNNING, CONVERGED, MAX_ITERS = 0, 1, 2
+# state_f64 / state_i32 slots
+SF_ALPHA, SF_BIAS, SF_INVS, SF_TACC, SF_EACC, SF_TOL, SF_MEAN, SF_LASTERR, SF_NORM, SF_PSUM = range(10)
+SI_TICKET, SI_STEPS, SI_STOP, SI_ITERATION, SI_MAX_ITERS, SI_END_MODULO, SI_ERR_MODE, SI_QUOTIENT = range(8)
+STATE_LEN = 16
+
+
+class Csr(Structure):
+    _fields_ = [("n", c_int64), ("nnz", c_int64), ("indptr", c_void_p), ("indices", c_void_p), ("values", c_void_p),
+                ("tile_row", c_void_p), ("n_tiles", c_int32), ("tile_items", c_int32)]
+
+
+class SpanWs(Structure):
+    _fields_ = [("acc", c_void_p), ("cnt", c_void_p)]
+
+
+_SIGNATURES = {
+    "pgb_abi_version": (c_int, []),
+    "pgb_last_error": (c_char_p, []),
+    "pgb_tile_items": (c_int, []),
+    "pgb_device_sm_count": (c_int, [c_int]),
+    "pgb_rmat_edges": (c_int, [c_int, c_int64, c_int64, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p,
+                               c_void_p]),
+    "pgb_ba_edges": (c_int, [c_int64, c_int, c_int64, c_int64, c_uint64, c_void_p, c_void_p, c_void_p]),
+    "pgb_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "pgb_csr_build": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p,
+                              c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
+    "pgb_csr_expand_rows": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "pgb_degree_order_workspace_bytes": (c_size_t, [c_int64]),
+    "pgb_degree_order": (c_int, [c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "pgb_relabel_coo": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgb_mergepath_partition": (c_int, [c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
+    "pgb_csr_row_sums": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgb_make_scales": (c_int, [c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "pgb_csr_normalized_values": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
+    "pgb_csr_row_sums_numpy": (c_int, [c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "pgb_spmv": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, SpanWs, c_void_p]),
+    "pgb_affine_steps": (c_int, [POINTER(Csr), c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, c_int, c_int,
+                                 c_void_p]),
+    "pgb_poly_steps": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, c_int, c_int, c_void_p]),
+    "pgb_state_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgb_scale": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "pgb_unscale": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "pgb_reduce3": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgb_affine_init": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p,
+                                c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgb_affine_init_finish": (c_int, [c_void_p, c_void_p, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+# number of kernels of OURS enqueued since import (bench.py reports the delta over the timed region)
+LAUNCHES = [0]
+
+
+def count_launches(k: int) -> None:
+    LAUNCHES[0] += int(k)
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libpgb200.so for sm_100a with nvcc (in-tree; needs no GPU)."""
+    res = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise Exception("building libpgb200.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Exception(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(pygrank_b200 has no CPU fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if handle.pgb_abi_version() != 1:
+            raise Exception("libpgb200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(status: int) -> None:
+    """Raise the library's last error (plain Exception, the reference's error style)."""
+    if status != 0:
+        raise Exception("pgb200: " + lib().pgb_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t) -> int:
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

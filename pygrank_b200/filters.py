@@ -1,0 +1,387 @@
+"""Fused on-device graph filters — the host-side mirror of pygrank's filter interface.
+
+Same class names, constructor arguments, iteration semantics and error behaviour as the
+reference (paths under /root/reference/pygrank/algorithms):
+
+* ``GraphFilter.rank``                 filters/abstract_filters.py:44-65
+* ``RecursiveGraphFilter._step``       filters/abstract_filters.py:126-136  (``use_quotient``)
+* ``ClosedFormGraphFilter._step``      filters/abstract_filters.py:196-256  (taylor, node space)
+* ``PageRank`` / ``PageRankClosed`` / ``HeatKernel`` / ``AbsorbingWalks``   filters/adhoc.py:10-174
+* ``GenericGraphFilter``               filters/low_pass.py:5-26
+* ``ConvergenceManager``               convergence.py:9-104
+
+but the whole loop runs on the device: every iteration is ONE launch of the fused merge-path
+kernel (csrc/spmv_fused.cu), convergence is decided by the last CTA of that launch, and the host
+enqueues iterations ahead of the device (run-ahead launches after convergence exit immediately),
+reading the 64-byte state back only once per chunk.  The unchanged reference drivers also run on
+this engine through the backend plugin (pygrank_b200/backend.py); these classes are the fast path.
+"""
+from __future__ import annotations
+
+import ctypes
+import time
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi as C
+from .graph import DeviceGraph, as_device_graph, dtype_code, preprocessor as device_preprocessor, span_struct
+
+_ERROR_NAMES = {"mabs": C.ERR_MABS, "l1": C.ERR_L1, "msq": C.ERR_MSQ, "iters": C.ERR_ITERS}
+
+
+def _error_code(error_type) -> int:
+    name = error_type if isinstance(error_type, str) else getattr(error_type, "__name__", str(error_type))
+    name = name.lower()
+    if name not in _ERROR_NAMES:
+        raise Exception("the device engine fuses the Mabs, L1, MSQ and 'iters' criteria; got " + str(error_type))
+    return _ERROR_NAMES[name]
+
+
+class ConvergenceManager:
+    """Argument-compatible with convergence.py:24-60; the checks themselves run on the device
+    (``finalize_state`` in csrc/spmv_fused.cu) and this object reports their outcome."""
+
+    def __init__(self, tol: Optional[float] = 1.E-6, error_type="mabs", max_iters: int = 100, end_modulo: int = 1,
+                 iter_exception=Exception):
+        self.tol = tol
+        self.error_type = error_type
+        self.max_iters = int(max_iters)
+        self.end_modulo = int(end_modulo)
+        self.iter_exception = iter_exception
+        self.iteration = 0
+        self.elapsed_time = None
+        self.errors = None
+
+    def __str__(self):
+        return str(self.iteration) + " iterations (" + str(self.elapsed_time) + " sec)"
+
+
+class RankResult:
+    """What ``rank`` returns: the scores as a device tensor in the user's node order
+    (``.np``, like ``GraphSignal.np``, signals.py:81-83) with dict-style access by node."""
+
+    def __init__(self, graph: DeviceGraph, values: torch.Tensor):
+        self.graph = graph
+        self.np = values
+
+    def numpy(self) -> np.ndarray:
+        return self.np.detach().cpu().numpy()
+
+    def __getitem__(self, node) -> float:
+        return float(self.np[self.graph._pygrank_node2id[node]])
+
+    def __len__(self):
+        return self.graph.n
+
+
+def _personalization(g: DeviceGraph, data, dtype: torch.dtype):
+    """``to_signal`` + the L1 norm of abstract_filters.py:52 — returns (device vector, norm)."""
+    dev = g.out_view.indptr.device
+    n = g.n
+    if isinstance(data, RankResult):
+        data = data.np
+    if data is None:                                         # signals.py:59-60: a signal of ones
+        return torch.ones(n, dtype=dtype, device=dev), float(n)
+    if isinstance(data, torch.Tensor):
+        p = data.to(device=dev, dtype=dtype).contiguous().reshape(-1)
+        if p.numel() != n:
+            raise Exception("Graph signal array dimensions " + str(p.numel()) + " should be equal to graph nodes " + str(n))
+        return p, float(p.abs().sum(dtype=torch.float64))
+    if isinstance(data, dict) or (isinstance(data, (list, tuple)) and len(data) != n):
+        if not isinstance(data, dict):
+            data = {v: 1 for v in data}                      # signals.py:314-315
+        node2id = g._pygrank_node2id
+        idx = np.fromiter((node2id[k] for k in data.keys()), dtype=np.int64, count=len(data))
+        vals = np.fromiter((float(v) for v in data.values()), dtype=np.float64, count=len(data))
+        p = torch.zeros(n, dtype=dtype, device=dev)
+        if len(idx):
+            p[torch.from_numpy(idx).to(dev)] = torch.from_numpy(vals).to(device=dev, dtype=dtype)
+        return p, float(np.abs(vals).sum())
+    arr = np.asarray(data, dtype=np.float64).reshape(-1)
+    if arr.shape[0] != n:
+        raise Exception("Graph signal array dimensions " + str(arr.shape[0]) + " should be equal to graph nodes " + str(n))
+    return torch.from_numpy(arr).to(device=dev, dtype=dtype), float(np.abs(arr).sum())
+
+
+class GraphFilter:
+    """Base of the device filters (constructor arguments of abstract_filters.py:14-39 that concern
+    the hot path).  ``dtype`` selects fp64 (parity mode, default) or fp32."""
+
+    def __init__(self, preprocessor=None, convergence=None, preserve_norm: bool = True,
+                 normalization: str = "auto", renormalize=False, assume_immutability: bool = False,
+                 tol: Optional[float] = 1.E-6, error_type="mabs", max_iters: int = 100, end_modulo: int = 1,
+                 dtype: torch.dtype = torch.float64, relabel: str = "degree", chunk: int = 8):
+        self.preprocessor = preprocessor if preprocessor is not None else device_preprocessor(
+            normalization=normalization, renormalize=renormalize, assume_immutability=assume_immutability,
+            relabel=relabel)
+        self.convergence = convergence if convergence is not None else ConvergenceManager(
+            tol=tol, error_type=error_type, max_iters=max_iters, end_modulo=end_modulo)
+        self.preserve_norm = preserve_norm
+        self.dtype = dtype
+        self.chunk = int(chunk)
+
+    # -- public API -------------------------------------------------------------------------
+    def __call__(self, graph=None, personalization=None, *args, **kwargs) -> RankResult:
+        return self.rank(graph, personalization, *args, **kwargs)
+
+    def __add__(self, other):                                 # abstract_filters.py:88-98
+        if isinstance(other, ConvergenceManager):
+            self.convergence = other
+        elif hasattr(other, "__name__") and other.__name__ == "preprocess":
+            self.preprocessor = other
+        else:
+            raise Exception("Can only add convergence managers and preprocessors to graph filters")
+        return self
+
+    def rank(self, graph=None, personalization=None, warm_start=None, graph_dropout: float = 0, **kwargs) -> RankResult:
+        if graph is None and isinstance(personalization, RankResult):
+            graph = personalization.graph
+        g = self.preprocessor(graph)
+        if not isinstance(g, DeviceGraph):
+            g = as_device_graph(g)
+        if graph_dropout != 0:
+            raise Exception("graph_dropout with the fused filters is not supported; use the backend plugin path")
+        p, norm = _personalization(g, personalization, self.dtype)
+        cm = self.convergence
+        cm.iteration, cm.errors = 0, None
+        t0 = time.perf_counter()
+        if norm == 0:                                         # abstract_filters.py:53-54
+            cm.elapsed_time = time.perf_counter() - t0
+            return RankResult(g, p)
+        if g.pathological:
+            raise Exception("a row of the graph has entries but a zero weight sum; the fused filters cannot represent it")
+        warm = None
+        if warm_start is not None:
+            warm, _ = _personalization(g, warm_start, self.dtype)
+        out = self._run(g, p, norm, warm, **kwargs)
+        cm.elapsed_time = time.perf_counter() - t0
+        return RankResult(g, out)
+
+    def propagate(self, graph, features, *args, **kwargs) -> torch.Tensor:
+        """``NodeRanking.propagate`` (signals.py:225-226): one rank per feature column."""
+        g = self.preprocessor(graph)
+        cols = features if isinstance(features, torch.Tensor) else torch.as_tensor(np.asarray(features))
+        outs = [self.rank(g, cols[:, c].contiguous(), *args, **kwargs).np for c in range(cols.shape[1])]
+        return torch.stack(outs, dim=1)
+
+    # -- machinery shared by the subclasses ---------------------------------------------------
+    def _new_state(self, g: DeviceGraph, norm: float, alpha_s: float, quotient: bool):
+        cm = self.convergence
+        dev = g.out_view.indptr.device
+        code = _error_code(cm.error_type)
+        sf = [0.0] * C.STATE_LEN
+        si = [0] * C.STATE_LEN
+        sf[C.SF_ALPHA] = float(alpha_s)
+        sf[C.SF_INVS] = 1.0
+        sf[C.SF_TOL] = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))  # convergence.py:101
+        sf[C.SF_MEAN] = 1.0 if code == C.ERR_L1 else float(g.n)
+        sf[C.SF_NORM] = float(norm)
+        si[C.SI_MAX_ITERS] = cm.max_iters
+        si[C.SI_END_MODULO] = max(cm.end_modulo, 1)
+        si[C.SI_ERR_MODE] = code
+        si[C.SI_QUOTIENT] = int(bool(quotient))
+        state_f64 = torch.tensor(sf, dtype=torch.float64, device=dev)
+        state_i32 = torch.tensor(si, dtype=torch.int32, device=dev)
+        err_hist = torch.zeros(cm.max_iters + 2, dtype=torch.float64, device=dev)
+        return state_f64, state_i32, err_hist
+
+    def _drive(self, launch, state_i32: torch.Tensor, err_hist: torch.Tensor):
+        """Run-ahead loop: enqueue a chunk of steps, read the state, repeat.  Returns #steps done."""
+        cm = self.convergence
+        budget = cm.max_iters - 1                             # convergence.py:85-90: at most max_iters-1 steps
+        done = 0
+        chunk = max(self.chunk, 1)
+        stop, steps, iteration = C.RUNNING, 0, 1
+        while done < budget:
+            k = min(chunk, budget - done)
+            launch(done + 1, k)
+            done += k
+            host = state_i32.cpu()
+            stop, steps, iteration = int(host[C.SI_STOP]), int(host[C.SI_STEPS]), int(host[C.SI_ITERATION])
+            if stop != C.RUNNING:
+                break
+            chunk = min(chunk * 2, 64)
+        if stop == C.RUNNING:                                 # max_iters <= 1: stopped before any step
+            iteration, stop = 1, C.MAX_ITERS
+        cm.iteration = iteration
+        cm.errors = err_hist[1:steps + 1]
+        if stop == C.MAX_ITERS and _error_code(cm.error_type) != C.ERR_ITERS and cm.iter_exception is not None:
+            raise cm.iter_exception("Could not converge within " + str(cm.max_iters) + " iterations")
+        return steps
+
+    def _run(self, g, p, norm, warm, **kwargs):
+        raise Exception("Use a derived class of GraphFilter")
+
+
+class RecursiveGraphFilter(GraphFilter):
+    """ranks <- (coefficient_vector * conv(ranks, M) + affine_term) [/ sum], the shape shared by
+    PageRank and AbsorbingWalks (abstract_filters.py:126-136)."""
+
+    def __init__(self, use_quotient: bool = True, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if not isinstance(use_quotient, bool) and use_quotient is not None:
+            raise Exception("the fused filters take use_quotient=True/False (postprocessor quotients run on the plugin path)")
+        self.use_quotient = bool(use_quotient)
+
+    def _affine(self, g: DeviceGraph, p, norm, warm, alpha: float, alpha_s: float, w_run, c_run, coef, coefvec):
+        lib = C.lib()
+        dtype, code = self.dtype, dtype_code(self.dtype)
+        dev, n = p.device, g.n
+        st = C.stream_ptr()
+        state_f64, state_i32, err_hist = self._new_state(g, norm, alpha_s, self.use_quotient)
+        sq = g.vec("sq", dtype)
+        c = c_run if c_run is not None else g.vec("c", dtype)
+        zbuf = [torch.empty(n, dtype=dtype, device=dev), torch.empty(n, dtype=dtype, device=dev)]
+        q = torch.empty(n, dtype=dtype, device=dev)
+        C.check(lib.pgb_affine_init(n, code, C.ptr(p), C.ptr(warm), C.ptr(sq), C.ptr(c), float(coef), C.ptr(coefvec),
+                                    C.ptr(g.perm), 0, C.ptr(zbuf[0]), C.ptr(q), C.ptr(state_f64), st))
+        C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
+        C.count_launches(3)                                   # init, init_finish, final unscale
+        view = g.in_view
+        cs = view.cstruct(dtype)
+        ws = view.new_span_ws()
+        symdeg = g.symdeg and w_run is None
+        w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
+        sq_arg = None if symdeg else sq
+
+        def launch(first, count):
+            C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, float(alpha), C.ptr(w), C.ptr(sq_arg), C.ptr(c),
+                                         C.ptr(q), C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(state_f64),
+                                         C.ptr(state_i32), C.ptr(err_hist), span_struct(ws), first, count, 1, st))
+            C.count_launches(count)
+
+        steps = self._drive(launch, state_i32, err_hist)
+        out = torch.empty(n, dtype=dtype, device=dev)
+        C.check(lib.pgb_unscale(n, code, C.ptr(zbuf[steps & 1]), C.ptr(sq), None,
+                                float(norm) if self.preserve_norm else 1.0, C.ptr(g.perm), C.ptr(out), st))
+        return out
+
+
+class PageRank(RecursiveGraphFilter):
+    """Personalized PageRank power method (adhoc.py:10-45):
+    ranks <- conv(ranks, M)*alpha + personalization*(1-alpha)."""
+
+    def __init__(self, alpha: float = 0.85, *args, **kwargs):
+        self.alpha = alpha
+        super().__init__(*args, **kwargs)
+
+    def _run(self, g, p, norm, warm, **kwargs):
+        return self._affine(g, p, norm, warm, alpha=self.alpha, alpha_s=self.alpha, w_run=None, c_run=None,
+                            coef=1 - self.alpha, coefvec=None)
+
+
+class AbsorbingWalks(RecursiveGraphFilter):
+    """Partially absorbing random walks (adhoc.py:124-174):
+    ranks <- (conv(ranks, M)*degrees + personalization*absorption) / (absorption + degrees)."""
+
+    def __init__(self, alpha: float = 1 - 1.E-6, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alpha = alpha
+
+    def _run(self, g, p, norm, warm, absorption=None, **kwargs):
+        dtype = self.dtype
+        f64 = torch.float64
+        dev = p.device
+        rate = (1 - self.alpha) / self.alpha                  # adhoc.py:158
+        if absorption is None:
+            ab = torch.full((g.n,), rate, dtype=f64, device=dev)
+        else:
+            ab_user, _ = _personalization(g, absorption, f64)
+            ab = (ab_user if g.perm is None else ab_user[g.perm.long()]) * rate
+        degM = g.vec("degM", f64)
+        denom = ab + degM
+        d1 = degM / denom
+        w_run = (g.vec("w", f64) * d1).to(dtype)              # coefficient of the gathered sum
+        coefvec = (ab / denom).to(dtype)                      # coefficient of the personalization
+        gsum = g._spmv_raw(g.out_view, g.R * d1, g.L, f64)    # rowsum of M*diag(d1): next normaliser is linear
+        c_run = (g.vec("sq", f64) * gsum).to(dtype)
+        return self._affine(g, p, norm, warm, alpha=1.0, alpha_s=1.0, w_run=w_run, c_run=c_run, coef=0.0,
+                            coefvec=coefvec)
+
+
+class ClosedFormGraphFilter(GraphFilter):
+    """Taylor-coefficient polynomial filters in the node space (abstract_filters.py:139-267)."""
+
+    def __init__(self, krylov_dims=None, coefficient_type: str = "taylor", optimization_dict=None, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if krylov_dims is not None or coefficient_type.lower() != "taylor" or optimization_dict is not None:
+            raise Exception("the fused closed-form filter implements taylor coefficients in the node space; "
+                            "krylov/chebyshev/optimization_dict run on the backend plugin path")
+
+    def _coefficient(self, previous_coefficient, iteration: int) -> float:
+        raise Exception("Use a derived class of ClosedFormGraphFilter that implements the _coefficient method")
+
+    def _run(self, g, p, norm, warm, **kwargs):
+        lib = C.lib()
+        dtype, code = self.dtype, dtype_code(self.dtype)
+        dev, n = p.device, g.n
+        st = C.stream_ptr()
+        cm = self.convergence
+        coefs, prev = [0.0], None
+        for k in range(1, max(cm.max_iters, 1) + 1):          # step k runs with convergence.iteration == k
+            prev = self._coefficient(prev, k)
+            coefs.append(float(prev))
+        coef_dev = torch.tensor(coefs, dtype=torch.float64, device=dev)
+        state_f64, state_i32, err_hist = self._new_state(g, norm, 1.0, False)
+        sq = g.vec("sq", dtype)
+        zbuf = [torch.empty(n, dtype=dtype, device=dev), torch.empty(n, dtype=dtype, device=dev)]
+        ranks = torch.zeros(n, dtype=dtype, device=dev)       # abstract_filters.py:213
+        C.check(lib.pgb_affine_init(n, code, C.ptr(p), None, C.ptr(sq), None, 0.0, None, C.ptr(g.perm), 0,
+                                    C.ptr(zbuf[0]), None, C.ptr(state_f64), st))   # power = personalization (:212)
+        C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
+        view = g.in_view
+        cs = view.cstruct(dtype)
+        ws = view.new_span_ws()
+        symdeg = g.symdeg
+        w = None if symdeg else g.vec("w", dtype)
+        sq_arg = None if symdeg else sq
+
+        def launch(first, count):
+            C.check(lib.pgb_poly_steps(ctypes.byref(cs), code, C.ptr(w), C.ptr(sq_arg), C.ptr(coef_dev), C.ptr(ranks),
+                                       C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(state_f64), C.ptr(state_i32),
+                                       C.ptr(err_hist), span_struct(ws), first, count, 1, st))
+            C.count_launches(count)
+
+        C.count_launches(3)
+        self._drive(launch, state_i32, err_hist)
+        out = torch.empty(n, dtype=dtype, device=dev)
+        C.check(lib.pgb_unscale(n, code, C.ptr(ranks), None, None, float(norm) if self.preserve_norm else 1.0,
+                                C.ptr(g.perm), C.ptr(out), st))
+        return out
+
+
+class HeatKernel(ClosedFormGraphFilter):
+    """adhoc.py:95-121 — coefficient 1, then previous*t/(iteration+1)."""
+
+    def __init__(self, t: float = 3, *args, **kwargs):
+        self.t = t
+        super().__init__(*args, **kwargs)
+
+    def _coefficient(self, previous_coefficient, iteration):
+        return 1. if previous_coefficient is None else previous_coefficient * self.t / (iteration + 1)
+
+
+class PageRankClosed(ClosedFormGraphFilter):
+    """adhoc.py:62-92 — coefficient 1, then previous*alpha."""
+
+    def __init__(self, alpha: float = 0.85, *args, **kwargs):
+        self.alpha = alpha
+        super().__init__(*args, **kwargs)
+
+    def _coefficient(self, previous_coefficient, iteration):
+        return 1. if previous_coefficient is None else previous_coefficient * self.alpha
+
+
+class GenericGraphFilter(ClosedFormGraphFilter):
+    """low_pass.py:5-26 — coefficient weights[iteration-1], 0 past the end."""
+
+    def __init__(self, weights: Optional[Sequence[float]] = None, **kwargs):
+        super().__init__(**kwargs)
+        self.weights = list(weights) if weights is not None else [0.9] * 10
+
+    def _coefficient(self, _, iteration):
+        if iteration > len(self.weights):
+            return 0
+        return self.weights[iteration - 1]

@@ -1,0 +1,518 @@
+"""Device-resident graphs and the device preprocessor.
+
+Mirrors ``pygrank.core.utils.preprocessing`` for the hot path
+(/root/reference/pygrank/core/utils/preprocessing.py):
+
+* ``to_sparse_matrix`` / ``preprocessor``  (:50-152, :233-287)  ->  :func:`preprocessor`,
+  :meth:`DeviceGraph.from_scipy`, :meth:`DeviceGraph.from_edges`
+* ``Adjacency`` (:9-28)                                          ->  :class:`DeviceGraph` (has ``.array``, ``.shape``)
+
+HBM layout (all torch CUDA tensors, owned here, handed to libpgb200 as raw pointers):
+
+* pull CSR of the propagation operator — ``indptr int32[n+1]``, ``indices int32[nnz]`` (sources of
+  every destination row, ascending), optional raw weights in the vector dtype — in the engine's
+  INTERNAL node order (optionally degree-sorted so that hub entries of the gather vector share
+  cache lines), plus the merge-path partition ``tile_row int32[n_tiles+1]``;
+* the normalisation kept FACTORISED: degrees (row/col sums, fp64), left/right scales
+  ``L = f(rowsum)``, ``R = f(colsum)`` with the reference's exact rounding, so an unweighted
+  graph streams no edge values at all — ``M[j,i] = (L[j]*a_ji)*R[i]`` is applied as a pre-scaled
+  gather vector and a per-row factor inside the kernels;
+* ``perm``/``iperm`` (int32[n]) between user order and internal order.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _capi as C
+
+_DT = {torch.float32: C.PGB_F32, torch.float64: C.PGB_F64}
+
+
+def _dev(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise Exception("pygrank_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype not in _DT:
+        raise Exception("pygrank_b200 vectors are float32 or float64, not " + str(dtype))
+    return _DT[dtype]
+
+
+def build_csr(n: int, row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], flags: int):
+    """COO -> canonical CSR through ``pgb_csr_build``; returns (indptr, indices, values|None)."""
+    lib = C.lib()
+    nnz_in = int(row.numel())
+    dev = row.device
+    weighted = val is not None
+    keep_vals = weighted and not (flags & C.BUILD_BINARY)
+    cap = nnz_in * (2 if flags & C.BUILD_SYMMETRIZE else 1)
+    ws_bytes = lib.pgb_csr_build_workspace_bytes(n, nnz_in, flags, int(weighted))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    values = torch.empty(max(cap, 1), dtype=torch.float64, device=dev) if keep_vals else None
+    nnz_out = ctypes.c_int64(0)
+    C.check(lib.pgb_csr_build(n, nnz_in, C.ptr(row), C.ptr(col), C.ptr(val), flags, C.ptr(ws), ws_bytes,
+                              C.ptr(indptr), C.ptr(indices), C.ptr(values), ctypes.byref(nnz_out), C.stream_ptr()))
+    del ws
+    nnz = int(nnz_out.value)
+    indices = indices[:nnz].clone() if nnz < cap else indices[:nnz]
+    if values is not None:
+        values = values[:nnz].clone() if nnz < cap else values[:nnz]
+    return indptr, indices, values
+
+
+class CsrView:
+    """One CSR structure in HBM with its merge-path partition and cross-tile workspace."""
+
+    def __init__(self, n: int, indptr: torch.Tensor, indices: torch.Tensor, values64: Optional[torch.Tensor]):
+        lib = C.lib()
+        self.n = int(n)
+        self.nnz = int(indices.numel())
+        self.indptr, self.indices = indptr, indices
+        self._values = {torch.float64: values64} if values64 is not None else {}
+        self.weighted = values64 is not None
+        self.tile_items = lib.pgb_tile_items()
+        self.n_tiles = (self.n + self.nnz + self.tile_items - 1) // self.tile_items
+        self.tile_row = torch.empty(self.n_tiles + 1, dtype=torch.int32, device=indptr.device)
+        C.check(lib.pgb_mergepath_partition(self.n, self.nnz, C.ptr(indptr), self.n_tiles, C.ptr(self.tile_row),
+                                            C.stream_ptr()))
+        self._ws = None
+
+    def values(self, dtype: torch.dtype) -> Optional[torch.Tensor]:
+        if not self.weighted:
+            return None
+        if dtype not in self._values:
+            self._values[dtype] = self._values[torch.float64].to(dtype)
+        return self._values[dtype]
+
+    def cstruct(self, dtype: torch.dtype) -> C.Csr:
+        return C.Csr(self.n, self.nnz, C.ptr(self.indptr), C.ptr(self.indices), C.ptr(self.values(dtype)),
+                     C.ptr(self.tile_row), self.n_tiles, self.tile_items)
+
+    def new_span_ws(self):
+        """Zeroed cross-tile workspace (one per concurrently running filter)."""
+        dev = self.indptr.device
+        acc = torch.zeros(max(self.n_tiles, 1), dtype=torch.float64, device=dev)
+        cnt = torch.zeros(max(self.n_tiles, 1), dtype=torch.int32, device=dev)
+        return (acc, cnt)
+
+    def span_ws(self):
+        if self._ws is None:
+            self._ws = self.new_span_ws()
+        return self._ws
+
+    def with_values(self, values64: torch.Tensor) -> "CsrView":
+        other = object.__new__(CsrView)
+        other.__dict__.update(self.__dict__)
+        other._values = {torch.float64: values64}
+        other.weighted = True
+        other._ws = None
+        return other
+
+
+def span_struct(ws) -> C.SpanWs:
+    return C.SpanWs(C.ptr(ws[0]), C.ptr(ws[1]))
+
+
+class IdentityNodeMap:
+    """Lazy node -> index mapping for graphs whose nodes are 0..n-1 (replaces the n-entry dict
+    of preprocessing.py:151, impractical at 10^8 nodes)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __getitem__(self, k):
+        k = int(k)
+        if not 0 <= k < self.n:
+            raise KeyError(k)
+        return k
+
+    def __iter__(self):
+        return iter(range(self.n))
+
+    def __len__(self):
+        return self.n
+
+    def __contains__(self, k):
+        try:
+            return 0 <= int(k) < self.n
+        except (TypeError, ValueError):
+            return False
+
+    def get(self, k, default=None):
+        return int(k) if k in self else default
+
+    def keys(self):
+        return range(self.n)
+
+    def items(self):
+        return ((i, i) for i in range(self.n))
+
+
+_SCALE_KINDS = {
+    "none": (C.SCALE_ONE, C.SCALE_ONE),
+    "col": (C.SCALE_RECIP, C.SCALE_ONE),           # preprocessing.py:109-113
+    "symmetric": (C.SCALE_RSQRT, C.SCALE_RSQRT),   # :131-138
+    "laplacian": (C.SCALE_RSQRT, C.SCALE_RSQRT),   # :114-122 (I - symmetric)
+    "both": (C.SCALE_RECIP, C.SCALE_RECIP),        # :123-130
+}
+
+
+class DeviceGraph:
+    """A normalised propagation operator resident in HBM (the backend's graph object).
+
+    Plays the role of ``Adjacency`` wrapping a backend matrix (preprocessing.py:9-28,145-151):
+    exposes ``.array`` (itself), ``.shape``, ``_pygrank_node2id`` and the
+    ``__pygrank_preprocessed`` cache entry so a second trip through ``pg.preprocessor`` short-cuts.
+    """
+
+    def __init__(self):
+        self.n = 0
+        self.shape = (0, 0)
+        self.array = self
+        self.directed = False
+        self.normalization = "none"
+        self.symmetric_structure = False
+        self.perm = None      # internal -> user
+        self.iperm = None     # user -> internal
+        self.out_view: CsrView = None   # rows of A (sources), internal labels
+        self.in_view: CsrView = None    # pull structure (rows = destinations)
+        self.rowsum = self.colsum = None
+        self.L = self.R = None          # fp64, zeros kept (S[S != 0] = 1/S)
+        self.pathological = False
+        self._cache = {}
+        self._pygrank_node2id = None
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def from_edges(n: int, src: torch.Tensor, dst: torch.Tensor, weights: Optional[torch.Tensor] = None,
+                   directed: bool = False, symmetrize: Optional[bool] = None, drop_self_loops: bool = False,
+                   binary: bool = False, normalization: str = "auto", renormalize=False,
+                   relabel: str = "degree", node2id=None) -> "DeviceGraph":
+        """Edge list (device int32 tensors) -> normalised operator.  ``symmetrize`` defaults to
+        ``not directed`` (an undirected edge list names every edge once)."""
+        lib = C.lib()
+        dev = src.device
+        g = DeviceGraph()
+        g.n, g.shape, g.directed = int(n), (int(n), int(n)), bool(directed)
+        symmetrize = (not directed) if symmetrize is None else symmetrize
+        flags = (C.BUILD_SYMMETRIZE if symmetrize else 0) | (C.BUILD_DROP_SELF_LOOPS if drop_self_loops else 0) | \
+                (C.BUILD_BINARY if binary else 0)
+        row = src.to(torch.int32).contiguous()
+        col = dst.to(torch.int32).contiguous()
+        val = None if (weights is None or binary) else weights.to(torch.float64).contiguous()
+        renormalize = float(renormalize)
+        indptr, indices, values = build_csr(n, row, col, val, flags)
+        del row, col, val
+        if renormalize != 0:                                  # preprocessing.py:107-108: M + I*renormalize
+            rows = torch.empty(indices.numel(), dtype=torch.int32, device=dev)
+            C.check(lib.pgb_csr_expand_rows(n, indices.numel(), C.ptr(indptr), C.ptr(rows), C.stream_ptr()))
+            diag = torch.arange(n, dtype=torch.int32, device=dev)
+            vals = torch.ones(indices.numel(), dtype=torch.float64, device=dev) if values is None else values
+            indptr, indices, values = build_csr(
+                n, torch.cat([rows, diag]), torch.cat([indices, diag]),
+                torch.cat([vals, torch.full((n,), renormalize, dtype=torch.float64, device=dev)]), 0)
+            del rows, diag, vals
+        if values is not None and bool((values == 1.0).all()):
+            values = None                                     # unweighted: stream no edge values
+        g._finish(indptr, indices, values, known_symmetric=bool(symmetrize), normalization=normalization,
+                  relabel=relabel)
+        g._pygrank_node2id = node2id if node2id is not None else IdentityNodeMap(n)
+        return g
+
+    @staticmethod
+    def from_scipy(A, directed: bool = False, normalization: str = "auto", renormalize=False,
+                   relabel: str = "degree", device=None, node2id=None) -> "DeviceGraph":
+        """A host scipy adjacency (what ``pg.AdjacencyWrapper`` carries, wrapgraph.py:4-22)."""
+        import scipy.sparse as sp
+        lib = C.lib()
+        dev = _dev(device)
+        A = sp.csr_matrix(A)
+        n = A.shape[0]
+        if A.nnz >= 2 ** 31:
+            raise Exception("graphs with nnz >= 2^31 must be row-partitioned (pygrank_b200.dist)")
+        indptr = torch.from_numpy(np.ascontiguousarray(A.indptr, dtype=np.int32)).to(dev)
+        col = torch.from_numpy(np.ascontiguousarray(A.indices, dtype=np.int32)).to(dev)
+        data = np.ascontiguousarray(A.data, dtype=np.float64)
+        val = None if bool(np.all(data == 1.0)) else torch.from_numpy(data).to(dev)
+        row = torch.empty(A.nnz, dtype=torch.int32, device=dev)
+        C.check(lib.pgb_csr_expand_rows(n, A.nnz, C.ptr(indptr), C.ptr(row), C.stream_ptr()))
+        g = DeviceGraph.from_edges(n, row, col, val, directed=directed, symmetrize=False,
+                                   normalization=normalization, renormalize=renormalize, relabel=relabel,
+                                   node2id=node2id)
+        return g
+
+    def _finish(self, indptr, indices, values, known_symmetric: bool, normalization, relabel: str):
+        lib = C.lib()
+        n, dev = self.n, indptr.device
+        st = C.stream_ptr()
+        nnz = int(indices.numel())
+        if isinstance(normalization, str):
+            normalization = normalization.lower()
+        if normalization == "auto":                           # preprocessing.py:101-102
+            normalization = "col" if self.directed else "symmetric"
+        if normalization not in _SCALE_KINDS:
+            raise Exception("Supported normalizations: none, col, symmetric, both, laplacian, auto")
+        self.normalization = normalization
+        if relabel not in ("degree", "none"):
+            raise Exception("relabel must be 'degree' or 'none'")
+        rows = None
+        if relabel == "degree" and n > 1 and nnz > 0:
+            wsb = lib.pgb_degree_order_workspace_bytes(n)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            self.perm = torch.empty(n, dtype=torch.int32, device=dev)
+            self.iperm = torch.empty(n, dtype=torch.int32, device=dev)
+            C.check(lib.pgb_degree_order(n, C.ptr(indptr), C.ptr(ws), wsb, C.ptr(self.perm), C.ptr(self.iperm), st))
+            del ws
+            rows = torch.empty(nnz, dtype=torch.int32, device=dev)
+            C.check(lib.pgb_csr_expand_rows(n, nnz, C.ptr(indptr), C.ptr(rows), st))
+            cols = indices.clone()
+            C.check(lib.pgb_relabel_coo(nnz, C.ptr(self.iperm), C.ptr(rows), C.ptr(cols), st))
+            indptr, indices, values = build_csr(n, rows, cols, values, 0)
+            del cols
+            rows = None
+        self.out_view = CsrView(n, indptr, indices, values)
+        if known_symmetric:
+            self.in_view = self.out_view
+        else:
+            rows = torch.empty(nnz, dtype=torch.int32, device=dev)
+            C.check(lib.pgb_csr_expand_rows(n, nnz, C.ptr(indptr), C.ptr(rows), st))
+            t_indptr, t_indices, t_values = build_csr(n, indices, rows, values, 0)
+            del rows
+            same = (torch.equal(t_indptr, indptr) and torch.equal(t_indices, indices) and
+                    (values is None or torch.equal(t_values, values)))
+            self.in_view = self.out_view if same else CsrView(n, t_indptr, t_indices, t_values)
+        self.symmetric_structure = self.in_view is self.out_view
+        # degrees and scales (preprocessing.py:104-138), fp64, reference rounding
+        self.rowsum = torch.empty(n, dtype=torch.float64, device=dev)
+        C.check(lib.pgb_csr_row_sums(n, C.ptr(self.out_view.indptr), C.ptr(self.out_view.values(torch.float64)),
+                                     C.ptr(self.rowsum), st))
+        if self.symmetric_structure:
+            self.colsum = self.rowsum
+        else:
+            self.colsum = torch.empty(n, dtype=torch.float64, device=dev)
+            C.check(lib.pgb_csr_row_sums(n, C.ptr(self.in_view.indptr), C.ptr(self.in_view.values(torch.float64)),
+                                         C.ptr(self.colsum), st))
+        lk, rk = _SCALE_KINDS[normalization]
+        self.L = torch.empty(n, dtype=torch.float64, device=dev)
+        C.check(lib.pgb_make_scales(n, C.ptr(self.rowsum), lk, C.ptr(self.L), st))
+        if rk == lk and self.symmetric_structure:
+            self.R = self.L
+        else:
+            self.R = torch.empty(n, dtype=torch.float64, device=dev)
+            C.check(lib.pgb_make_scales(n, C.ptr(self.colsum), rk, C.ptr(self.R), st))
+        # a row whose weights cancel to a zero sum keeps entries the reference multiplies by 0;
+        # the scaled-domain engine cannot represent that (plain conv can)
+        out_deg = self.out_view.indptr[1:] - self.out_view.indptr[:-1]
+        self.pathological = bool(((self.L == 0) & (out_deg > 0)).any()) if self.out_view.weighted else False
+        self.__dict__["__pygrank_preprocessed"] = {"b200": self}
+
+    # ------------------------------------------------------------------ derived vectors
+    @property
+    def nnz(self) -> int:
+        return self.out_view.nnz
+
+    @property
+    def symdeg(self) -> bool:
+        """Scales derivable from the row pointers inside the kernel (no per-node scale streams)."""
+        return (self.symmetric_structure and not self.in_view.weighted and self.normalization == "symmetric")
+
+    def vec(self, name: str, dtype: torch.dtype) -> torch.Tensor:
+        """Cached per-dtype node vectors in internal order:
+        L, R (true scales), Lp (L with 0 -> 1), w = Lp*R, sq = 1/Lp, degM = rowsum(M), c = sq*degM."""
+        key = (name, dtype)
+        if key in self._cache:
+            return self._cache[key]
+        f64 = torch.float64
+        if dtype != f64:
+            out = self.vec(name, f64).to(dtype)
+        elif name == "L":
+            out = self.L
+        elif name == "R":
+            out = self.R
+        elif name == "Lp":
+            out = torch.where(self.L == 0, torch.ones_like(self.L), self.L)
+        elif name == "w":
+            out = self.vec("Lp", f64) * self.R
+        elif name == "sq":
+            out = 1.0 / self.vec("Lp", f64)
+        elif name == "degM":
+            out = self._spmv_raw(self.out_view, self.R, self.L, f64)
+        elif name == "c":
+            out = self.vec("sq", f64) * self.vec("degM", f64)
+        else:
+            raise KeyError(name)
+        self._cache[key] = out
+        return out
+
+    def _spmv_raw(self, view: CsrView, z: torch.Tensor, rscale: Optional[torch.Tensor], dtype, out_perm=None,
+                  out=None) -> torch.Tensor:
+        lib = C.lib()
+        if out is None:
+            out = torch.empty(self.n, dtype=dtype, device=z.device)
+        cs = view.cstruct(dtype)
+        C.check(lib.pgb_spmv(ctypes.byref(cs), dtype_code(dtype), C.ptr(z), C.ptr(rscale), None, C.ptr(out_perm),
+                             C.ptr(out), span_struct(view.span_ws()), C.stream_ptr()))
+        return out
+
+    # ------------------------------------------------------------------ backend operations
+    def conv(self, x: torch.Tensor) -> torch.Tensor:
+        """``x @ M`` (numpy.py:64-65) for a user-order vector; one pre-scale pass + one gather kernel."""
+        lib = C.lib()
+        dtype = x.dtype
+        code = dtype_code(dtype)
+        x = x.contiguous()
+        if x.numel() != self.n:
+            raise Exception(f"conv: vector of length {x.numel()} on a graph with {self.n} nodes")
+        z = torch.empty(self.n, dtype=dtype, device=x.device)
+        C.check(lib.pgb_scale(self.n, code, C.ptr(x), C.ptr(self.vec("L", dtype)), 1.0, C.ptr(self.perm), C.ptr(z),
+                              C.stream_ptr()))
+        rscale = None if self.normalization in ("none", "col") else self.vec("R", dtype)
+        y = self._spmv_raw(self.in_view, z, rscale, dtype, out_perm=self.perm)
+        if self.normalization == "laplacian":                 # preprocessing.py:122: -M + I
+            y = x - y
+        return y
+
+    def degrees(self, dtype=torch.float64) -> torch.Tensor:
+        """``degrees(M)`` (numpy.py:76-77): row sums of the NORMALISED matrix, user order, summed in
+        numpy's pairwise order over the stored row (bit-exact when relabel='none')."""
+        lib = C.lib()
+        st = C.stream_ptr()
+        v = self.out_view
+        dev = v.indptr.device
+        data = torch.empty(max(v.nnz, 1), dtype=torch.float64, device=dev)
+        C.check(lib.pgb_csr_normalized_values(self.n, C.ptr(v.indptr), C.ptr(v.indices), C.ptr(v.values(torch.float64)),
+                                              C.ptr(self.L), C.ptr(self.R), C.ptr(data), st))
+        if self.normalization == "laplacian":
+            raise Exception("degrees() of a laplacian operator is not provided by the device preprocessor")
+        sums = torch.empty(self.n, dtype=torch.float64, device=dev)
+        C.check(lib.pgb_csr_row_sums_numpy(self.n, C.ptr(v.indptr), C.ptr(data), int(self.normalization == "col"),
+                                           C.ptr(sums), st))
+        if self.perm is not None:
+            out = torch.empty_like(sums)
+            out[self.perm.long()] = sums
+            sums = out
+        return sums.to(dtype)
+
+    def graph_degrees(self):
+        """(rowsum, colsum) of the un-normalised adjacency in user order (fp64; exact integers for
+        unweighted graphs) — what preprocessing.py:104-105 reduces."""
+        if self.perm is None:
+            return self.rowsum, self.colsum
+        p = self.iperm.long()
+        return self.rowsum[p], self.colsum[p]
+
+    def dropout(self, p: float) -> "DeviceGraph":
+        """``graph_dropout`` with the torch backends' semantics (pytorch.py:34-38): every stored
+        entry is zeroed with probability p and survivors are rescaled by 1/(1-p); a fresh mask per call."""
+        p = float(p)
+        if p == 0:
+            return self
+        if not self.symmetric_structure:
+            raise Exception("graph_dropout on directed device graphs is not implemented yet")
+        g = object.__new__(DeviceGraph)
+        g.__dict__.update(self.__dict__)
+        g._cache = {}
+        view = self.in_view
+        base = view.values(torch.float64)
+        keep = (torch.rand(view.nnz, device=view.indptr.device) >= p).to(torch.float64) / (1.0 - p)
+        g.in_view = g.out_view = view.with_values(keep if base is None else base * keep)
+        g.array = g
+        return g
+
+    def to_scipy_normalized(self):
+        """Normalised matrix as canonical host scipy CSR in USER labels (parity checks; not hot)."""
+        import scipy.sparse as sp
+        lib = C.lib()
+        v = self.out_view
+        data = torch.empty(max(v.nnz, 1), dtype=torch.float64, device=v.indptr.device)
+        C.check(lib.pgb_csr_normalized_values(self.n, C.ptr(v.indptr), C.ptr(v.indices), C.ptr(v.values(torch.float64)),
+                                              C.ptr(self.L), C.ptr(self.R), C.ptr(data), C.stream_ptr()))
+        indptr = v.indptr.cpu().numpy()
+        indices = v.indices.cpu().numpy()
+        data = data[:v.nnz].cpu().numpy()
+        rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(indptr))
+        cols = indices.astype(np.int64)
+        if self.perm is not None:
+            perm = self.perm.cpu().numpy().astype(np.int64)
+            rows, cols = perm[rows], perm[cols]
+        order = np.lexsort((cols, rows))
+        rows, cols, data = rows[order], cols[order], data[order]
+        out_indptr = np.zeros(self.n + 1, dtype=np.int32)
+        np.cumsum(np.bincount(rows, minlength=self.n), out=out_indptr[1:])
+        M = sp.csr_matrix((data, cols.astype(np.int32), out_indptr), shape=self.shape)
+        if self.normalization == "laplacian":
+            M = (-M + sp.eye(self.n, format="csr")).tocsr()
+            M.sort_indices()
+        return M
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return iter(range(self.n))
+
+    def is_directed(self):
+        return self.directed
+
+
+def as_device_graph(graph, normalization="auto", renormalize=False, relabel="degree", weight="weight",
+                    device=None) -> DeviceGraph:
+    """Anything the reference's preprocessor accepts -> DeviceGraph (preprocessing.py:88-103)."""
+    if isinstance(graph, DeviceGraph):
+        return graph
+    if hasattr(graph, "array") and isinstance(getattr(graph, "array"), DeviceGraph):
+        return graph.array
+    import scipy.sparse as sp
+    if sp.issparse(graph):
+        return DeviceGraph.from_scipy(graph, directed=False, normalization=normalization, renormalize=renormalize,
+                                      relabel=relabel, device=device)
+    if hasattr(graph, "to_scipy_sparse_array"):               # fastgraph.Graph / AdjacencyWrapper
+        return DeviceGraph.from_scipy(graph.to_scipy_sparse_array(), directed=bool(graph.is_directed()),
+                                      normalization=normalization, renormalize=renormalize, relabel=relabel,
+                                      device=device, node2id={v: i for i, v in enumerate(graph)}
+                                      if not _is_range_nodes(graph) else None)
+    try:
+        import networkx as nx
+    except ImportError:  # pragma: no cover
+        nx = None
+    if nx is not None and isinstance(graph, nx.Graph):
+        A = nx.to_scipy_sparse_array(graph, weight=weight, dtype=float)   # preprocessing.py:103
+        return DeviceGraph.from_scipy(A, directed=graph.is_directed(), normalization=normalization,
+                                      renormalize=renormalize, relabel=relabel, device=device,
+                                      node2id={v: i for i, v in enumerate(graph)})
+    raise Exception("cannot build a device graph from " + str(type(graph)))
+
+
+def _is_range_nodes(graph) -> bool:
+    it = iter(graph)
+    return isinstance(it, type(iter(range(0))))
+
+
+def preprocessor(normalization: str = "auto", assume_immutability: bool = False, weight: str = "weight",
+                 renormalize=False, relabel: str = "degree", device=None):
+    """Device twin of ``pg.preprocessor`` (preprocessing.py:233-287): returns a callable named
+    ``preprocess`` (so ``filter + preprocess`` works, abstract_filters.py:91-92) mapping a graph
+    to a :class:`DeviceGraph`; ``assume_immutability`` memoises per input object like MethodHasher."""
+    memo = {}
+
+    def preprocess(G):
+        if isinstance(G, DeviceGraph):
+            return G
+        key = id(G)
+        if assume_immutability and key in memo and memo[key][0] is G:
+            return memo[key][1]
+        out = as_device_graph(G, normalization=normalization, renormalize=renormalize, relabel=relabel,
+                              weight=weight, device=device)
+        if assume_immutability:
+            memo[key] = (G, out)
+        return out
+
+    return preprocess

@@ -1,0 +1,132 @@
+"""Drop-in: the UNMODIFIED reference (baseline/_ref) runs its own filters on the b200 backend.
+
+These read like the reference's tests (tests/test_core.py, tests/test_filters.py): a
+``supported_backends()`` loop over ["numpy", "b200"], relations between algorithms, and direct
+parity of pg.PageRank(...) outputs between the two backends on the same synthetic graph.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l1
+from refutil import import_pygrank
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pg():
+    mod = import_pygrank()
+    if mod is None:
+        pytest.skip("baseline/_ref (the unmodified reference) is not installed on this box")
+    import pygrank_b200
+    pygrank_b200.install(mod)
+    yield mod
+    mod.load_backend("numpy")
+
+
+def supported_backends(pg):
+    for backend in ["numpy", "b200"]:
+        pg.load_backend(backend)
+        yield backend
+    pg.load_backend("numpy")
+
+
+def test_backend_load_and_with(pg):
+    pg.load_backend("b200")
+    assert pg.backend_name() == "b200"
+    pg.load_backend("numpy")
+    assert pg.backend_name() == "numpy"
+    with pytest.raises(Exception):
+        pg.load_backend("unknown")
+    with pg.Backend("b200") as backend:
+        assert pg.backend_name() == "b200" and backend.backend_name() == "b200"
+    assert pg.backend_name() == "numpy"
+
+
+def test_primitive_conversion(pg):
+    for _ in supported_backends(pg):
+        assert pg.sum(pg.to_array([1, 2, 3])) == 6
+        assert pg.sum(pg.dot(pg.exp(pg.log(pg.to_array([4, 5]))), pg.to_array([2, 2]))) == pytest.approx(18)
+        primitive = pg.to_array([1, 2, 3])
+        assert id(primitive) == id(pg.to_array(primitive, copy_array=False))
+        assert id(primitive) != id(pg.to_array(primitive, copy_array=True))
+        table = pg.to_primitive([[1, 2, 3], [4, 5, 6]])
+        cols = pg.separate_cols(table)
+        assert len(cols) == 3 and all(pg.length(c) == 2 for c in cols)
+        assert pg.sum(pg.abs(table - pg.combine_cols(cols))) == 0
+
+
+def test_signal_direct_operations(pg):
+    import networkx as nx
+    for _ in supported_backends(pg):
+        graph = nx.DiGraph([(1, 2), (2, 3)])
+        signal = pg.to_signal(graph, [1., 2., 3.])
+        assert pg.sum(signal) == 6
+        assert pg.sum(signal + 1) == 9
+        assert pg.sum(signal ** 2) == 14
+        assert pg.sum(signal / pg.to_signal(graph, [1., 2., 3.])) == 3
+        signal *= 4
+        assert pg.sum(signal) == 24
+        assert signal[2] == 8.0
+        del signal[2]
+        assert signal[2] == 0
+
+
+@pytest.mark.parametrize("name", ["ba2000", "rmat10", "gnp600d", "weighted300"])
+def test_reference_filters_unchanged_on_b200(pg, name):
+    z, A, directed = load_golden(name)
+    P = z["P"]
+    runs = {
+        "ppr85": lambda pre: pg.PageRank(0.85, tol=1e-9, preprocessor=pre, max_iters=1000),
+        "ppr90_noq": lambda pre: pg.PageRank(0.9, tol=1e-9, use_quotient=False, preprocessor=pre, max_iters=1000),
+        "heat3_tol9": lambda pre: pg.HeatKernel(3, tol=1e-9, preprocessor=pre),
+        "gen40": lambda pre: pg.GenericGraphFilter([0.9 ** k for k in range(40)], error_type="iters", max_iters=41,
+                                                   preprocessor=pre),
+        "absorb85": lambda pre: pg.AbsorbingWalks(0.85, tol=1e-9, preprocessor=pre, max_iters=1000),
+    }
+    with pg.Backend("b200"):
+        graph = pg.AdjacencyWrapper(A, directed=directed)
+        pre = pg.preprocessor(normalization="auto", assume_immutability=True)   # the reference's own preprocessor
+        M = pre(graph)
+        assert M.array.__class__.__name__ == "DeviceGraph"
+        for rname, make in runs.items():
+            for c in (0, 3):
+                alg = make(pre)
+                r = alg(pg.to_signal(M, P[:, c].copy()))
+                assert alg.convergence.iteration == int(z[f"run_{rname}_iters"][c]), (name, rname, c)
+                got = r.np.cpu().numpy()
+                assert rel_l1(got, z[f"run_{rname}_scores"][:, c]) <= 1e-10, (name, rname, c)
+
+
+def test_device_preprocessor_injected_into_reference_filter(pg):
+    """`pg.PageRank(preprocessor=pygrank_b200.preprocessor(...))`: CSR built and normalised on the device."""
+    import pygrank_b200
+    z, A, directed = load_golden("ba2000")
+    P = z["P"]
+    with pg.Backend("b200"):
+        pre = pygrank_b200.preprocessor(normalization="symmetric", assume_immutability=True)
+        graph = pg.AdjacencyWrapper(A, directed=False)
+        alg = pg.PageRank(0.85, tol=1e-9, preprocessor=pre, max_iters=1000)
+        r = alg(pg.to_signal(pre(graph), P[:, 0].copy()))
+        assert alg.convergence.iteration == int(z["run_ppr85_sym_iters"][0])
+        assert rel_l1(r.np.cpu().numpy(), z["run_ppr85_sym_scores"][:, 0]) <= 1e-10
+        # AbsorbingWalks == PageRank under col normalisation (reference tests/test_filters.py:151-157)
+        pre_col = pygrank_b200.preprocessor(normalization="col", assume_immutability=True)
+        a = pg.AbsorbingWalks(0.85, tol=1e-12, preprocessor=pre_col, max_iters=1000)(pg.to_signal(pre_col(graph), P[:, 0].copy()))
+        b = pg.PageRank(0.85, tol=1e-12, preprocessor=pre_col, max_iters=1000)(pg.to_signal(pre_col(graph), P[:, 0].copy()))
+        assert float(pg.sum(pg.abs(a.np - b.np))) < 1e-9
+
+
+def test_graph_dropout_semantics(pg):
+    import torch
+    z, A, directed = load_golden("ba2000")
+    with pg.Backend("b200") as backend:
+        M = backend.scipy_sparse_to_backend(A)
+        assert backend.graph_dropout(M, 0) is M
+        x = backend.to_array(np.ones(A.shape[0]))
+        full = backend.conv(x, M)
+        torch.manual_seed(0)
+        dropped = backend.conv(x, backend.graph_dropout(M, 0.5))
+        # survivors rescaled by 1/(1-p): the expectation is preserved
+        assert abs(float(dropped.sum()) / float(full.sum()) - 1.0) < 0.05
+        assert float((dropped - full).abs().sum()) > 0
