@@ -194,26 +194,56 @@ __global__ void normalized_values_kernel(int64_t n, const int32_t *__restrict__ 
 // numpy's pairwise summation (the add.reduce inner loop np.add.reduceat runs per segment):
 // n < 8 sequential; n <= 128 eight interleaved accumulators combined as a fixed tree plus a
 // sequential tail; else split at (n/2 rounded down to a multiple of 8) and recurse.
-__device__ double numpy_pairwise(const double *a, int64_t n, int64_t stride) {
+__device__ __forceinline__ double numpy_pairwise_block(const double *a, int64_t n, int64_t stride) {
     if (n < 8) {
-        // numpy seeds the reduction with the first element, then adds the rest left to right
         double res = 0.0;
         for (int64_t i = 0; i < n; ++i) res += a[i * stride];
         return res;
-    } else if (n <= 128) {
-        double r[8];
-        for (int j = 0; j < 8; ++j) r[j] = a[j * stride];
-        int64_t i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] += a[(i + j) * stride];
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += a[i * stride];
-        return res;
-    } else {
-        int64_t n2 = n / 2;
-        n2 -= n2 % 8;
-        return numpy_pairwise(a, n2, stride) + numpy_pairwise(a + n2 * stride, n - n2, stride);
     }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j * stride];
+    int64_t i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += a[(i + j) * stride];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i * stride];
+    return res;
+}
+
+// The recursion sum(a, n) = sum(a, n2) + sum(a + n2, n - n2) (n > 128) is evaluated with an explicit
+// post-order stack (depth <= 40 covers any int64 length) — device recursion would overflow the
+// default 1 KB thread stack on hub rows.
+__device__ double numpy_pairwise(const double *a, int64_t n, int64_t stride) {
+    if (n <= 128) return numpy_pairwise_block(a, n, stride);
+    int64_t off[40], len[40];
+    double left[40];
+    int stage[40];
+    int sp = 0;
+    off[0] = 0; len[0] = n; stage[0] = 0; left[0] = 0.0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        if (len[sp] <= 128) {
+            ret = numpy_pairwise_block(a + off[sp] * stride, len[sp], stride);
+            --sp;
+            continue;
+        }
+        int64_t n2 = len[sp] / 2;
+        n2 -= n2 % 8;
+        if (stage[sp] == 0) {          // descend into the left half
+            stage[sp] = 1;
+            off[sp + 1] = off[sp]; len[sp + 1] = n2; stage[sp + 1] = 0;
+            ++sp;
+        } else if (stage[sp] == 1) {   // left half done -> descend into the right half
+            left[sp] = ret;
+            stage[sp] = 2;
+            off[sp + 1] = off[sp] + n2; len[sp + 1] = len[sp] - n2; stage[sp + 1] = 0;
+            ++sp;
+        } else {                       // both halves done
+            ret = left[sp] + ret;
+            --sp;
+        }
+    }
+    return ret;
 }
 
 __global__ void row_sums_numpy_kernel(int64_t n, const int32_t *__restrict__ indptr, const double *__restrict__ data,
