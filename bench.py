@@ -251,6 +251,17 @@ def run_single(args):
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / reps
+    # gather ceiling of this graph: index stream + gathers only (pgb_gather_probe)
+    scratch = torch.zeros(8, dtype=dtype, device=dev)
+    for _ in range(3):
+        C.check(lib.pgb_gather_probe(ctypes.byref(cs), code, C.ptr(zbuf[0]), C.ptr(scratch), st))
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(10):
+        C.check(lib.pgb_gather_probe(ctypes.byref(cs), code, C.ptr(zbuf[0]), C.ptr(scratch), st))
+    p1.record()
+    torch.cuda.synchronize()
+    probe_ms = p0.elapsed_time(p1) / 10
     alg_bytes = nnz * 4 + (n + 1) * 4 + 5 * n * w
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
@@ -270,9 +281,11 @@ def run_single(args):
                 "d2h_bytes_per_step": n * w + 64 * 2},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "tile_kernel<%s,unweighted,AFFINE,SYMDEG=%s>" % (args.dtype, symdeg),
+                     "traffic": None, "kernel": "warp_tile_kernel<%s,unweighted,AFFINE,SYMDEG=%s>" % (args.dtype, symdeg),
                      "kernel_ms": kernel_ms, "kernel_gteps": nnz / (kernel_ms * 1e-3) / 1e9,
-                     "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+                     "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                     "gather_probe_ms": probe_ms, "gather_probe_gteps": nnz / (probe_ms * 1e-3) / 1e9,
+                     "frac_of_gather_probe": probe_ms / kernel_ms},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

@@ -72,6 +72,8 @@ typedef struct pgb_csr {
     const int32_t *tile_row; /* [n_tiles+1]                               */
     int32_t n_tiles;
     int32_t tile_items;      /* must equal pgb_tile_items()               */
+    const int32_t *istream;  /* [n+nnz] item stream: each row's indices then -1-deg (pgb_build_item_stream) */
+    const void *vstream;     /* [n+nnz] weights at the same positions (dtype) or NULL                      */
 } pgb_csr;
 
 /* Cross-tile workspace of one running filter: rows that straddle merge-path tiles are
@@ -111,6 +113,16 @@ int pgb_abi_version(void);
 const char *pgb_last_error(void);
 int pgb_tile_items(void);       /* merge-path items (rows + entries) per tile            */
 int pgb_device_sm_count(int device);
+/* Item-space stream of a CSR (what the fused kernels actually read): for every row its column
+ * indices followed by one terminator -1-deg; vstream (optional) carries the weights. */
+int pgb_build_item_stream(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, int dtype,
+                          const void *values, int32_t *istream, void *vstream, void *stream);
+/* Roofline probe: streams the graph's index array and gathers z[indices[k]] exactly like the fused
+ * kernel's phase 2, and nothing else — the measured ceiling of any row-gather formulation for this
+ * graph (bench.py reports the fused kernel against it).  scratch: >= 8 bytes. */
+int pgb_gather_probe(const pgb_csr *g, int dtype, const void *z, void *scratch, void *stream);
+/* 3 (default): warp tiles over the item stream; 2: warp tiles over CSR; 1: CTA-wide tiles (A/B timing). */
+int pgb_set_kernel_variant(int variant);
 
 /* ---- synthetic graphs (bench/tests; no reference counterpart, graphs are downloaded in
  *      /root/reference/pygrank/benchmarks/download.py:62-72) ------------------------------ */

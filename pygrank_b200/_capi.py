@@ -27,7 +27,8 @@ STATE_LEN = 16
 
 class Csr(Structure):
     _fields_ = [("n", c_int64), ("nnz", c_int64), ("indptr", c_void_p), ("indices", c_void_p), ("values", c_void_p),
-                ("tile_row", c_void_p), ("n_tiles", c_int32), ("tile_items", c_int32)]
+                ("tile_row", c_void_p), ("n_tiles", c_int32), ("tile_items", c_int32), ("istream", c_void_p),
+                ("vstream", c_void_p)]
 
 
 class SpanWs(Structure):
@@ -39,6 +40,10 @@ _SIGNATURES = {
     "pgb_last_error": (c_char_p, []),
     "pgb_tile_items": (c_int, []),
     "pgb_device_sm_count": (c_int, [c_int]),
+    "pgb_set_kernel_variant": (c_int, [c_int]),
+    "pgb_build_item_stream": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
+    "pgb_gather_probe": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p]),
     "pgb_rmat_edges": (c_int, [c_int, c_int64, c_int64, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p,
                                c_void_p]),
     "pgb_ba_edges": (c_int, [c_int64, c_int, c_int64, c_int64, c_uint64, c_void_p, c_void_p, c_void_p]),
@@ -100,13 +105,17 @@ def lib() -> ctypes.CDLL:
         if not os.path.exists(LIB_PATH):
             raise Exception(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(pygrank_b200 has no CPU fallback)")
-        handle = ctypes.CDLL(LIB_PATH)
+        handle = ctypes.CDLL(os.environ.get("PGB_LIB", LIB_PATH))   # PGB_LIB: A/B builds of the same ABI
         for name, (restype, argtypes) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype = restype
             fn.argtypes = argtypes
         if handle.pgb_abi_version() != 1:
             raise Exception("libpgb200.so ABI version mismatch")
+        variant = os.environ.get("PGB_KERNEL_VARIANT")
+        if variant:   # A/B timing aid: 1 = CTA-wide tiles, 2 = warp tiles (default)
+            if handle.pgb_set_kernel_variant(int(variant)) != 0:
+                raise Exception("pgb200: " + handle.pgb_last_error().decode())
         _lib = handle
     return _lib
 

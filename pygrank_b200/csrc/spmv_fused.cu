@@ -19,13 +19,18 @@
 // tile that reaches them (fp64 atomic partial + ticket per completing tile; no spinning, no
 // ordering assumption).  Grid-level sums (error numerator, next normaliser) are one fp64 atomic
 // per CTA; the last CTA to finish plays ConvergenceManager on the device.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pgb {
 
 constexpr int BLOCK = 256;
 constexpr int IPT = 9;  // odd: thread-blocked reads of shared memory hit distinct banks
-constexpr int TILE_ITEMS = BLOCK * IPT;
+constexpr int TILE_ITEMS = BLOCK * IPT;   // merge items per tile (v1: one CTA; v2: one warp, 8 sub-tiles)
+constexpr int WARPS = BLOCK / 32;
+constexpr int SUB_ITEMS = 32 * IPT;       // v2: items one warp consumes per pass
+static_assert(TILE_ITEMS % SUB_ITEMS == 0, "a tile is a whole number of warp passes");
 
 enum { MODE_CONV = 0, MODE_AFFINE = 1, MODE_POLY = 2 };
 
@@ -35,6 +40,8 @@ struct StepParams {
     const void *values;
     const int32_t *tile_row;
     int32_t n_tiles;
+    const int32_t *istream;  // item-space index stream: row entries then the terminator -1-deg (v3)
+    const void *vstream;     // item-space weights (weighted graphs), same positions as istream
     const void *zin;
     void *zout;
     int64_t out_offset;  // index of local row 0 inside the (full-length) z vectors
@@ -131,16 +138,17 @@ struct RowUpdate {
             wi = deg > 0 ? RowMath<T>::inv((T)deg) : (T)0;
             sqi = deg > 0 ? RowMath<T>::root((T)deg) : (T)1;
         } else {
-            wi = ((const T *)P.w)[row];
-            sqi = ((const T *)P.sq)[row];
+            wi = ld_stream((const T *)P.w + row);
+            sqi = ld_stream((const T *)P.sq + row);
         }
         const T zi = __ldg((const T *)P.zin + own);
         if (MODE == MODE_AFFINE) {
-            const T znew = (alpha * wi * acc + ((const T *)P.q)[row]) * invS;
+            // row-aligned streams are touched once per launch: evict-first keeps L1/L2 for the gathers
+            const T znew = (alpha * wi * acc + ld_stream((const T *)P.q + row)) * invS;
             ((T *)P.zout)[own] = znew;
             double d = (double)sqi * fabs((double)znew - (double)zi);
             err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
-            tsum += (double)znew * (double)((const T *)P.c)[row];
+            tsum += (double)znew * (double)ld_stream((const T *)P.c + row);
         } else {  // MODE_POLY
             const T pw = sqi * zi;
             if (coef != (T)0) {  // abstract_filters.py:226-228
@@ -155,6 +163,25 @@ struct RowUpdate {
         }
     }
 };
+
+// Cross-tile row completion without a gpu-scope fence.  __threadfence() compiles to
+// MEMBAR.SC.GPU + CCTL.IVALL, and the CCTL invalidates the whole L1 of the SM — issued once or twice
+// per tile by every warp it kept the gather vector out of L1 (6 % hit rate measured).  Both atomics
+// below are performed at L2; the ticket increment is made data-dependent on the RETURN of the partial
+// sum's atomic, so it cannot be issued before that add has been performed, and the last arrival reads
+// the total with another L2 atomic after it has seen every ticket.
+__device__ __forceinline__ bool span_arrive(double *acc, uint32_t *cnt, double partial, uint32_t expected,
+                                            double *total) {
+    const double old = atomicAdd(acc, partial);
+    // never true for finite data; forces the scoreboard wait on `old` before the ticket is issued
+    const uint32_t inc = (__double_as_longlong(old) == 0x7ff8dead00000001ll) ? 2u : 1u;
+    const uint32_t arrived = atomicAdd(cnt, inc);
+    if (arrived != expected - 1) return false;
+    const unsigned long long raw = atomicExch((unsigned long long *)acc, 0ull);
+    atomicExch(cnt, 0u);
+    *total = __longlong_as_double((long long)raw);
+    return true;
+}
 
 template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
 __global__ void __launch_bounds__(BLOCK, 4) tile_kernel(const StepParams P) {
@@ -261,15 +288,9 @@ __global__ void __launch_bounds__(BLOCK, 4) tile_kernel(const StepParams P) {
             const int64_t b = indptr[r], e = indptr[r + 1];
             const int64_t t_a = (b + r) / TILE_ITEMS, t_b = (e + r) / TILE_ITEMS;
             const uint32_t expected = (uint32_t)(t_b - t_a + 1);
-            atomicAdd(&P.span_acc[t_b], partial);
-            __threadfence();
-            const uint32_t arrived = atomicAdd(&P.span_cnt[t_b], 1u);
-            if (arrived == expected - 1) {
-                __threadfence();
-                const unsigned long long bits = atomicExch((unsigned long long *)&P.span_acc[t_b], 0ull);
-                P.span_cnt[t_b] = 0;
-                update(r, (T)__longlong_as_double((long long)bits), (int)(e - b));
-            }
+            double total;
+            if (span_arrive(&P.span_acc[t_b], &P.span_cnt[t_b], partial, expected, &total))
+                update(r, (T)total, (int)(e - b));
         }
         __syncthreads();  // shared memory is reused by the next tile
     }
@@ -293,21 +314,533 @@ __global__ void __launch_bounds__(BLOCK, 4) tile_kernel(const StepParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: warp-autonomous merge tiles.  Each WARP owns a tile (TILE_ITEMS consecutive merge items) and
+// walks it in passes of SUB_ITEMS = 32 x IPT items with __syncwarp only — no block barrier on the
+// hot loop, so the 32 resident warps of an SM are always spread over all phases and the L1 wavefront
+// pipe (the measured limit for scattered 4-byte gathers, ~1 line/clk/SM) stays busy.
+//   1. the row-end markers of the pass become a bitmask over its items (REDUX.OR across lanes);
+//   2. lanes take items STRIPED (item = s*32+lane): non-marker items are consecutive CSR entries ->
+//      coalesced evict-first index loads, IPT independent gathers in flight per lane, values parked
+//      in shared memory in ITEM space (markers hold 0);
+//   3. lanes re-read their IPT consecutive items BLOCKED (conflict-free, IPT odd) and run the merge
+//      from registers: a marker bit closes a row; the open head/tail pieces are stitched with one
+//      5-step segmented warp scan; the piece still open at the end is carried to the next pass;
+//   4. finished rows are updated 32 at a time by consecutive lanes (coalesced row-aligned streams).
+// Shared memory is 2 x SUB_ITEMS values per warp (18 KB per CTA in fp32), leaving most of the 228 KB
+// for L1, which holds the hub end of the degree-ranked gather vector.
+template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
+__global__ void __launch_bounds__(BLOCK, 4) warp_tile_kernel(const StepParams P) {
+    // one buffer per warp: item values (phase 2 -> 3), then reused for the finished-row sums (3 -> 4)
+    __shared__ T s_item[WARPS][SUB_ITEMS + 1];
+    __shared__ unsigned s_mask[WARPS][IPT + 1];  // marker words of the pass (+ a zero guard word)
+    __shared__ int s_pre[WARPS][IPT + 1];        // markers before each word
+    __shared__ double s_red[32];
+
+    if (MODE != MODE_CONV) {
+        if (P.si[PGB_SI_STOP] != PGB_RUNNING) return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_mask[warp][IPT] = 0u;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const T *__restrict__ zin = (const T *)P.zin;
+    const int32_t *__restrict__ indices = P.indices;
+    const int32_t *__restrict__ indptr = P.indptr;
+    const T *__restrict__ values = (const T *)P.values;
+    T *item = s_item[warp];
+    T *rowsum = s_item[warp];
+    RowUpdate<T, MODE, SYMDEG> update(P);
+    const int64_t total_items = P.n + P.nnz;
+
+    for (int32_t tile = blockIdx.x * WARPS + warp; tile < P.n_tiles; tile += gridDim.x * WARPS) {
+        const int64_t item_lo = (int64_t)tile * TILE_ITEMS;
+        const int64_t item_hi = (item_lo + TILE_ITEMS < total_items) ? item_lo + TILE_ITEMS : total_items;
+        const int32_t r_lo = P.tile_row[tile], r_hi = P.tile_row[tile + 1];
+        const int64_t e_lo = item_lo - r_lo, e_hi = item_hi - r_hi;
+        const bool lead_span = (r_hi > r_lo) && ((int64_t)indptr[r_lo] < e_lo);  // first finished row began earlier
+        int64_t r_cur = r_lo;
+        T carry = (T)0;  // sum of the row still open at the end of the previous pass
+
+        for (int64_t I0 = item_lo; I0 < item_hi; I0 += SUB_ITEMS) {
+            const int nitems = (int)((item_hi - I0 < SUB_ITEMS) ? item_hi - I0 : SUB_ITEMS);
+            const int64_t e_cur = I0 - r_cur;  // CSR entry of the first non-marker item
+
+            // ---- 1. marker bitmask of this pass -------------------------------------------------
+            unsigned m[IPT];
+#pragma unroll
+            for (int s = 0; s < IPT; ++s) m[s] = 0u;
+            int nrows = 0;
+            for (int b = 0;; ++b) {
+                const int64_t row = r_cur + b * 32 + lane;
+                int64_t pos = nitems;
+                if (row < P.n) pos = (int64_t)indptr[row + 1] + row - I0;
+                const bool valid = pos < nitems;
+                const int w = valid ? (int)(pos >> 5) : -1;
+                const unsigned bit = valid ? (1u << (pos & 31)) : 0u;
+#pragma unroll
+                for (int s = 0; s < IPT; ++s) m[s] |= __reduce_or_sync(FULL, (w == s) ? bit : 0u);
+                const int cnt = __popc(__ballot_sync(FULL, valid));
+                nrows += cnt;
+                if (cnt < 32) break;
+            }
+
+            // ---- 2. striped: stream indices, gather, park values in item space ------------------
+            {
+                int32_t cols[IPT];
+                int64_t eidx[WEIGHTED ? IPT : 1];
+                int pre = 0;
+#pragma unroll
+                for (int s = 0; s < IPT; ++s) {
+                    const int p = s * 32 + lane;
+                    const bool is_marker = (m[s] >> lane) & 1u;
+                    const int rank = pre + __popc(m[s] & lt_mask);
+                    const int64_t e = e_cur + p - rank;
+                    const bool active = (p < nitems) && !is_marker;
+                    cols[s] = active ? ld_stream(indices + e) : -1;
+                    if (WEIGHTED) eidx[s] = e;
+                    if (lane == s) {  // publish the mask for the blocked phase (dynamic word index there)
+                        s_mask[warp][s] = m[s];
+                        s_pre[warp][s] = pre;
+                    }
+                    pre += __popc(m[s]);
+                }
+                T x[IPT];
+#pragma unroll
+                for (int s = 0; s < IPT; ++s) x[s] = (cols[s] >= 0) ? __ldg(zin + cols[s]) : (T)0;
+                if (WEIGHTED) {
+#pragma unroll
+                    for (int s = 0; s < IPT; ++s)
+                        if (cols[s] >= 0) x[s] *= ld_stream(values + eidx[WEIGHTED ? s : 0]);
+                }
+#pragma unroll
+                for (int s = 0; s < IPT; ++s) item[s * 32 + lane] = x[s];
+            }
+            __syncwarp();
+
+            // ---- 3. blocked: IPT consecutive items per lane, merge from registers ---------------
+            {
+                const int p0 = lane * IPT;
+                const int w0 = p0 >> 5, sh = p0 & 31;
+                const unsigned lo = s_mask[warp][w0], hi = s_mask[warp][w0 + 1];
+                int k = s_pre[warp][w0] + __popc(lo & ((1u << sh) - 1u));  // rows finished before item p0
+                const unsigned bits = __funnelshift_r(lo, hi, sh) & ((1u << IPT) - 1u);
+                T it[IPT];
+#pragma unroll
+                for (int j = 0; j < IPT; ++j) it[j] = item[p0 + j];
+                __syncwarp();  // every lane holds its items in registers: the buffer becomes the row sums
+                T run = (T)0, head = (T)0;
+                int first_k = -1;
+#pragma unroll
+                for (int j = 0; j < IPT; ++j) {
+                    if ((bits >> j) & 1u) {
+                        if (first_k < 0) {
+                            head = run;
+                            first_k = k;
+                        } else {
+                            rowsum[k] = run;  // row lies entirely inside this lane
+                        }
+                        run = (T)0;
+                        ++k;
+                    } else {
+                        run += it[j];
+                    }
+                }
+                // stitch pieces across lanes: segments restart at every lane that closed a row
+                const bool closed = first_k >= 0;
+                const unsigned closed_mask = __ballot_sync(FULL, closed);
+                T seg = run;  // inclusive segmented scan of the open tails
+                bool f = closed;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const T t = __shfl_up_sync(FULL, seg, d);
+                    const bool tf = __shfl_up_sync(FULL, (int)f, d);
+                    if (lane >= d && !f) {
+                        seg += t;
+                        f = tf;
+                    }
+                }
+                T carry_in = __shfl_up_sync(FULL, seg, 1);
+                if (lane == 0) carry_in = (T)0;
+                if ((closed_mask & lt_mask) == 0u) carry_in += carry;  // nothing closed before this lane
+                if (closed) rowsum[first_k] = head + carry_in;
+                const T last = __shfl_sync(FULL, seg, 31);
+                carry = (closed_mask == 0u) ? carry + last : last;
+            }
+            __syncwarp();
+
+            // ---- 4. fused update of the rows finished in this pass ------------------------------
+            for (int k = lane; k < nrows; k += 32) {
+                const int64_t row = r_cur + k;
+                const T acc = rowsum[k];
+                const int64_t b = indptr[row], e = indptr[row + 1];
+                if (lead_span && row == r_lo) {
+                    // began in an earlier tile: this tile is its completing slot
+                    const int64_t t_a = (b + row) / TILE_ITEMS;
+                    const uint32_t expected = (uint32_t)(tile - t_a + 1);
+                    double total;
+                    if (span_arrive(&P.span_acc[tile], &P.span_cnt[tile], (double)acc, expected, &total))
+                        update(row, (T)total, (int)(e - b));
+                } else {
+                    update(row, acc, (int)(e - b));
+                }
+            }
+            __syncwarp();
+            r_cur += nrows;
+        }
+
+        // row still open at the end of the tile: hand the partial to the tile that completes it
+        if (lane == 0 && r_hi < P.n) {
+            const int64_t b = indptr[r_hi], e = indptr[r_hi + 1];
+            const int64_t first_here = b > e_lo ? b : e_lo;
+            if (e_hi > first_here) {
+                const int64_t t_a = (b + r_hi) / TILE_ITEMS, t_b = (e + r_hi) / TILE_ITEMS;
+                const uint32_t expected = (uint32_t)(t_b - t_a + 1);
+                double total;
+                if (span_arrive(&P.span_acc[t_b], &P.span_cnt[t_b], (double)carry, expected, &total))
+                    update(r_hi, (T)total, (int)(e - b));
+            }
+        }
+    }
+
+    if (MODE != MODE_CONV) {
+        const double err = block_sum(update.err, s_red);
+        const double tsum = block_sum(update.tsum, s_red);
+        if (threadIdx.x == 0) {
+            atomicAdd(&P.sf[PGB_SF_EACC], err);
+            atomicAdd(&P.sf[PGB_SF_TACC], tsum);
+            __threadfence();
+            const int ticket = atomicAdd(&P.si[PGB_SI_TICKET], 1);
+            if (ticket == (int)gridDim.x - 1) {
+                __threadfence();
+                if (P.finalize)
+                    finalize_state(P.sf, P.si, P.err_hist);
+                else
+                    P.si[PGB_SI_TICKET] = 0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v3: warp-autonomous tiles over the ITEM-SPACE stream.  The graph is additionally stored as
+// istream[n + nnz]: for every row its ascending column indices followed by one terminator
+// -1-deg (same bytes as indices + row pointers).  A merge tile is then a plain slice of that array:
+// no row-pointer loads, no rank arithmetic — a lane's item is an entry (col >= 0) or a row end
+// (col < 0), and the terminator carries the degree the SYMDEG update needs.  The dependent chain
+// of a pass is item load -> gather -> merge, and it is software-pipelined: the items of pass i+1
+// are loaded, and the finished rows of pass i-1 are updated, while the gathers of pass i fly.
+#ifndef PGB_V3_MINB
+#define PGB_V3_MINB 4
+#endif
+template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
+__global__ void __launch_bounds__(BLOCK, PGB_V3_MINB) item_stream_kernel(const StepParams P) {
+    __shared__ T s_buf[WARPS][2][SUB_ITEMS + 1];      // items -> row sums, double buffered across passes
+    __shared__ uint16_t s_deg[WARPS][2][SYMDEG ? SUB_ITEMS + 2 : 2];  // row degrees (0xFFFF: look it up)
+    __shared__ unsigned s_mask[WARPS][IPT + 1];
+    __shared__ int s_pre[WARPS][IPT + 1];
+    __shared__ double s_red[32];
+
+    if (MODE != MODE_CONV) {
+        if (P.si[PGB_SI_STOP] != PGB_RUNNING) return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int32_t PAD = (int32_t)0x80000000;  // items past the end of the stream
+    const T *__restrict__ zin = (const T *)P.zin;
+    const int32_t *__restrict__ istream = P.istream;
+    const T *__restrict__ vstream = (const T *)P.vstream;
+    if (lane == 0) s_mask[warp][IPT] = 0u;
+    RowUpdate<T, MODE, SYMDEG> update(P);
+    const int64_t total_items = P.n + P.nnz;
+
+    for (int32_t tile = blockIdx.x * WARPS + warp; tile < P.n_tiles; tile += gridDim.x * WARPS) {
+        const int64_t item_lo = (int64_t)tile * TILE_ITEMS;
+        const int64_t item_hi = (item_lo + TILE_ITEMS < total_items) ? item_lo + TILE_ITEMS : total_items;
+        const int32_t r_lo = P.tile_row[tile], r_hi = P.tile_row[tile + 1];
+        // the first row finished here began in an earlier tile iff its first item precedes the tile
+        const bool lead_span = (r_hi > r_lo) && ((int64_t)P.indptr[r_lo] + r_lo < item_lo);
+        int64_t r_cur = r_lo;
+        T carry = (T)0;
+        int cur = 0;
+        int pend_rows = 0, pend_buf = 0;   // finished rows of the previous pass, not yet updated
+        int64_t pend_r = 0;
+
+        int32_t nxt[IPT];
+        T nxtv[WEIGHTED ? IPT : 1];
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+            const int64_t g = item_lo + s * 32 + lane;
+            nxt[s] = (g < item_hi) ? ld_stream(istream + g) : PAD;
+            if (WEIGHTED) nxtv[s] = (g < item_hi) ? ld_stream(vstream + g) : (T)0;
+        }
+
+        for (int64_t I0 = item_lo; I0 < item_hi; I0 += SUB_ITEMS) {
+            T *buf = s_buf[warp][cur];
+            // ---- a. classify the items of this pass, launch the gathers -------------------------
+            int32_t cols[IPT];
+            T x[IPT];
+            unsigned m[IPT];
+            int nrows = 0;
+#pragma unroll
+            for (int s = 0; s < IPT; ++s) {
+                cols[s] = nxt[s];
+                m[s] = __ballot_sync(FULL, cols[s] < 0 && cols[s] != PAD);
+            }
+#pragma unroll
+            for (int s = 0; s < IPT; ++s) x[s] = (cols[s] >= 0) ? __ldg(zin + cols[s]) : (T)0;
+            if (WEIGHTED) {
+#pragma unroll
+                for (int s = 0; s < IPT; ++s) x[s] *= nxtv[WEIGHTED ? s : 0];
+            }
+#pragma unroll
+            for (int s = 0; s < IPT; ++s) {
+                if (lane == s) {
+                    s_mask[warp][s] = m[s];
+                    s_pre[warp][s] = nrows;
+                }
+                if (SYMDEG) {
+                    if (cols[s] < 0 && cols[s] != PAD) {
+                        const int deg = -1 - cols[s];
+                        s_deg[warp][cur][nrows + __popc(m[s] & lt_mask)] = (uint16_t)(deg < 0xFFFF ? deg : 0xFFFF);
+                    }
+                }
+                nrows += __popc(m[s]);
+            }
+            // ---- b. prefetch the items of the next pass -----------------------------------------
+            {
+                const int64_t nbase = I0 + SUB_ITEMS;
+#pragma unroll
+                for (int s = 0; s < IPT; ++s) {
+                    const int64_t g = nbase + s * 32 + lane;
+                    nxt[s] = (g < item_hi) ? ld_stream(istream + g) : PAD;
+                    if (WEIGHTED) nxtv[s] = (g < item_hi) ? ld_stream(vstream + g) : (T)0;
+                }
+            }
+            // ---- c. update the rows finished in the previous pass (loads fly with the gathers) ----
+            if (pend_rows > 0) {
+                const T *rs = s_buf[warp][pend_buf];
+                for (int k = lane; k < pend_rows; k += 32) {
+                    const int64_t row = pend_r + k;
+                    int deg = SYMDEG ? (int)s_deg[warp][pend_buf][k] : 0;
+                    if (SYMDEG && deg == 0xFFFF) deg = P.indptr[row + 1] - P.indptr[row];
+                    if (lead_span && row == r_lo) {
+                        const int64_t t_a = ((int64_t)P.indptr[row] + row) / TILE_ITEMS;
+                        const uint32_t expected = (uint32_t)(tile - t_a + 1);
+                        double total;
+                        if (span_arrive(&P.span_acc[tile], &P.span_cnt[tile], (double)rs[k], expected, &total))
+                            update(row, (T)total, deg);
+                    } else {
+                        update(row, rs[k], deg);
+                    }
+                }
+                pend_rows = 0;
+            }
+            // ---- d. park the gathered values in item space, merge blocked -----------------------
+#pragma unroll
+            for (int s = 0; s < IPT; ++s) buf[s * 32 + lane] = x[s];
+            __syncwarp();
+            {
+                const int p0 = lane * IPT;
+                const int w0 = p0 >> 5, sh = p0 & 31;
+                const unsigned lo = s_mask[warp][w0], hi = s_mask[warp][w0 + 1];
+                int k = s_pre[warp][w0] + __popc(lo & ((1u << sh) - 1u));
+                const unsigned bits = __funnelshift_r(lo, hi, sh) & ((1u << IPT) - 1u);
+                T it[IPT];
+#pragma unroll
+                for (int j = 0; j < IPT; ++j) it[j] = buf[p0 + j];
+                __syncwarp();  // items are in registers: the buffer now receives the row sums
+                T run = (T)0, head = (T)0;
+                int first_k = -1;
+#pragma unroll
+                for (int j = 0; j < IPT; ++j) {
+                    if ((bits >> j) & 1u) {
+                        if (first_k < 0) {
+                            head = run;
+                            first_k = k;
+                        } else {
+                            buf[k] = run;
+                        }
+                        run = (T)0;
+                        ++k;
+                    } else {
+                        run += it[j];
+                    }
+                }
+                const bool closed = first_k >= 0;
+                const unsigned closed_mask = __ballot_sync(FULL, closed);
+                T seg = run;
+                bool f = closed;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const T t = __shfl_up_sync(FULL, seg, d);
+                    const bool tf = __shfl_up_sync(FULL, (int)f, d);
+                    if (lane >= d && !f) {
+                        seg += t;
+                        f = tf;
+                    }
+                }
+                T carry_in = __shfl_up_sync(FULL, seg, 1);
+                if (lane == 0) carry_in = (T)0;
+                if ((closed_mask & lt_mask) == 0u) carry_in += carry;
+                if (closed) buf[first_k] = head + carry_in;
+                const T last = __shfl_sync(FULL, seg, 31);
+                carry = (closed_mask == 0u) ? carry + last : last;
+            }
+            __syncwarp();
+            pend_rows = nrows;
+            pend_buf = cur;
+            pend_r = r_cur;
+            r_cur += nrows;
+            cur ^= 1;
+            if (I0 + SUB_ITEMS >= item_hi && pend_rows > 0) {
+                // last pass of the tile: nothing left to hide behind, update now
+                const T *rs = s_buf[warp][pend_buf];
+                for (int k = lane; k < pend_rows; k += 32) {
+                    const int64_t row = pend_r + k;
+                    int deg = SYMDEG ? (int)s_deg[warp][pend_buf][k] : 0;
+                    if (SYMDEG && deg == 0xFFFF) deg = P.indptr[row + 1] - P.indptr[row];
+                    if (lead_span && row == r_lo) {
+                        const int64_t t_a = ((int64_t)P.indptr[row] + row) / TILE_ITEMS;
+                        const uint32_t expected = (uint32_t)(tile - t_a + 1);
+                        double total;
+                        if (span_arrive(&P.span_acc[tile], &P.span_cnt[tile], (double)rs[k], expected, &total))
+                            update(row, (T)total, deg);
+                    } else {
+                        update(row, rs[k], deg);
+                    }
+                }
+                pend_rows = 0;
+                __syncwarp();
+            }
+        }
+
+        // row still open at the end of the tile: hand the partial to the tile that completes it
+        if (lane == 0 && r_hi < P.n) {
+            const int64_t b = P.indptr[r_hi], e = P.indptr[r_hi + 1];
+            const int64_t e_lo = item_lo - r_lo, e_hi = item_hi - r_hi;
+            const int64_t first_here = b > e_lo ? b : e_lo;
+            if (e_hi > first_here) {
+                const int64_t t_a = (b + r_hi) / TILE_ITEMS, t_b = (e + r_hi) / TILE_ITEMS;
+                const uint32_t expected = (uint32_t)(t_b - t_a + 1);
+                double total;
+                if (span_arrive(&P.span_acc[t_b], &P.span_cnt[t_b], (double)carry, expected, &total))
+                    update(r_hi, (T)total, (int)(e - b));
+            }
+        }
+    }
+
+    if (MODE != MODE_CONV) {
+        const double err = block_sum(update.err, s_red);
+        const double tsum = block_sum(update.tsum, s_red);
+        if (threadIdx.x == 0) {
+            atomicAdd(&P.sf[PGB_SF_EACC], err);
+            atomicAdd(&P.sf[PGB_SF_TACC], tsum);
+            __threadfence();
+            const int ticket = atomicAdd(&P.si[PGB_SI_TICKET], 1);
+            if (ticket == (int)gridDim.x - 1) {
+                __threadfence();
+                if (P.finalize)
+                    finalize_state(P.sf, P.si, P.err_hist);
+                else
+                    P.si[PGB_SI_TICKET] = 0;
+            }
+        }
+    }
+}
+
+// Builds the item-space stream from CSR: warp per row.
+template <typename V>
+__global__ void build_item_stream_kernel(int64_t n, const int32_t *__restrict__ indptr,
+                                         const int32_t *__restrict__ indices, const V *__restrict__ values,
+                                         int32_t *__restrict__ istream, V *__restrict__ vstream) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const int64_t b = indptr[r], e = indptr[r + 1];
+        for (int64_t k = b + lane; k < e; k += 32) {
+            istream[k + r] = indices[k];
+            if (values) vstream[k + r] = values[k];
+        }
+        if (lane == 0) {
+            istream[e + r] = (int32_t)(-1 - (e - b));
+            if (values) vstream[e + r] = (V)0;
+        }
+    }
+}
+
+// Roofline probe (not on the product path): the same evict-first index stream and read-only
+// gathers as the fused kernel, nothing else.  Its rate is the ceiling any CSR row-gather can reach
+// for this graph on this part; bench.py and DESIGN.md quote the fused kernel against it.
+template <typename T>
+__global__ void __launch_bounds__(BLOCK, 4) gather_probe_kernel(const int32_t *__restrict__ indices, int64_t nnz,
+                                                                const T *__restrict__ z, T *out) {
+    T acc = (T)0;
+    const int64_t span = (int64_t)BLOCK * IPT;
+    for (int64_t base = blockIdx.x * span; base < nnz; base += (int64_t)gridDim.x * span) {
+        int32_t cols[IPT];
+#pragma unroll
+        for (int s = 0; s < IPT; ++s) {
+            const int64_t i = base + s * BLOCK + threadIdx.x;
+            cols[s] = (i < nnz) ? ld_stream(indices + i) : -1;
+        }
+#pragma unroll
+        for (int s = 0; s < IPT; ++s)
+            if (cols[s] >= 0) acc += __ldg(z + cols[s]);
+    }
+    if (acc == (T)-123456789) out[0] = acc;  // keeps the loads alive
+}
+
+static int g_kernel_variant = 3;  // 1 = CTA tiles, 2 = warp tiles over CSR, 3 = warp tiles over the item stream
+
 template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
 static int launch_tiles(const StepParams &P, cudaStream_t st) {
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
+    static int ctas_per_sm[4] = {0, 0, 0, 0};
+    int variant = g_kernel_variant;
+    if (variant == 3 && (!P.istream || (WEIGHTED && !P.vstream)))
+        return fail("the item-stream kernel needs pgb_csr.istream%s (pgb_build_item_stream)", WEIGHTED ? "/vstream" : "");
+    if (ctas_per_sm[variant] == 0) {
         int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, tile_kernel<T, WEIGHTED, MODE, SYMDEG>, BLOCK, 0) !=
-                cudaSuccess || v < 1)
-            v = 2;
-        ctas_per_sm = v;
+        cudaError_t e = (variant == 1)
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, tile_kernel<T, WEIGHTED, MODE, SYMDEG>, BLOCK, 0)
+            : (variant == 2)
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, warp_tile_kernel<T, WEIGHTED, MODE, SYMDEG>, BLOCK, 0)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, item_stream_kernel<T, WEIGHTED, MODE, SYMDEG>, BLOCK, 0);
+        if (e != cudaSuccess || v < 1) v = 2;
+        ctas_per_sm[variant] = v;
+        if (const char *c = getenv("PGB_SMEM_CARVEOUT")) {  // experiment knob: percent of the 228 KB given to smem
+            const int pct = atoi(c);
+            if (variant == 1)
+                cudaFuncSetAttribute(tile_kernel<T, WEIGHTED, MODE, SYMDEG>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            else if (variant == 2)
+                cudaFuncSetAttribute(warp_tile_kernel<T, WEIGHTED, MODE, SYMDEG>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            else
+                cudaFuncSetAttribute(item_stream_kernel<T, WEIGHTED, MODE, SYMDEG>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
     }
-    int grid = sm_count() * ctas_per_sm;
-    if (grid > P.n_tiles) grid = P.n_tiles;
-    if (grid < 1) return 0;
-    tile_kernel<T, WEIGHTED, MODE, SYMDEG><<<grid, BLOCK, 0, st>>>(P);
-    PGB_LAUNCH_OK("tile_kernel");
+    int grid = sm_count() * ctas_per_sm[variant];
+    if (variant == 1) {
+        if (grid > P.n_tiles) grid = P.n_tiles;
+        if (grid < 1) return 0;
+        tile_kernel<T, WEIGHTED, MODE, SYMDEG><<<grid, BLOCK, 0, st>>>(P);
+        PGB_LAUNCH_OK("tile_kernel");
+    } else {
+        const int need = (int)ceil_div(P.n_tiles, WARPS);
+        if (grid > need) grid = need;
+        if (grid < 1) return 0;
+        if (variant == 2) {
+            warp_tile_kernel<T, WEIGHTED, MODE, SYMDEG><<<grid, BLOCK, 0, st>>>(P);
+            PGB_LAUNCH_OK("warp_tile_kernel");
+        } else {
+            item_stream_kernel<T, WEIGHTED, MODE, SYMDEG><<<grid, BLOCK, 0, st>>>(P);
+            PGB_LAUNCH_OK("item_stream_kernel");
+        }
+    }
     return 0;
 }
 
@@ -339,6 +872,8 @@ static int fill_graph(StepParams &P, const pgb_csr *g) {
     P.values = g->values;
     P.tile_row = g->tile_row;
     P.n_tiles = g->n_tiles;
+    P.istream = g->istream;
+    P.vstream = g->vstream;
     return 0;
 }
 
@@ -349,6 +884,46 @@ using namespace pgb;
 extern "C" {
 
 int pgb_tile_items(void) { return TILE_ITEMS; }
+
+int pgb_build_item_stream(int64_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, int dtype,
+                          const void *values, int32_t *istream, void *vstream, void *stream) {
+    if (n <= 0) return 0;
+    if (n + nnz >= (1ll << 31)) return fail("pgb_build_item_stream: n + nnz exceeds the int32 item space of one device");
+    const int grid = stride_grid(n * 32, 256);
+    if (!values)
+        build_item_stream_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(n, indptr, indices, nullptr, istream, nullptr);
+    else if (dtype == PGB_F32)
+        build_item_stream_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(n, indptr, indices, (const float *)values,
+                                                                              istream, (float *)vstream);
+    else if (dtype == PGB_F64)
+        build_item_stream_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(n, indptr, indices, (const double *)values,
+                                                                               istream, (double *)vstream);
+    else
+        return fail("pgb_build_item_stream: unknown dtype %d", dtype);
+    PGB_LAUNCH_OK("build_item_stream_kernel");
+    return 0;
+}
+
+int pgb_gather_probe(const pgb_csr *g, int dtype, const void *z, void *scratch, void *stream) {
+    if (!g || g->nnz <= 0) return 0;
+    const int grid = sm_count() * 4;
+    if (dtype == PGB_F32)
+        gather_probe_kernel<float><<<grid, BLOCK, 0, as_stream(stream)>>>(g->indices, g->nnz, (const float *)z,
+                                                                          (float *)scratch);
+    else if (dtype == PGB_F64)
+        gather_probe_kernel<double><<<grid, BLOCK, 0, as_stream(stream)>>>(g->indices, g->nnz, (const double *)z,
+                                                                           (double *)scratch);
+    else
+        return fail("pgb_gather_probe: unknown dtype %d", dtype);
+    PGB_LAUNCH_OK("gather_probe_kernel");
+    return 0;
+}
+
+int pgb_set_kernel_variant(int variant) {
+    if (variant < 1 || variant > 3) return fail("pgb_set_kernel_variant: %d is not 1, 2 or 3", variant);
+    g_kernel_variant = variant;
+    return 0;
+}
 
 int pgb_spmv(const pgb_csr *g, int dtype, const void *z, const void *rscale, const void *x_for_laplacian,
              const int32_t *out_perm, void *out, pgb_span_ws ws, void *stream) {

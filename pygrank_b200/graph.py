@@ -84,6 +84,36 @@ class CsrView:
         C.check(lib.pgb_mergepath_partition(self.n, self.nnz, C.ptr(indptr), self.n_tiles, C.ptr(self.tile_row),
                                             C.stream_ptr()))
         self._ws = None
+        self._istream = None
+        self._vstream = {}
+
+    def istream(self) -> torch.Tensor:
+        """Item-space index stream (row entries + terminator -1-deg) read by the fused kernels."""
+        if self._istream is None:
+            self._build_streams(None)
+        return self._istream
+
+    def vstream(self, dtype: torch.dtype) -> Optional[torch.Tensor]:
+        if not self.weighted:
+            return None
+        if dtype not in self._vstream:
+            self._build_streams(dtype)
+        return self._vstream[dtype]
+
+    def _build_streams(self, dtype):
+        lib = C.lib()
+        dev = self.indptr.device
+        # the index stream is written once and never replaced: C structs hold its raw pointer
+        ist = self._istream if self._istream is not None else torch.empty(self.n + self.nnz, dtype=torch.int32,
+                                                                          device=dev)
+        vals = self.values(dtype) if (dtype is not None and self.weighted) else None
+        vst = torch.empty(self.n + self.nnz, dtype=dtype, device=dev) if vals is not None else None
+        C.check(lib.pgb_build_item_stream(self.n, self.nnz, C.ptr(self.indptr), C.ptr(self.indices),
+                                          dtype_code(dtype) if vals is not None else C.PGB_F32, C.ptr(vals),
+                                          C.ptr(ist), C.ptr(vst), C.stream_ptr()))
+        self._istream = ist
+        if vst is not None:
+            self._vstream[dtype] = vst
 
     def values(self, dtype: torch.dtype) -> Optional[torch.Tensor]:
         if not self.weighted:
@@ -94,7 +124,8 @@ class CsrView:
 
     def cstruct(self, dtype: torch.dtype) -> C.Csr:
         return C.Csr(self.n, self.nnz, C.ptr(self.indptr), C.ptr(self.indices), C.ptr(self.values(dtype)),
-                     C.ptr(self.tile_row), self.n_tiles, self.tile_items)
+                     C.ptr(self.tile_row), self.n_tiles, self.tile_items, C.ptr(self.istream()),
+                     C.ptr(self.vstream(dtype)))
 
     def new_span_ws(self):
         """Zeroed cross-tile workspace (one per concurrently running filter)."""
@@ -114,6 +145,7 @@ class CsrView:
         other._values = {torch.float64: values64}
         other.weighted = True
         other._ws = None
+        other._vstream = {}
         return other
 
 

@@ -154,3 +154,166 @@ def test_model_matches_row_sums(kind, block, ipt):
         order = rng.permutation(n_tiles)
         got = model_spmv(indptr, indices, z, block, ipt, tile_order=order)
         assert np.array_equal(got, expect)
+
+
+# ------------------------------------------------------------------------------------------------
+# v2: warp-autonomous tiles (warp_tile_kernel).  LANES plays the role of the 32 lanes; a tile is
+# `subs` passes of LANES*ipt items.
+def model_spmv_v2(indptr, indices, z, lanes, ipt, subs, tile_order=None):
+    n, nnz = len(indptr) - 1, len(indices)
+    sub_items = lanes * ipt
+    tile_items = sub_items * subs
+    n_tiles, tile_row = partition(indptr, n, nnz, tile_items)
+    total_items = n + nnz
+    out = np.full(n, np.nan)
+    written = np.zeros(n, dtype=int)
+    span_acc = np.zeros(max(n_tiles, 1))
+    span_cnt = np.zeros(max(n_tiles, 1), dtype=np.int64)
+
+    def update(row, acc, deg):
+        assert deg == indptr[row + 1] - indptr[row]
+        out[row] = acc
+        written[row] += 1
+
+    def commit(slot, partial, expected, row):
+        assert expected >= 2
+        span_acc[slot] += partial
+        arrived = span_cnt[slot]
+        span_cnt[slot] += 1
+        if arrived == expected - 1:
+            total = span_acc[slot]
+            span_acc[slot] = 0.0
+            span_cnt[slot] = 0
+            update(row, total, indptr[row + 1] - indptr[row])
+
+    order = range(n_tiles) if tile_order is None else tile_order
+    for tile in order:
+        item_lo = tile * tile_items
+        item_hi = min(item_lo + tile_items, total_items)
+        r_lo, r_hi = int(tile_row[tile]), int(tile_row[tile + 1])
+        e_lo, e_hi = item_lo - r_lo, item_hi - r_hi
+        lead_span = (r_hi > r_lo) and (indptr[r_lo] < e_lo)
+        r_cur, carry = r_lo, 0.0
+        I0 = item_lo
+        while I0 < item_hi:
+            nitems = min(item_hi - I0, sub_items)
+            e_cur = I0 - r_cur
+            # 1. marker mask, batches of `lanes` rows
+            m = [0] * ipt
+            nrows, b = 0, 0
+            while True:
+                cnt = 0
+                for lane in range(lanes):
+                    row = r_cur + b * lanes + lane
+                    pos = nitems
+                    if row < n:
+                        pos = indptr[row + 1] + row - I0
+                    if pos < nitems:
+                        assert pos >= 0
+                        m[int(pos) // lanes] |= 1 << (int(pos) % lanes)
+                        cnt += 1
+                nrows += cnt
+                if cnt < lanes:
+                    break
+                b += 1
+            # 2. striped gather into item space
+            item = [0.0] * sub_items
+            pre = 0
+            s_pre = [0] * (ipt + 1)
+            for s in range(ipt):
+                s_pre[s] = pre
+                for lane in range(lanes):
+                    p = s * lanes + lane
+                    is_marker = (m[s] >> lane) & 1
+                    rank = pre + bin(m[s] & ((1 << lane) - 1)).count("1")
+                    e = e_cur + p - rank
+                    if p < nitems and not is_marker:
+                        assert e_lo <= e < e_hi
+                        item[p] = z[indices[e]]
+                pre += bin(m[s]).count("1")
+            assert pre == nrows
+            # 3. blocked merge
+            rowsum = [None] * (sub_items + 1)
+            tails, closed, firsts, heads = [], [], [], []
+            allbits = 0
+            for s in range(ipt):
+                allbits |= int(m[s]) << (s * lanes)
+            for lane in range(lanes):
+                p0 = lane * ipt
+                w0, sh = p0 // lanes, p0 % lanes
+                lo = m[w0]
+                k = s_pre[w0] + bin(lo & ((1 << sh) - 1)).count("1")
+                bits = (allbits >> p0) & ((1 << ipt) - 1)   # funnel shift of (lo, hi); ipt <= lanes assumed below
+                run, head, first_k = 0.0, 0.0, -1
+                for j in range(ipt):
+                    if (bits >> j) & 1:
+                        if first_k < 0:
+                            head, first_k = run, k
+                        else:
+                            assert rowsum[k] is None
+                            rowsum[k] = run
+                        run = 0.0
+                        k += 1
+                    else:
+                        run += item[p0 + j]
+                tails.append(run)
+                closed.append(first_k >= 0)
+                firsts.append(first_k)
+                heads.append(head)
+            # segmented inclusive scan (Hillis-Steele with flags), exactly as the shuffles do it
+            seg, f = list(tails), list(closed)
+            d = 1
+            while d < lanes:
+                nseg, nf = list(seg), list(f)
+                for lane in range(lanes):
+                    if lane >= d and not f[lane]:
+                        nseg[lane] = seg[lane] + seg[lane - d]
+                        nf[lane] = f[lane - d]
+                seg, f = nseg, nf
+                d <<= 1
+            for lane in range(lanes):
+                carry_in = seg[lane - 1] if lane > 0 else 0.0
+                if not any(closed[:lane]):
+                    carry_in += carry
+                if closed[lane]:
+                    assert rowsum[firsts[lane]] is None
+                    rowsum[firsts[lane]] = heads[lane] + carry_in
+            carry = (carry + seg[lanes - 1]) if not any(closed) else seg[lanes - 1]
+            # 4. row updates
+            for k in range(nrows):
+                row = r_cur + k
+                assert rowsum[k] is not None
+                b_, e_ = indptr[row], indptr[row + 1]
+                if lead_span and row == r_lo:
+                    t_a = (b_ + row) // tile_items
+                    commit(tile, rowsum[k], tile - t_a + 1, row)
+                else:
+                    update(row, rowsum[k], e_ - b_)
+            r_cur += nrows
+            I0 += sub_items
+        assert r_cur == r_hi
+        if r_hi < n:
+            b_, e_ = indptr[r_hi], indptr[r_hi + 1]
+            if e_hi > max(b_, e_lo):
+                t_a, t_b = (b_ + r_hi) // tile_items, (e_ + r_hi) // tile_items
+                commit(t_b, carry, t_b - t_a + 1, r_hi)
+    assert np.all(written == 1), np.flatnonzero(written != 1)
+    assert not span_acc.any() and not span_cnt.any()
+    return out
+
+
+@pytest.mark.parametrize("kind", ["powerlaw", "star", "empty", "dense_rows", "edges"])
+@pytest.mark.parametrize("lanes,ipt,subs", [(4, 3, 2), (8, 5, 1), (8, 3, 4), (32, 9, 8), (4, 1, 3)])
+def test_warp_tile_model_matches_row_sums(kind, lanes, ipt, subs):
+    rng = np.random.default_rng(abs(hash((len(kind), lanes, ipt, subs))) % 2 ** 32)
+    for n in (1, 2, 17, 64, 301, 1500):
+        if n == 1500 and lanes * ipt * subs < 64:
+            continue
+        indptr, indices = random_csr(rng, n, kind)
+        z = rng.integers(1, 100, n).astype(np.float64)
+        expect = np.array([z[indices[indptr[i]:indptr[i + 1]]].sum() for i in range(n)])
+        got = model_spmv_v2(indptr, indices, z, lanes, ipt, subs)
+        assert np.array_equal(got, expect)
+        n_tiles = -(-(n + len(indices)) // (lanes * ipt * subs))
+        got = model_spmv_v2(indptr, indices, z, lanes, ipt, subs, tile_order=rng.permutation(n_tiles))
+        assert np.array_equal(got, expect)
