@@ -26,7 +26,11 @@
 namespace pgb {
 
 constexpr int BLOCK = 256;
-constexpr int IPT = 9;  // odd: thread-blocked reads of shared memory hit distinct banks
+#ifndef PGB_IPT
+#define PGB_IPT 9
+#endif
+constexpr int IPT = PGB_IPT;  // odd: thread-blocked reads of shared memory hit distinct banks
+static_assert(IPT % 2 == 1 && IPT <= 31, "items per thread must be odd");
 constexpr int TILE_ITEMS = BLOCK * IPT;   // merge items per tile (v1: one CTA; v2: one warp, 8 sub-tiles)
 constexpr int WARPS = BLOCK / 32;
 constexpr int SUB_ITEMS = 32 * IPT;       // v2: items one warp consumes per pass
@@ -531,7 +535,7 @@ __global__ void __launch_bounds__(BLOCK, 4) warp_tile_kernel(const StepParams P)
 // of a pass is item load -> gather -> merge, and it is software-pipelined: the items of pass i+1
 // are loaded, and the finished rows of pass i-1 are updated, while the gathers of pass i fly.
 #ifndef PGB_V3_MINB
-#define PGB_V3_MINB 4
+#define PGB_V3_MINB 3   // 80 registers/thread: the pipelined pass keeps 3 x IPT values live without spilling
 #endif
 template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
 __global__ void __launch_bounds__(BLOCK, PGB_V3_MINB) item_stream_kernel(const StepParams P) {
@@ -638,6 +642,17 @@ __global__ void __launch_bounds__(BLOCK, PGB_V3_MINB) item_stream_kernel(const S
                 pend_rows = 0;
             }
             // ---- d. park the gathered values in item space, merge blocked -----------------------
+            if (nrows == 0) {
+                // interior of a long row (about half of all passes on power-law graphs): no row ends,
+                // so the pass is one warp-wide sum added to the open row
+                T tot = x[0];
+#pragma unroll
+                for (int s = 1; s < IPT; ++s) tot += x[s];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+                carry += tot;
+                continue;
+            }
 #pragma unroll
             for (int s = 0; s < IPT; ++s) buf[s * 32 + lane] = x[s];
             __syncwarp();
