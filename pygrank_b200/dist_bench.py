@@ -1,0 +1,145 @@
+"""bench.py's N>1 leg: weak-scaling PPR on a row-partitioned RMAT graph (scale 24 + log2 N)."""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def run(args):
+    from . import _capi as C
+    from . import synthetic
+    from .dist import DistGraph, DistPageRank
+    from .graph import dtype_code, span_struct
+    import bench as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    w = 4 if dtype == torch.float32 else 8
+    scale = args.scale
+    t0 = time.perf_counter()
+    g = DistGraph.rmat(scale, 16, seed=1)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    alg = DistPageRank(B.ALPHA, tol=B.TOL, max_iters=B.MAX_ITERS, dtype=dtype)
+    total = args.warmup + args.steps
+    seeds = synthetic.seed_sets(g.n_nodes, total, 10, seed=0)
+    pers = [alg.local_personalization(g, s) for s in seeds]
+
+    def timed(fn):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t = time.perf_counter()
+        e0.record()
+        calls = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max(e0.elapsed_time(e1), (time.perf_counter() - t) * 1e3 * 0.0)
+        worst = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        return float(worst.item()), calls
+
+    for i in range(args.warmup):
+        alg.rank(g, p_local=pers[i][0], norm=pers[i][1])
+    sampler = B.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = C.LAUNCHES[0]
+
+    def resident():
+        calls = 0
+        for i in range(args.warmup, total):
+            alg.rank(g, p_local=pers[i][0], norm=pers[i][1])
+            calls += alg.iteration - 1
+        return calls
+
+    dev_ms, conv_calls = timed(resident)
+    launches = C.LAUNCHES[0] - launches0
+    value = g.nnz_global * conv_calls / (dev_ms * 1e-3) / 1e9
+
+    host_out = torch.empty(g.n_local, dtype=dtype).pin_memory()
+
+    def end_to_end():
+        calls = 0
+        for i in range(args.warmup, total):
+            r = alg.rank(g, seeds[i])
+            host_out.copy_(r, non_blocking=False)
+            calls += alg.iteration - 1
+        return calls
+
+    e2e_ms, e2e_calls = timed(end_to_end)
+    e2e_value = g.nnz_global * e2e_calls / (e2e_ms * 1e-3) / 1e9
+    clocks = sampler.stop() if rank == 0 else None
+
+    # the fused kernel alone on this rank's rows (no exchange), CUDA events on the launch stream
+    lib = C.lib()
+    code = dtype_code(dtype)
+    st = C.stream_ptr()
+    n_loc, off = g.n_local, g.offset
+    sf = [0.0] * C.STATE_LEN
+    si = [0] * C.STATE_LEN
+    sf[C.SF_ALPHA], sf[C.SF_INVS], sf[C.SF_MEAN], sf[C.SF_NORM] = B.ALPHA, 1.0, float(g.n_nodes), 10.0
+    si[C.SI_MAX_ITERS], si[C.SI_END_MODULO], si[C.SI_ERR_MODE], si[C.SI_QUOTIENT] = 10 ** 6, 1, C.ERR_ITERS, 0
+    state_f64 = torch.tensor(sf, dtype=torch.float64, device=dev)
+    state_i32 = torch.tensor(si, dtype=torch.int32, device=dev)
+    zfull = [torch.rand(g.n_global, dtype=dtype, device=dev), torch.rand(g.n_global, dtype=dtype, device=dev)]
+    q = torch.zeros(n_loc, dtype=dtype, device=dev)
+    cvec = g.vec("c", dtype)
+    cs = g.view.cstruct(dtype)
+    ws = g.view.new_span_ws()
+    err_hist = torch.zeros(128, dtype=torch.float64, device=dev)
+    reps = 20
+
+    def steps(first, count):
+        C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, B.ALPHA, None, None, C.ptr(cvec), C.ptr(q),
+                                     C.ptr(zfull[0]), C.ptr(zfull[1]), off, C.ptr(state_f64), C.ptr(state_i32),
+                                     C.ptr(err_hist), span_struct(ws), first, count, 1, st))
+
+    steps(1, 3)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    steps(4, reps)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = torch.tensor([k0.elapsed_time(k1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
+    kernel_ms = float(kernel_ms.item())
+    alg_bytes = g.nnz_local * 4 + (n_loc + 1) * 4 + (g.n_global + 4 * n_loc) * w
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = B.hbm_peak()
+    nnz_all = [None] * world
+    dist.all_gather_object(nnz_all, g.nnz_local)
+    if rank == 0:
+        line = {
+            "metric": "PPR GTEPS", "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": dict(B.workload_config(world, scale), n=g.n_nodes, nnz=g.nnz_global,
+                           nnz_per_rank=[int(x) for x in nnz_all], conv_calls_per_solve=conv_calls / args.steps,
+                           exchange="NCCL all_gather_into_tensor of n/N rank-vector slices + 16-byte all_reduce per iteration",
+                           graph_build_s=round(build_s, 2)),
+            "e2e": {"value": e2e_value, "unit": "GTEPS", "h2d_bytes_per_step": 10 * 8 + 10 * 8,
+                    "d2h_bytes_per_step": g.n_local * w * world + 64 * 2},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "item_stream_kernel<%s,unweighted,AFFINE,SYMDEG> (per rank, max over ranks)" % args.dtype,
+                         "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+            "cpu_baseline": None,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()

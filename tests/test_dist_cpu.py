@@ -1,0 +1,122 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes run the partition helpers of
+pygrank_b200/dist.py and a stand-in for the per-rank kernel (the oracle's arithmetic, test-only),
+exchanging slices with all_gather / all_reduce exactly as the GPU driver does."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, scale, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pygrank_b200 import synthetic
+    from pygrank_b200.dist import interleaved_ids, local_entries, padded_size
+    n = 1 << scale
+    src, dst = synthetic.rmat_edges_host(scale, 8, seed=3)
+    total = len(src)
+    n_global = padded_size(n, world)
+    n_local = n_global // world
+    # pass 1: each rank counts its slice of the edge stream, then all-reduce
+    per = (total + world - 1) // world
+    lo, hi = rank * per, min((rank + 1) * per, total)
+    deg = torch.zeros(n_global, dtype=torch.int32)
+    ones = torch.ones(hi - lo, dtype=torch.int32)
+    deg.index_add_(0, torch.from_numpy(src[lo:hi]).long(), ones)
+    deg.index_add_(0, torch.from_numpy(dst[lo:hi]).long(), ones)
+    dist.all_reduce(deg)
+    new_id = interleaved_ids(deg, world)
+    rows, cols = local_entries(torch.from_numpy(src), torch.from_numpy(dst), new_id, rank, n_local)
+    A_loc = sp.coo_matrix((np.ones(len(rows)), (rows.numpy(), cols.numpy())), shape=(n_local, n_global)).tocsr()
+    A_loc.sum_duplicates()
+    A_loc.data[:] = 1.0
+    # row-partitioned PPR with the S-in-advance normaliser (mirrors DistPageRank + finalize_state)
+    alpha, tol = 0.85, 1e-9
+    d_loc = np.asarray(A_loc.sum(axis=1)).ravel()
+    sq = np.where(d_loc > 0, np.sqrt(d_loc), 1.0)
+    R_loc = np.where(d_loc > 0, 1.0 / np.sqrt(np.maximum(d_loc, 1)), 0.0)
+    R_full = torch.empty(n_global, dtype=torch.float64)
+    dist.all_gather_into_tensor(R_full, torch.from_numpy(R_loc))
+    degM = R_loc * (A_loc @ R_full.numpy())
+    c = sq * degM
+    seeds = synthetic.seed_sets(n, 1, 10, seed=0)[0]
+    p_user = np.zeros(n_global)
+    p_user[seeds] = 1.0
+    p_int = np.zeros(n_global)
+    p_int[new_id.numpy()] = p_user
+    off = rank * n_local
+    pn = p_int[off:off + n_local] / 10.0
+    z = pn / sq
+    q = (1 - alpha) * pn / sq
+    acc = torch.tensor([float((z * c).sum()), float((q * sq).sum())], dtype=torch.float64)
+    dist.all_reduce(acc)
+    invS = 1.0 / (alpha * acc[0].item() + acc[1].item())
+    bias = acc[1].item()
+    zfull = torch.empty(n_global, dtype=torch.float64)
+    dist.all_gather_into_tensor(zfull, torch.from_numpy(z))
+    iteration, steps = 1, 0
+    w = np.where(d_loc > 0, 1.0 / np.maximum(d_loc, 1), 0.0)
+    while True:
+        znew = (alpha * w * (A_loc @ zfull.numpy()) + q) * invS
+        zold = zfull.numpy()[off:off + n_local]
+        acc = torch.tensor([float((znew * c).sum()), float((sq * np.abs(znew - zold)).sum())], dtype=torch.float64)
+        dist.all_gather_into_tensor(zfull, torch.from_numpy(znew))
+        dist.all_reduce(acc)
+        steps += 1
+        iteration = steps + 1
+        if acc[1].item() / n <= tol:
+            break
+        invS = 1.0 / (alpha * acc[0].item() + bias)
+    scores_int = zfull.numpy() * np.concatenate([np.empty(0)] + [None] * 0) if False else None
+    sq_full = torch.empty(n_global, dtype=torch.float64)
+    dist.all_gather_into_tensor(sq_full, torch.from_numpy(sq))
+    scores_user = (zfull.numpy() * sq_full.numpy() * 10.0)[new_id.numpy()][:n]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (A_loc.indptr, A_loc.indices, A_loc.nnz))
+    if rank == 0:
+        np.savez(out, new_id=new_id.numpy(), scores=scores_user, iteration=iteration,
+                 nnz=np.array([g[2] for g in gathered]),
+                 **{f"indptr{r}": gathered[r][0] for r in range(world)},
+                 **{f"indices{r}": gathered[r][1] for r in range(world)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_and_ppr(tmp_path):
+    sys.path.insert(0, ROOT)
+    from oracle import reference_port as orc
+    from pygrank_b200 import synthetic
+    world, scale = 2, 10
+    out = str(tmp_path / "dist.npz")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, scale, out), nprocs=world, join=True)
+    z = np.load(out)
+    n = 1 << scale
+    new_id = z["new_id"]
+    assert sorted(new_id.tolist()) == list(range(n)), "the relabelling must be a permutation"
+    A = synthetic.rmat_graph_host(scale, 8, seed=3)
+    P = sp.coo_matrix((np.ones(n), (new_id, np.arange(n))), shape=(n, n)).tocsr()
+    A_int = (P @ A @ P.T).tocsr()
+    A_int.sort_indices()
+    n_local = n // world
+    for r in range(world):                       # every rank holds exactly its rows of the relabelled graph
+        block = A_int[r * n_local:(r + 1) * n_local]
+        assert np.array_equal(block.indptr, z[f"indptr{r}"])
+        assert np.array_equal(block.indices, z[f"indices{r}"])
+    nnz = z["nnz"]
+    assert abs(int(nnz[0]) - int(nnz[1])) <= 0.02 * nnz.sum(), nnz   # degree-interleaving balances the ranks
+    M = orc.to_sparse_matrix(A, "symmetric", False)
+    p = np.zeros(n)
+    p[synthetic.seed_sets(n, 1, 10, seed=0)[0]] = 1.0
+    ref, iters, _ = orc.pagerank(M, p, 0.85, tol=1e-9, max_iters=1000)
+    assert int(z["iteration"]) == iters
+    assert np.abs(z["scores"] - ref).sum() / np.abs(ref).sum() < 1e-10
