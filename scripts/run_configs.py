@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Measures the BASELINE.json configs that are not the bench.py headline, each with a parity check
+against the oracle at a size the CPU finishes in seconds.  Writes gpurun_out/configs_<tag>.json.
+
+    python scripts/run_configs.py [--tag r1] [--quick]
+
+C1  PageRank(0.85, tol 1e-9) symmetric on Barabási–Albert n=100k m=5, 10 seed sets (fp64), vs oracle
+C2  HeatKernel(t=3) and GenericGraphFilter K=40 on RMAT scale 22, fp64 and fp32
+C5  32 alphas of PageRank + AbsorbingWalks on Barabási–Albert n=10M m=8 (fp32)
+(C3 batched and C4 multi-GPU are measured by their own entry points.)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rel_l1(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).sum() / np.abs(b).sum())
+
+
+def timed(fn, reps=1):
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = None
+    for _ in range(reps):
+        out = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tag", default="r1")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    import torch
+
+    import pygrank_b200 as pgb
+    from oracle import reference_port as orc
+    from pygrank_b200 import device_synthetic, synthetic
+
+    report = {"gpu": torch.cuda.get_device_name(0)}
+
+    # ---------------------------------------------------------------- C1
+    n, m = (20_000, 5) if args.quick else (100_000, 5)
+    A = synthetic.ba_graph_host(n, m, seed=1)
+    g = pgb.DeviceGraph.from_scipy(A, directed=False, normalization="symmetric")
+    M = orc.to_sparse_matrix(A, "symmetric", False)
+    seeds = synthetic.seed_sets(n, 10, 10, seed=0)
+    alg = pgb.PageRank(0.85, tol=1e-9, max_iters=1000)
+    alg(g, [int(v) for v in seeds[0]])
+    gpu_s, cpu_s, calls, worst, iters_equal = 0.0, 0.0, 0, 0.0, True
+    for s in seeds:
+        p = np.zeros(n)
+        p[s] = 1.0
+        dt, r = timed(lambda: alg(g, [int(v) for v in s]).numpy())
+        gpu_s += dt
+        t0 = time.perf_counter()
+        ref, iters, _ = orc.pagerank(M, p, 0.85, tol=1e-9, max_iters=1000)
+        cpu_s += time.perf_counter() - t0
+        calls += iters - 1
+        worst = max(worst, rel_l1(r, ref))
+        iters_equal &= (alg.convergence.iteration == iters)
+    report["C1"] = {"graph": f"BA-like n={n} m={m} (nnz {A.nnz})", "solves": 10, "conv_calls": calls,
+                    "gpu_e2e_s": gpu_s, "gpu_gteps": A.nnz * calls / gpu_s / 1e9,
+                    "cpu_oracle_s": cpu_s, "cpu_gteps": A.nnz * calls / cpu_s / 1e9,
+                    "iterations_equal": bool(iters_equal), "worst_rel_l1_fp64": worst}
+    print("C1", report["C1"], flush=True)
+
+    # ---------------------------------------------------------------- C2
+    scale = 16 if args.quick else 22
+    g = device_synthetic.rmat_graph_device(scale, 16, seed=1)
+    n = g.n
+    seeds = synthetic.seed_sets(n, 3, 10, seed=0)
+    w40 = [0.9 ** k for k in range(40)]
+    c2 = {"graph": f"RMAT scale {scale} (n {n}, nnz {g.nnz})"}
+    for dtype, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+        heat = pgb.HeatKernel(3, dtype=dtype)
+        gen = pgb.GenericGraphFilter(w40, error_type="iters", max_iters=41, dtype=dtype)
+        for label, alg in (("heat3", heat), ("generic40", gen)):
+            alg(g, [int(v) for v in seeds[0]])
+            dt, _ = timed(lambda: [alg(g, [int(v) for v in s]) for s in seeds])
+            calls = (alg.convergence.iteration - 1) * len(seeds)
+            c2[f"{label}_{name}"] = {"iterations": alg.convergence.iteration, "s_per_solve": dt / len(seeds),
+                                     "gteps": g.nnz * calls / dt / 1e9}
+    # parity at a CPU-sized scale
+    ps = 16
+    gs = device_synthetic.rmat_graph_device(ps, 16, seed=1)
+    Ms = orc.to_sparse_matrix(synthetic.rmat_graph_host(ps, 16, seed=1), "symmetric", False)
+    p = np.zeros(1 << ps)
+    p[synthetic.seed_sets(1 << ps, 1, 10, seed=0)[0]] = 1.0
+    for label, mk, ref_fn in (("heat3", lambda dt: pgb.HeatKernel(3, dtype=dt), lambda: orc.heat_kernel(Ms, p, 3)),
+                              ("generic40", lambda dt: pgb.GenericGraphFilter(w40, error_type="iters", max_iters=41, dtype=dt),
+                               lambda: orc.generic_filter(Ms, p, w40, error_type="iters", max_iters=41))):
+        ref, iters, _ = ref_fn()
+        a64, a32 = mk(torch.float64), mk(torch.float32)
+        r64, r32 = a64(gs, p).numpy(), a32(gs, p).numpy()
+        c2[f"parity_{label}"] = {"scale": ps, "iterations_equal": a64.convergence.iteration == iters,
+                                 "rel_l1_fp64": rel_l1(r64, ref), "rel_l1_fp32": rel_l1(r32, ref)}
+    report["C2"] = c2
+    print("C2", c2, flush=True)
+
+    # ---------------------------------------------------------------- C5
+    n, m = (200_000, 8) if args.quick else (10_000_000, 8)
+    t0 = time.perf_counter()
+    g = device_synthetic.ba_graph_device(n, m, seed=1)
+    torch.cuda.synchronize()
+    build = time.perf_counter() - t0
+    seeds = synthetic.seed_sets(n, 1, 10, seed=0)[0]
+    alphas = np.linspace(0.5, 0.99, 32)
+    algs = [pgb.PageRank(float(a), tol=1e-9, max_iters=2000, dtype=torch.float32) for a in alphas]
+    algs[0](g, [int(v) for v in seeds])
+    dt, _ = timed(lambda: [a(g, [int(v) for v in seeds]) for a in algs])
+    calls = sum(a.convergence.iteration - 1 for a in algs)
+    ab = pgb.AbsorbingWalks(0.85, tol=1e-9, max_iters=2000, dtype=torch.float32)
+    dta, _ = timed(lambda: ab(g, [int(v) for v in seeds]))
+    report["C5"] = {"graph": f"BA-like n={n} m={m} (nnz {g.nnz})", "build_s": build, "sweep_32_alphas_s": dt,
+                    "sweep_conv_calls": calls, "sweep_gteps": g.nnz * calls / dt / 1e9,
+                    "absorbing_iterations": ab.convergence.iteration, "absorbing_s": dta,
+                    "absorbing_gteps": g.nnz * (ab.convergence.iteration - 1) / dta / 1e9}
+    print("C5", report["C5"], flush=True)
+
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"configs_{args.tag}.json"), "w") as f:
+        json.dump(report, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
