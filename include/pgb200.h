@@ -197,6 +197,19 @@ int pgb_poly_steps(const pgb_csr *g, int dtype, const void *w, const void *sq, c
                    int32_t *state_i32, double *err_hist, pgb_span_ws ws, int first_step, int num_launches,
                    int finalize, void *stream);
 
+/* K3 — batched affine recursion (NodeRanking.propagate, core/signals.py:225-226, as one SpMM-like
+ * pass): PB = pgb_panel_width(dtype) seed columns (8 x fp32 / 4 x fp64 = one 32-byte sector per node)
+ * advance together.  Vectors z, q are [n][PB] row-major; w/sq/c are per-row as in pgb_affine_steps.
+ * state_f64 is [PB][PGB_STATE_F64_LEN]; state_i32 is [PB][PGB_STATE_I32_LEN] followed by one shared
+ * ticket word; err_hist is [PB][hist_stride].  A column whose STOP != RUNNING is frozen (z' = z), so
+ * every column ends at the iteration where the reference's per-column loop would have stopped.
+ * span workspace: acc [n_tiles][PB] doubles, cnt [n_tiles]. */
+int pgb_panel_width(int dtype);
+int pgb_affine_steps_batched(const pgb_csr *g, int dtype, double alpha, const void *w, const void *sq, const void *c,
+                             const void *q, void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64,
+                             int32_t *state_i32, double *err_hist, int32_t hist_stride, pgb_span_ws ws,
+                             int first_step, int num_launches, void *stream);
+
 /* One-thread state update for the deferred (multi-GPU) mode. */
 int pgb_state_finalize(double *state_f64, int32_t *state_i32, double *err_hist, void *stream);
 

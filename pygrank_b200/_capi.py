@@ -66,6 +66,10 @@ _SIGNATURES = {
                                  c_void_p]),
     "pgb_poly_steps": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, c_int, c_int, c_void_p]),
+    "pgb_panel_width": (c_int, [c_int]),
+    "pgb_affine_steps_batched": (c_int, [POINTER(Csr), c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, SpanWs,
+                                         c_int, c_int, c_void_p]),
     "pgb_state_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgb_scale": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "pgb_unscale": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),

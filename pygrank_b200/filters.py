@@ -160,11 +160,26 @@ class GraphFilter:
         return RankResult(g, out)
 
     def propagate(self, graph, features, *args, **kwargs) -> torch.Tensor:
-        """``NodeRanking.propagate`` (signals.py:225-226): one rank per feature column."""
+        """``NodeRanking.propagate`` (signals.py:225-226): one rank per feature column.  Filters
+        with a batched kernel (``_run_batched``) advance a panel of columns per pass over the CSR;
+        the others run column by column like the reference."""
         g = self.preprocessor(graph)
+        if not isinstance(g, DeviceGraph):
+            g = as_device_graph(g)
         cols = features if isinstance(features, torch.Tensor) else torch.as_tensor(np.asarray(features))
-        outs = [self.rank(g, cols[:, c].contiguous(), *args, **kwargs).np for c in range(cols.shape[1])]
+        if cols.dim() != 2 or cols.shape[0] != g.n:
+            raise Exception("propagate expects a features matrix with one row per node")
+        if self._can_batch(g, *args, **kwargs):
+            return self._propagate_batched(g, cols, *args, **kwargs)
+        self.convergence.iterations = []
+        outs = []
+        for c in range(cols.shape[1]):
+            outs.append(self.rank(g, cols[:, c].contiguous(), *args, **kwargs).np)
+            self.convergence.iterations.append(self.convergence.iteration)
         return torch.stack(outs, dim=1)
+
+    def _can_batch(self, g, *args, **kwargs) -> bool:
+        return False
 
     # -- machinery shared by the subclasses ---------------------------------------------------
     def _new_state(self, g: DeviceGraph, norm: float, alpha_s: float, quotient: bool):
@@ -225,6 +240,125 @@ class RecursiveGraphFilter(GraphFilter):
             raise Exception("the fused filters take use_quotient=True/False (postprocessor quotients run on the plugin path)")
         self.use_quotient = bool(use_quotient)
 
+    def _affine_args(self, g: DeviceGraph, **kwargs) -> dict:
+        """alpha, alpha_s, w_run, c_run, coef, coefvec of the affine recursion (per derived filter)."""
+        raise Exception("Use a derived class of RecursiveGraphFilter")
+
+    def _run(self, g, p, norm, warm, **kwargs):
+        return self._affine(g, p, norm, warm, **self._affine_args(g, **kwargs))
+
+    def _can_batch(self, g, warm_start=None, graph_dropout: float = 0, **kwargs) -> bool:
+        # the panel kernel streams no edge values (every BASELINE config is unweighted)
+        return (not g.in_view.weighted) and warm_start is None and graph_dropout == 0 and not g.pathological
+
+    def _propagate_batched(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
+        """All feature columns through ``pgb_affine_steps_batched``: panels of ``pgb_panel_width``
+        columns share one pass over the index stream per iteration; every column keeps its own
+        normaliser, error and stop decision, so results and iteration counts equal the reference's
+        column-by-column loop (signals.py:225-226)."""
+        lib = C.lib()
+        dtype, code = self.dtype, dtype_code(self.dtype)
+        f64 = torch.float64
+        dev, n = g.out_view.indptr.device, g.n
+        st = C.stream_ptr()
+        cm = self.convergence
+        B = int(cols.shape[1])
+        PB = lib.pgb_panel_width(code)
+        a = self._affine_args(g, **kwargs)
+        alpha, alpha_s, w_run, c_run, coef, coefvec = (a["alpha"], a["alpha_s"], a["w_run"], a["c_run"], a["coef"],
+                                                       a["coefvec"])
+        sq = g.vec("sq", dtype)
+        c = c_run if c_run is not None else g.vec("c", dtype)
+        symdeg = g.symdeg and w_run is None
+        w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
+        sq_arg = None if symdeg else sq
+        view = g.in_view
+        cs = view.cstruct(dtype)
+        err_code = _error_code(cm.error_type)
+        tol = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))
+        perm = None if g.perm is None else g.perm.long()
+        out = torch.empty((n, B), dtype=dtype, device=dev)
+        acc = torch.zeros(max(view.n_tiles, 1) * PB, dtype=f64, device=dev)
+        cnt = torch.zeros(max(view.n_tiles, 1), dtype=torch.int32, device=dev)
+        ws = (acc, cnt)
+        hist = cm.max_iters + 2
+        budget = cm.max_iters - 1
+        iterations, errors = [], []
+        t0 = time.perf_counter()
+        for c0 in range(0, B, PB):
+            nb = min(PB, B - c0)
+            pp = cols[:, c0:c0 + nb].to(device=dev, dtype=dtype)
+            if perm is not None:
+                pp = pp[perm]
+            norms = pp.abs().sum(dim=0, dtype=f64)                              # abstract_filters.py:52
+            live = norms > 0
+            pn = (pp.to(f64) / torch.where(live, norms, torch.ones_like(norms))).to(dtype)   # :55
+            del pp
+            zbuf = [torch.zeros((n, PB), dtype=dtype, device=dev), torch.zeros((n, PB), dtype=dtype, device=dev)]
+            q = torch.zeros((n, PB), dtype=dtype, device=dev)
+            zbuf[0][:, :nb] = pn / sq[:, None]
+            qc = coefvec.to(f64)[:, None] if coefvec is not None else float(coef)
+            q[:, :nb] = (qc * pn.to(f64)).to(dtype) / sq[:, None]
+            del pn
+            tacc = (zbuf[0].to(f64) * c.to(f64)[:, None]).sum(dim=0)
+            bias = (q.to(f64) * sq.to(f64)[:, None]).sum(dim=0)
+            sf = torch.zeros((PB, C.STATE_LEN), dtype=f64, device=dev)
+            sf[:, C.SF_ALPHA] = float(alpha_s)
+            sf[:, C.SF_BIAS] = bias
+            sf[:, C.SF_INVS] = 1.0 / (float(alpha_s) * tacc + bias) if self.use_quotient else 1.0
+            sf[:, C.SF_TOL] = tol
+            sf[:, C.SF_MEAN] = 1.0 if err_code == C.ERR_L1 else float(n)
+            sf[:nb, C.SF_NORM] = norms
+            si_host = np.zeros((PB, C.STATE_LEN), dtype=np.int32)
+            si_host[:, C.SI_MAX_ITERS] = cm.max_iters
+            si_host[:, C.SI_END_MODULO] = max(cm.end_modulo, 1)
+            si_host[:, C.SI_ERR_MODE] = err_code
+            si_host[:, C.SI_QUOTIENT] = int(self.use_quotient)
+            live_host = live.cpu().numpy()
+            si_host[:, C.SI_STOP] = C.CONVERGED                                 # padding / zero columns never run
+            si_host[:nb, C.SI_STOP] = np.where(live_host, C.RUNNING, C.CONVERGED)
+            si = torch.from_numpy(np.concatenate([si_host.reshape(-1), np.zeros(1, np.int32)])).to(dev)
+            err_hist = torch.zeros((PB, hist), dtype=f64, device=dev)
+            C.count_launches(1)
+            done, chunk = 0, max(self.chunk, 1)
+            host = si_host
+            while done < budget and (host[:, C.SI_STOP] == C.RUNNING).any():
+                k = min(chunk, budget - done)
+                C.check(lib.pgb_affine_steps_batched(ctypes.byref(cs), code, float(alpha), C.ptr(w), C.ptr(sq_arg),
+                                                     C.ptr(c), C.ptr(q), C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(sf),
+                                                     C.ptr(si), C.ptr(err_hist), hist, span_struct(ws), done + 1, k, st))
+                C.count_launches(k)
+                done += k
+                host = si.cpu().numpy()[:PB * C.STATE_LEN].reshape(PB, C.STATE_LEN)
+                chunk = min(chunk * 2, 64)
+            steps = host[:, C.SI_STEPS]
+            final = zbuf[int(steps.max()) & 1]
+            scale = torch.where(live, norms, torch.ones_like(norms)) if self.preserve_norm else torch.ones_like(norms)
+            res = final[:, :nb] * sq[:, None] * scale.to(dtype)[None, :]
+            if perm is not None:
+                out[perm, c0:c0 + nb] = res
+            else:
+                out[:, c0:c0 + nb] = res
+            hist_host = None
+            for j in range(nb):
+                if not live_host[j]:                                            # abstract_filters.py:53-54
+                    iterations.append(0)
+                    errors.append(None)
+                    continue
+                stop, it = int(host[j, C.SI_STOP]), int(host[j, C.SI_ITERATION])
+                if stop == C.RUNNING:                                           # max_iters <= 1
+                    stop, it = C.MAX_ITERS, 1
+                iterations.append(it)
+                errors.append(err_hist[j, 1:int(steps[j]) + 1])
+                if stop == C.MAX_ITERS and err_code != C.ERR_ITERS and cm.iter_exception is not None:
+                    raise cm.iter_exception("Could not converge within " + str(cm.max_iters) + " iterations")
+        cm.iterations = iterations
+        cm.iteration = iterations[-1] if iterations else 0
+        cm.errors = errors[-1] if errors else None
+        cm.column_errors = errors
+        cm.elapsed_time = time.perf_counter() - t0
+        return out
+
     def _affine(self, g: DeviceGraph, p, norm, warm, alpha: float, alpha_s: float, w_run, c_run, coef, coefvec):
         lib = C.lib()
         dtype, code = self.dtype, dtype_code(self.dtype)
@@ -267,9 +401,8 @@ class PageRank(RecursiveGraphFilter):
         self.alpha = alpha
         super().__init__(*args, **kwargs)
 
-    def _run(self, g, p, norm, warm, **kwargs):
-        return self._affine(g, p, norm, warm, alpha=self.alpha, alpha_s=self.alpha, w_run=None, c_run=None,
-                            coef=1 - self.alpha, coefvec=None)
+    def _affine_args(self, g, **kwargs):
+        return dict(alpha=self.alpha, alpha_s=self.alpha, w_run=None, c_run=None, coef=1 - self.alpha, coefvec=None)
 
 
 class AbsorbingWalks(RecursiveGraphFilter):
@@ -280,10 +413,10 @@ class AbsorbingWalks(RecursiveGraphFilter):
         super().__init__(*args, **kwargs)
         self.alpha = alpha
 
-    def _run(self, g, p, norm, warm, absorption=None, **kwargs):
+    def _affine_args(self, g, absorption=None, **kwargs):
         dtype = self.dtype
         f64 = torch.float64
-        dev = p.device
+        dev = g.out_view.indptr.device
         rate = (1 - self.alpha) / self.alpha                  # adhoc.py:158
         if absorption is None:
             ab = torch.full((g.n,), rate, dtype=f64, device=dev)
@@ -297,8 +430,7 @@ class AbsorbingWalks(RecursiveGraphFilter):
         coefvec = (ab / denom).to(dtype)                      # coefficient of the personalization
         gsum = g._spmv_raw(g.out_view, g.R * d1, g.L, f64)    # rowsum of M*diag(d1): next normaliser is linear
         c_run = (g.vec("sq", f64) * gsum).to(dtype)
-        return self._affine(g, p, norm, warm, alpha=1.0, alpha_s=1.0, w_run=w_run, c_run=c_run, coef=0.0,
-                            coefvec=coefvec)
+        return dict(alpha=1.0, alpha_s=1.0, w_run=w_run, c_run=c_run, coef=0.0, coefvec=coefvec)
 
 
 class ClosedFormGraphFilter(GraphFilter):

@@ -247,6 +247,67 @@ def test_custom_absorption_and_propagate(pgb, torch_cuda, name):
     assert rel_l1(out.cpu().numpy(), z["run_propagate_ppr85"]) <= FP64_TOL
 
 
+@pytest.mark.parametrize("name", GOLDEN_GRAPHS)
+@pytest.mark.parametrize("run", ["ppr85", "ppr90_noq", "ppr85_col", "ppr85_l1", "ppr85_msq", "ppr85_tol6_mod3",
+                                 "absorb85", "absorb85_col"])
+@pytest.mark.parametrize("relabel", ["degree", "none"])
+def test_batched_propagate_matches_golden(pgb, torch_cuda, name, run, relabel):
+    """propagate() through the panel kernel (pgb_affine_steps_batched): every column must stop at the
+    reference's own iteration count and match its scores (signals.py:225-226 runs them one by one)."""
+    torch = torch_cuda
+    z, A, directed = load_golden(name)
+    norm, make, _ = _runs(pgb)[run]
+    g = _graph(pgb, A, directed, norm, relabel)
+    P = z["P"]
+    alg = make({"dtype": torch.float64})
+    out = alg.propagate(g, P).cpu().numpy()
+    assert list(alg.convergence.iterations) == [int(v) for v in z[f"run_{run}_iters"]], (name, run)
+    for c in range(P.shape[1]):
+        assert rel_l1(out[:, c], z[f"run_{run}_scores"][:, c]) <= FP64_TOL, (name, run, c)
+    if run not in ("ppr85", "ppr85_col", "absorb85"):
+        return          # tolerances below the fp32 noise floor (L1 1e-7, MSQ 1e-16) are fp64-only cases
+    alg32 = make({"dtype": torch.float32})
+    out32 = alg32.propagate(g, P).cpu().numpy()
+    for c in range(P.shape[1]):
+        assert abs(alg32.convergence.iterations[c] - int(z[f"run_{run}_iters"][c])) <= 1
+        assert rel_l1(out32[:, c], z[f"run_{run}_scores"][:, c]) <= FP32_TOL, (name, run, c)
+
+
+@pytest.mark.parametrize("dtype_name,tol", [("float64", 1e-12), ("float32", 2e-6)])
+def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, dtype_name, tol):
+    """11 columns (one full panel + a ragged one), one all-zero column, columns that converge at
+    different iterations; the batched result must equal the single-column fused path."""
+    torch = torch_cuda
+    from pygrank_b200 import synthetic, device_synthetic
+    dtype = getattr(torch, dtype_name)
+    scale = 17
+    n = 1 << scale
+    src, dst = device_synthetic.rmat_edges_device(scale, 16, seed=4)
+    g = pgb.DeviceGraph.from_edges(n, src, dst, directed=False, drop_self_loops=True, binary=True,
+                                   normalization="symmetric")
+    assert not g.in_view.weighted
+    rng = np.random.default_rng(5)
+    B = 11
+    P = np.zeros((n, B))
+    for c in range(B):
+        if c == 4:
+            continue                                    # zero personalization: returned untouched, 0 iterations
+        k = [1, 10, 1000, n // 2][c % 4]
+        P[rng.choice(n, k, replace=False), c] = rng.uniform(0.5, 2.0, k)
+    alg = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=dtype)
+    out = alg.propagate(g, torch.from_numpy(P).cuda())
+    its = list(alg.convergence.iterations)
+    assert out.shape == (n, B) and its[4] == 0 and not bool(out[:, 4].any())
+    assert len(set(its)) > 2                            # the panel really freezes columns at different steps
+    for c in range(B):
+        one = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=dtype)
+        ref = one(g, P[:, c]).np
+        assert abs(one.convergence.iteration - its[c]) <= (0 if dtype == torch.float64 else 1), (c, its)
+        assert rel_l1(out[:, c].cpu().numpy(), ref.cpu().numpy()) <= tol, c
+    with pytest.raises(Exception, match="Could not converge within 4 iterations"):
+        pgb.PageRank(0.99, tol=1e-14, max_iters=4, dtype=dtype).propagate(g, torch.from_numpy(P).cuda())
+
+
 def test_personalization_forms_and_edge_cases(pgb, torch_cuda):
     torch = torch_cuda
     z, A, directed = load_golden("ba2000")
