@@ -232,7 +232,8 @@ def run_single(args):
                                 C.ptr(zbuf[0]), C.ptr(q), C.ptr(state_f64), st))
     C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
     cs = g.in_view.cstruct(dtype)
-    ws = g.in_view.new_span_ws()
+    ws = g.in_view.new_span_ws(dtype)
+    form = g.in_view.hsell(dtype)
     symdeg = g.symdeg
     wv = None if symdeg else g.vec("w", dtype)
     sqa = None if symdeg else sq
@@ -281,11 +282,19 @@ def run_single(args):
                 "d2h_bytes_per_step": n * w + 64 * 2},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "warp_tile_kernel<%s,unweighted,AFFINE,SYMDEG=%s>" % (args.dtype, symdeg),
+                     "traffic": None,
+                     "kernel": ("hsell_gather_kernel<%s> + hsell_update_kernel<%s,AFFINE,SYMDEG=%s> (one step)"
+                                if form is not None else "item_stream_kernel<%s,unweighted,AFFINE,SYMDEG=%s>")
+                     % ((args.dtype, args.dtype, symdeg) if form is not None else (args.dtype, symdeg)),
                      "kernel_ms": kernel_ms, "kernel_gteps": nnz / (kernel_ms * 1e-3) / 1e9,
                      "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                      "gather_probe_ms": probe_ms, "gather_probe_gteps": nnz / (probe_ms * 1e-3) / 1e9,
-                     "frac_of_gather_probe": probe_ms / kernel_ms},
+                     "frac_of_gather_probe": probe_ms / kernel_ms,
+                     "hsell": None if form is None else {
+                         "block_cols": form.block_cols, "n_blocks": form.n_blocks, "hub_chunks": form.n_hub_chunks,
+                         "tail_chunks": form.n_tail_chunks, "hub_slots": form.n_hub_words * 2,
+                         "tail_slots": form.n_tail_words, "partial_rows": form.n_partials,
+                         "heavy_slices": form.n_heavy, "bytes": form.nbytes()}},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PGB_ABI_VERSION 1
+#define PGB_ABI_VERSION 2
 
 enum { PGB_F32 = 0, PGB_F64 = 1 };
 
@@ -74,13 +74,62 @@ typedef struct pgb_csr {
     int32_t tile_items;      /* must equal pgb_tile_items()               */
     const int32_t *istream;  /* [n+nnz] item stream: each row's indices then -1-deg (pgb_build_item_stream) */
     const void *vstream;     /* [n+nnz] weights at the same positions (dtype) or NULL                      */
+    const struct pgb_hsell *hsell; /* hub-blocked sliced-ELL form (HOST pointer to the struct) or NULL     */
 } pgb_csr;
+
+/* Hub-blocked sliced-ELL form of an UNWEIGHTED pull CSR whose nodes are ranked by degree (built once
+ * per graph and vector dtype with pgb_hsell_count + pgb_hsell_fill).  Rows are cut into slices of 32
+ * (one lane per row); columns into n_blocks "hub blocks" of block_cols columns — what one SM keeps of
+ * the gather vector in shared memory — and a tail.  The entries of (slice, block) form a UNIT of
+ * `rounds` rounds, stored [round][lane]: a hub round is one 32-bit word per lane holding two 16-bit
+ * block-local columns (block_cols = padding), a tail round one 32-bit global column per lane (-1 =
+ * padding).  The units of a block (slices ascending), then of the next block, form one stream of rounds
+ * (each block padded to a whole chunk); the tail units form a second stream.  Streams are cut into
+ * CHUNKS of PGB_HSELL_CHUNK rounds, the unit of work of one warp: chunk c starts at word c*32*CHUNK,
+ * carries the rounds at which a unit ends inside it (endmask) and the partial row its first piece
+ * writes (p_first); a piece ends at every unit end and at the chunk end, and every piece writes one
+ * partial row of 32 sums.  slice_parts[slice_ptr[s] .. slice_ptr[s+1]) lists the partial rows of slice
+ * s for the update pass.  A slice whose pieces number more than heavy_parts (hub rows: their units span
+ * many chunks) is first reduced by groups of 32 partial rows into second-level partial rows
+ * (reduce_items / reduce_parts) and lists those instead; if it still lists more than heavy_parts it is
+ * also named in heavy_slices (one CTA adds them).  Chunks are dealt to
+ * n_ctas CTAs in contiguous ranges (cta_*_begin).  With n_segments > 1 (row-partitioned multi-GPU) the
+ * gather vector is n_segments ranges of seg_len entries (one per rank, each degree-ranked), hub block b
+ * is the union of entries [b*block_cols/n_segments, ...) of every range, and the CSR given to the
+ * builders uses the virtual column b*block_cols + segment*(block_cols/n_segments) + offset-in-block. */
+#define PGB_HSELL_CHUNK 32
+typedef struct pgb_hsell {
+    int64_t n_rows;          /* local rows                                    */
+    int64_t n_slices;        /* ceil(n_rows / 32)                             */
+    int64_t n_partials;      /* partial rows (32 values each)                 */
+    int64_t seg_len;         /* entries per segment of the gather vector      */
+    int32_t n_segments;
+    int32_t block_cols;      /* H (<= 65535)                                  */
+    int32_t n_blocks;        /* K                                             */
+    int32_t n_ctas;          /* CTAs the schedule was cut for                 */
+    int32_t n_hub_chunks, n_tail_chunks;
+    int32_t n_heavy, heavy_parts;     /* slices listing more than heavy_parts partial rows          */
+    int32_t n_reduce, reserved0;      /* second-level reduction items (groups of <= 32 partial rows) */
+    const uint32_t *hub_chunks;       /* [n_hub_chunks][2]: p_first, endmask                        */
+    const uint32_t *tail_chunks;      /* [n_tail_chunks][2]: p_first, endmask                       */
+    const uint32_t *hub_words;        /* [n_hub_chunks*CHUNK*32]                                    */
+    const int32_t *tail_cols;         /* [n_tail_chunks*CHUNK*32]                                   */
+    const int32_t *slice_ptr;         /* [n_slices+1]                                               */
+    const int32_t *slice_parts;       /* [slice_ptr[n_slices]] partial rows of each slice           */
+    const int32_t *heavy_slices;      /* [n_heavy]                                                  */
+    const int32_t *reduce_items;      /* [n_reduce][3]: first entry of reduce_parts, count, output partial row */
+    const int32_t *reduce_parts;      /* partial rows (first level) of the slices reduced in two levels */
+    const int32_t *block_chunk_begin; /* [n_blocks+1] first hub chunk of each block                 */
+    const int32_t *cta_hub_begin;     /* [n_ctas+1]                                                 */
+    const int32_t *cta_tail_begin;    /* [n_ctas+1]                                                 */
+} pgb_hsell;
 
 /* Cross-tile workspace of one running filter: rows that straddle merge-path tiles are
  * completed by the last tile to arrive.  Zero-filled by the caller once; self-resetting. */
 typedef struct pgb_span_ws {
     double *acc;        /* [n_tiles * ncols]  */
     uint32_t *cnt;      /* [n_tiles]          */
+    void *partials;     /* [hsell.n_partials][32] of the vector dtype when the graph has an hsell form, else NULL */
 } pgb_span_ws;
 
 /* Device-resident iteration state (mirror of ConvergenceManager, convergence.py:24-101). */
@@ -121,7 +170,8 @@ int pgb_build_item_stream(int64_t n, int64_t nnz, const int32_t *indptr, const i
  * kernel's phase 2, and nothing else — the measured ceiling of any row-gather formulation for this
  * graph (bench.py reports the fused kernel against it).  scratch: >= 8 bytes. */
 int pgb_gather_probe(const pgb_csr *g, int dtype, const void *z, void *scratch, void *stream);
-/* 3 (default): warp tiles over the item stream; 2: warp tiles over CSR; 1: CTA-wide tiles (A/B timing). */
+/* 4 (default): hsell when the graph carries that form, else 3; 3: warp tiles over the item stream;
+ * 2: warp tiles over CSR; 1: CTA-wide tiles (A/B timing). */
 int pgb_set_kernel_variant(int variant);
 
 /* ---- synthetic graphs (bench/tests; no reference counterpart, graphs are downloaded in
@@ -149,6 +199,27 @@ int pgb_degree_order(int64_t n, const int32_t *indptr, void *workspace, size_t w
 int pgb_relabel_coo(int64_t nnz, const int32_t *iperm, int32_t *row, int32_t *col, void *stream);
 int pgb_mergepath_partition(int64_t n, int64_t nnz, const int32_t *indptr, int32_t n_tiles,
                             int32_t *tile_row, void *stream);
+
+/* ---- hub-blocked sliced-ELL builders (no reference counterpart: the reference hands scipy's CSR to
+ *      csc_matvec as is, core/backend/numpy.py:64-65) ------------------------------------------------ */
+/* Largest block_cols the gather kernel can keep in shared memory for this dtype (0: unknown dtype). */
+int pgb_hsell_max_block_cols(int dtype);
+/* Pass 1 — one warp per slice: hub_rounds[b*n_slices+s] = rounds (2 entries each) of the unit of
+ * slice s in block b, or 0 when the slice has fewer than min_entries entries there (they stay in the
+ * tail); tail_rounds[s] = longest tail row of the slice. */
+int pgb_hsell_count(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
+                    int32_t min_entries, int32_t *hub_rounds, int32_t *tail_rounds, void *stream);
+/* Pass 2 — writes the round data and slice_parts.  The caller supplies, per (block, slice) in
+ * block-major order and per slice for the tail: the first round of the unit in its stream and the
+ * partial row of its first piece (exclusive scans); hub_words must be pre-filled with the padding word
+ * (block_cols | block_cols << 16). */
+int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
+                   int32_t n_segments, int64_t seg_len, const int32_t *hub_rounds, const int32_t *tail_rounds,
+                   const int64_t *hub_round_base, const int64_t *hub_part_base, const int64_t *tail_round_base,
+                   const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
+                   int32_t *slice_parts, void *stream);
+/* Experiment knob: warps (of 32) per CTA that prefer tail units (L2 gathers) over hub units. */
+int pgb_hsell_set_tail_warps(int warps);
 
 /* ---- K1/K7: degrees and normalisation (preprocessing.py:104-138; numpy.py:76-77) ----- */
 /* out[i] = sum of values (or entry count when values == NULL) of row i, fp64 */

@@ -23,16 +23,29 @@ RUNNING, CONVERGED, MAX_ITERS = 0, 1, 2
 SF_ALPHA, SF_BIAS, SF_INVS, SF_TACC, SF_EACC, SF_TOL, SF_MEAN, SF_LASTERR, SF_NORM, SF_PSUM = range(10)
 SI_TICKET, SI_STEPS, SI_STOP, SI_ITERATION, SI_MAX_ITERS, SI_END_MODULO, SI_ERR_MODE, SI_QUOTIENT = range(8)
 STATE_LEN = 16
+HSELL_CHUNK = 32   # PGB_HSELL_CHUNK: rounds per chunk of the hsell streams
 
 
 class Csr(Structure):
     _fields_ = [("n", c_int64), ("nnz", c_int64), ("indptr", c_void_p), ("indices", c_void_p), ("values", c_void_p),
                 ("tile_row", c_void_p), ("n_tiles", c_int32), ("tile_items", c_int32), ("istream", c_void_p),
-                ("vstream", c_void_p)]
+                ("vstream", c_void_p), ("hsell", c_void_p)]
+
+
+class Hsell(Structure):
+    """pgb_hsell (include/pgb200.h): hub-blocked sliced-ELL form of an unweighted pull CSR."""
+    _fields_ = [("n_rows", c_int64), ("n_slices", c_int64), ("n_partials", c_int64), ("seg_len", c_int64),
+                ("n_segments", c_int32), ("block_cols", c_int32), ("n_blocks", c_int32), ("n_ctas", c_int32),
+                ("n_hub_chunks", c_int32), ("n_tail_chunks", c_int32), ("n_heavy", c_int32), ("heavy_parts", c_int32),
+                ("n_reduce", c_int32), ("reserved0", c_int32),
+                ("hub_chunks", c_void_p), ("tail_chunks", c_void_p), ("hub_words", c_void_p), ("tail_cols", c_void_p),
+                ("slice_ptr", c_void_p), ("slice_parts", c_void_p), ("heavy_slices", c_void_p),
+                ("reduce_items", c_void_p), ("reduce_parts", c_void_p),
+                ("block_chunk_begin", c_void_p), ("cta_hub_begin", c_void_p), ("cta_tail_begin", c_void_p)]
 
 
 class SpanWs(Structure):
-    _fields_ = [("acc", c_void_p), ("cnt", c_void_p)]
+    _fields_ = [("acc", c_void_p), ("cnt", c_void_p), ("partials", c_void_p)]
 
 
 _SIGNATURES = {
@@ -41,6 +54,12 @@ _SIGNATURES = {
     "pgb_tile_items": (c_int, []),
     "pgb_device_sm_count": (c_int, [c_int]),
     "pgb_set_kernel_variant": (c_int, [c_int]),
+    "pgb_hsell_max_block_cols": (c_int, [c_int]),
+    "pgb_hsell_set_tail_warps": (c_int, [c_int]),
+    "pgb_hsell_count": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "pgb_hsell_fill": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
     "pgb_build_item_stream": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "pgb_gather_probe": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p]),
@@ -114,11 +133,15 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.pgb_abi_version() != 1:
+        if handle.pgb_abi_version() != 2:
             raise Exception("libpgb200.so ABI version mismatch")
         variant = os.environ.get("PGB_KERNEL_VARIANT")
-        if variant:   # A/B timing aid: 1 = CTA-wide tiles, 2 = warp tiles (default)
+        if variant:   # A/B timing aid: 1 = CTA-wide tiles, 2 = warp tiles, 3 = item stream, 4 = hsell (default)
             if handle.pgb_set_kernel_variant(int(variant)) != 0:
+                raise Exception("pgb200: " + handle.pgb_last_error().decode())
+        tail_warps = os.environ.get("PGB_HSELL_TAIL_WARPS")
+        if tail_warps:
+            if handle.pgb_hsell_set_tail_warps(int(tail_warps)) != 0:
                 raise Exception("pgb200: " + handle.pgb_last_error().decode())
         _lib = handle
     return _lib

@@ -1,0 +1,600 @@
+// Hub-blocked sliced-ELL (hsell) — the per-iteration gather of the hot path for unweighted graphs,
+// organised around what the measurements of round 1 showed: a scattered 4-byte gather from
+// global memory costs one L1 wavefront (~1 cycle per SM) whether it hits or misses, so a CSR
+// row-gather is capped near 270 G gathers/s no matter how little HBM traffic it causes, while a
+// shared-memory gather costs ~0.11 cycle (128 B/clk/SM over 32 banks, ~3.5-way conflicts on random
+// addresses).  On degree-ranked power-law graphs a few hundred thousand hub columns carry 80-90 % of
+// the entries, so:
+//
+//   * columns are cut into hub blocks of `block_cols` (what fits in the 227 KB of shared memory);
+//     a CTA loads one block of the gather vector z with coalesced 16-byte loads and serves every
+//     entry of that block from shared memory; entries are stored as 16-bit block-local columns
+//     (half the index bytes of CSR);
+//   * rows are cut into slices of 32, one lane per row, entries stored [round][lane]: index loads are
+//     coalesced, every lane accumulates privately, there is no segmented reduction and no per-row
+//     bookkeeping in the inner loop (degree ranking makes neighbouring rows equally long);
+//   * what is left (the tail: columns past the hub blocks, and slices too sparse in a block to be
+//     worth a unit) is gathered from L2 by "tail units" — on other warps of the same CTA, so the
+//     L1-wavefront-bound tail and the shared-memory-bound hub work overlap;
+//   * the rounds of all (slice, block) units form one stream per kind, cut into chunks of 32 rounds —
+//     the uniform unit of work of a warp (no per-unit latency chain, exact load balance); a piece of
+//     a unit (it ends at the unit's last round or at the chunk end) writes one 128-byte row of
+//     partial sums; a second light kernel adds the partial rows of each slice and applies the fused
+//     filter update + convergence reduction (RowUpdate).
+//
+// Replaces, per iteration, the same reference sequence as spmv_fused.cu: conv
+// (/root/reference/pygrank/core/backend/numpy.py:64-65), the filter formula (algorithms/filters/adhoc.py:34-36,
+// 166-169; abstract_filters.py:225-256), the quotient (abstract_filters.py:126-136) and the convergence
+// check (algorithms/convergence.py:77-101).
+#include <stdlib.h>
+
+#include "step_common.cuh"
+
+namespace pgb {
+
+constexpr int HS_THREADS = 1024;
+constexpr int HS_WARPS = HS_THREADS / 32;
+constexpr int HS_SMEM_LIMIT = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100a
+constexpr int UPD_BLOCK = 256;
+constexpr int UPD_MIN_CTAS = 6;
+
+static int g_tail_warps = 8;
+
+__device__ __forceinline__ unsigned ld_stream_u32(const uint32_t *p) { return __ldcs(p); }
+
+// ---------------------------------------------------------------------------------------------
+// builders
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_i32(const int32_t *__restrict__ a, int lo, int hi, int key) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void hsell_count_kernel(int64_t n, int64_t n_slices, const int32_t *__restrict__ indptr,
+                                   const int32_t *__restrict__ indices, int H, int K, int min_entries,
+                                   int32_t *__restrict__ hub_rounds, int32_t *__restrict__ tail_rounds) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned FULL = 0xffffffffu;
+    for (int64_t s = warp; s < n_slices; s += nwarps) {
+        const int64_t row = s * 32 + lane;
+        int b = 0, e = 0;
+        if (row < n) {
+            b = indptr[row];
+            e = indptr[row + 1];
+        }
+        int pos = b, tail_len = 0;
+        for (int blk = 0; blk < K; ++blk) {
+            const int nxt = lower_bound_i32(indices, pos, e, (blk + 1) * H);
+            const int len = nxt - pos;
+            pos = nxt;
+            const int ent = __reduce_add_sync(FULL, len);
+            const int mx = __reduce_max_sync(FULL, len);
+            const bool use = ent >= min_entries && ent > 0;
+            if (lane == 0) hub_rounds[(int64_t)blk * n_slices + s] = use ? (mx + 1) / 2 : 0;
+            if (!use) tail_len += len;
+        }
+        tail_len += e - pos;
+        const int tmx = __reduce_max_sync(FULL, tail_len);
+        if (lane == 0) tail_rounds[s] = tmx;
+    }
+}
+
+// virtual column (what the builders' CSR is indexed by) -> position in the gather vector
+__device__ __forceinline__ int32_t hsell_real_col(int32_t v, int H, int K, int N, int64_t seg_len) {
+    if (N == 1) return v;
+    const int Hs = H / N;
+    const int64_t hub_span = (int64_t)K * H;
+    if (v < hub_span) {
+        const int blk = v / H, local = v - blk * H;
+        const int rnk = local / Hs, off = local - rnk * Hs;
+        return (int32_t)(rnk * seg_len + (int64_t)blk * Hs + off);
+    }
+    const int64_t vt = v - hub_span;
+    const int64_t tl = seg_len - (int64_t)K * Hs;   // tail entries per segment
+    const int64_t rnk = vt / tl, off = vt - rnk * tl;
+    return (int32_t)(rnk * seg_len + (int64_t)K * Hs + off);
+}
+
+__global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__restrict__ indptr,
+                                  const int32_t *__restrict__ indices, int H, int K, int N, int64_t seg_len,
+                                  const int32_t *__restrict__ hub_rounds, const int32_t *__restrict__ tail_rounds,
+                                  const int64_t *__restrict__ hub_round_base, const int64_t *__restrict__ hub_part_base,
+                                  const int64_t *__restrict__ tail_round_base,
+                                  const int64_t *__restrict__ tail_part_base, const int32_t *__restrict__ slice_ptr,
+                                  uint32_t *__restrict__ hub_words, int32_t *__restrict__ tail_cols,
+                                  int32_t *__restrict__ slice_parts) {
+    constexpr int CH = PGB_HSELL_CHUNK;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = warp; s < n_slices; s += nwarps) {
+        const int64_t row = s * 32 + lane;
+        int b = 0, e = 0;
+        if (row < n) {
+            b = indptr[row];
+            e = indptr[row + 1];
+        }
+        const int64_t first_part = slice_ptr[s];
+        const int TR = tail_rounds[s];
+        const int64_t tg0 = tail_round_base[s];
+        const int64_t tw = tg0 * 32;
+        int pos = b, t = 0;
+        int64_t ord = 0;
+        for (int blk = 0; blk < K; ++blk) {
+            const int nxt = lower_bound_i32(indices, pos, e, (blk + 1) * H);
+            const int len = nxt - pos;
+            const int R = hub_rounds[(int64_t)blk * n_slices + s];
+            if (R > 0) {
+                const int64_t g0 = hub_round_base[(int64_t)blk * n_slices + s];
+                const int64_t wb = g0 * 32;
+                const int base = blk * H;
+                for (int j = 0; j < R; ++j) {
+                    const int i0 = 2 * j, i1 = 2 * j + 1;
+                    const uint32_t lo = (i0 < len) ? (uint32_t)(indices[pos + i0] - base) : (uint32_t)H;
+                    const uint32_t hi = (i1 < len) ? (uint32_t)(indices[pos + i1] - base) : (uint32_t)H;
+                    hub_words[wb + (int64_t)j * 32 + lane] = lo | (hi << 16);
+                }
+                // pieces: the unit is cut at every chunk boundary of its stream
+                const int pieces = (int)((g0 + R - 1) / CH - g0 / CH) + 1;
+                const int64_t p0 = hub_part_base[(int64_t)blk * n_slices + s];
+                for (int p = lane; p < pieces; p += 32) slice_parts[first_part + ord + p] = (int32_t)(p0 + p);
+                ord += pieces;
+            } else {
+                for (int i = 0; i < len; ++i, ++t)
+                    tail_cols[tw + (int64_t)t * 32 + lane] = hsell_real_col(indices[pos + i], H, K, N, seg_len);
+            }
+            pos = nxt;
+        }
+        for (int i = pos; i < e; ++i, ++t) tail_cols[tw + (int64_t)t * 32 + lane] = hsell_real_col(indices[i], H, K, N, seg_len);
+        for (; t < TR; ++t) tail_cols[tw + (int64_t)t * 32 + lane] = -1;
+        if (TR > 0) {
+            const int pieces = (int)((tg0 + TR - 1) / CH - tg0 / CH) + 1;
+            const int64_t p0 = tail_part_base[s];
+            for (int p = lane; p < pieces; p += 32) slice_parts[first_part + ord + p] = (int32_t)(p0 + p);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel A: the gather.  One CTA of 32 warps per SM; shared memory holds one hub block of z.
+// ---------------------------------------------------------------------------------------------
+struct GatherParams {
+    pgb_hsell h;
+    const void *z;
+    void *partials;
+    const int32_t *stop;   // device state word: run-ahead launches after convergence are no-ops (or NULL)
+    int tail_warps;
+};
+
+constexpr int CH = PGB_HSELL_CHUNK;   // rounds per chunk
+constexpr int BATCH = 8;              // rounds loaded ahead per lane
+static_assert(CH == 32 && CH % BATCH == 0, "the end mask of a chunk is one 32-bit word");
+
+// One chunk of the hub stream: 32 rounds, two shared-memory gathers per lane and round.
+template <typename T>
+__device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, int64_t chunk, uint32_t p_first,
+                                          uint32_t endmask, const T *s_z, T *__restrict__ partials, int lane) {
+    const uint32_t *d = words + chunk * (CH * 32) + lane;
+    endmask |= 0x80000000u;   // the chunk end closes the last piece
+    uint32_t w[BATCH], nx[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) w[u] = ld_stream_u32(d + u * 32);
+    T a0 = (T)0, a1 = (T)0;
+    int64_t p = p_first;
+#pragma unroll
+    for (int bt = 0; bt < CH / BATCH; ++bt) {
+        if (bt + 1 < CH / BATCH) {
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) nx[u] = ld_stream_u32(d + ((bt + 1) * BATCH + u) * 32);
+        }
+        const uint32_t m8 = (endmask >> (bt * BATCH)) & 0xffu;
+        if (m8 == 0u) {
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                a0 += s_z[w[u] & 0xffffu];
+                a1 += s_z[w[u] >> 16];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                a0 += s_z[w[u] & 0xffffu];
+                a1 += s_z[w[u] >> 16];
+                if ((m8 >> u) & 1u) {
+                    partials[p * 32 + lane] = a0 + a1;
+                    ++p;
+                    a0 = a1 = (T)0;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) w[u] = nx[u];
+    }
+}
+
+// One chunk of the tail stream: 32 rounds, one L2 gather per lane and round (padding lanes are off).
+template <typename T>
+__device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int64_t chunk, uint32_t p_first,
+                                           uint32_t endmask, const T *__restrict__ z, T *__restrict__ partials,
+                                           int lane) {
+    const int32_t *d = cols + chunk * (CH * 32) + lane;
+    endmask |= 0x80000000u;
+    int32_t c[BATCH], nx[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) c[u] = ld_stream(d + u * 32);
+    T a0 = (T)0, a1 = (T)0;
+    int64_t p = p_first;
+#pragma unroll
+    for (int bt = 0; bt < CH / BATCH; ++bt) {
+        T x[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) x[u] = (c[u] >= 0) ? __ldg(z + c[u]) : (T)0;
+        if (bt + 1 < CH / BATCH) {
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) nx[u] = ld_stream(d + ((bt + 1) * BATCH + u) * 32);
+        }
+        const uint32_t m8 = (endmask >> (bt * BATCH)) & 0xffu;
+        if (m8 == 0u) {
+#pragma unroll
+            for (int u = 0; u < BATCH; u += 2) {
+                a0 += x[u];
+                a1 += x[u + 1];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                a0 += x[u];
+                if ((m8 >> u) & 1u) {
+                    partials[p * 32 + lane] = a0 + a1;
+                    ++p;
+                    a0 = a1 = (T)0;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) c[u] = nx[u];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const GatherParams G) {
+    extern __shared__ __align__(16) unsigned char hs_smem[];
+    T *s_z = reinterpret_cast<T *>(hs_smem);   // [block_cols + 1]; the last entry is the padding target (0)
+    __shared__ int s_hub_next, s_tail_next;
+
+    if (G.stop && *G.stop != PGB_RUNNING) return;
+    const pgb_hsell &h = G.h;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const T *__restrict__ z = (const T *)G.z;
+    T *__restrict__ partials = (T *)G.partials;
+    const int cta = blockIdx.x;
+    const int hub_lo = h.cta_hub_begin[cta], hub_hi = h.cta_hub_begin[cta + 1];
+    const int tail_hi = h.cta_tail_begin[cta + 1];
+    const bool tail_pref = warp < G.tail_warps;
+    const int H = h.block_cols, N = h.n_segments;
+    const int Hs = H / N;
+    if (tid == 0) {
+        s_tail_next = h.cta_tail_begin[cta];
+        s_z[H] = (T)0;
+    }
+
+    auto run_tail = [&](int u) {
+        const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.tail_chunks) + u);
+        tail_chunk<T>(h.tail_cols, u, d.x, d.y, z, partials, lane);
+    };
+
+    int cur = hub_lo;
+    int blk = 0;
+    while (cur < hub_hi) {
+        // ---- one segment: the chunks of one hub block inside this CTA's range ------------------------
+        while (h.block_chunk_begin[blk + 1] <= cur) ++blk;
+        const int blk_end = h.block_chunk_begin[blk + 1];
+        const int seg_end = blk_end < hub_hi ? blk_end : hub_hi;
+        __syncthreads();   // every warp is done with the previous block (and s_tail_next is initialised)
+        for (int sgm = 0; sgm < N; ++sgm) {
+            const int64_t first = (int64_t)sgm * h.seg_len + (int64_t)blk * Hs;
+            int64_t avail = h.seg_len - (int64_t)blk * Hs;
+            const int cnt = (int)(avail < Hs ? (avail < 0 ? 0 : avail) : Hs);
+            T *dst = s_z + sgm * Hs;
+            const T *src = z + first;
+            // vector part when both sides are 16-byte aligned, scalar otherwise
+            constexpr int V = 16 / sizeof(T);
+            if (((first % V) == 0) && (((sgm * Hs) % V) == 0)) {
+                const int nv = cnt / V;
+                const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                float4 *d4 = reinterpret_cast<float4 *>(dst);
+                for (int i = tid; i < nv; i += HS_THREADS) d4[i] = __ldg(s4 + i);
+                for (int i = nv * V + tid; i < cnt; i += HS_THREADS) dst[i] = __ldg(src + i);
+            } else {
+                for (int i = tid; i < cnt; i += HS_THREADS) dst[i] = __ldg(src + i);
+            }
+            for (int i = cnt + tid; i < Hs; i += HS_THREADS) dst[i] = (T)0;
+        }
+        if (tid == 0) s_hub_next = cur;
+        __syncthreads();
+        while (true) {
+            int kind = 0, u = 0;   // 0: nothing left in this segment, 1: hub chunk, 2: tail chunk
+            if (lane == 0) {
+                if (tail_pref && *(volatile int *)&s_hub_next < seg_end) {
+                    u = atomicAdd(&s_tail_next, 1);
+                    if (u < tail_hi) kind = 2;
+                }
+                if (kind == 0) {
+                    u = atomicAdd(&s_hub_next, 1);
+                    if (u < seg_end) kind = 1;
+                }
+            }
+            kind = __shfl_sync(FULL, kind, 0);
+            u = __shfl_sync(FULL, u, 0);
+            if (kind == 0) break;
+            if (kind == 1) {
+                const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.hub_chunks) + u);
+                hub_chunk<T>(h.hub_words, u, d.x, d.y, s_z, partials, lane);
+            } else {
+                run_tail(u);
+            }
+        }
+        cur = seg_end;
+    }
+    __syncthreads();
+    // ---- drain the tail queue ---------------------------------------------------------------------
+    while (true) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(&s_tail_next, 1);
+        u = __shfl_sync(FULL, u, 0);
+        if (u >= tail_hi) break;
+        run_tail(u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel B: add the partial rows of each slice, fused filter update, convergence reduction.
+// Slices with many parts (hub rows: their units span many chunks) are reduced by a whole CTA first,
+// in a fixed order (deterministic); the others by one warp each, 32 slices per warp pass.
+// ---------------------------------------------------------------------------------------------
+constexpr int UPD_WARPS = UPD_BLOCK / 32;
+
+// Kernel B1 (only when some slice has more than heavy_parts partial rows): every group of <= 32
+// partial rows of such a slice is added by one warp into a second-level partial row, in list order
+// (deterministic); slice_parts of the slice then lists the second-level rows.
+template <typename T>
+__global__ void __launch_bounds__(256) hsell_reduce_kernel(const pgb_hsell h, T *__restrict__ partials,
+                                                           const int32_t *stop) {
+    if (stop && *stop != PGB_RUNNING) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = warp; it < h.n_reduce; it += nwarps) {
+        const int32_t start = h.reduce_items[it * 3], cnt = h.reduce_items[it * 3 + 1], out = h.reduce_items[it * 3 + 2];
+        const int mine = (lane < cnt) ? h.reduce_parts[start + lane] : -1;
+        T acc = (T)0;
+        int t = 0;
+        for (; t + 8 <= cnt; t += 8) {
+            T x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t + u) * 32 + lane);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += x[u];
+        }
+        for (; t < cnt; ++t) acc += ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t) * 32 + lane);
+        partials[(int64_t)out * 32 + lane] = acc;
+    }
+}
+
+
+template <typename T, int MODE, bool SYMDEG>
+__global__ void __launch_bounds__(UPD_BLOCK, UPD_MIN_CTAS) hsell_update_kernel(const StepParams P, const pgb_hsell h,
+                                                                  const T *__restrict__ partials) {
+    __shared__ double s_red[32];
+    __shared__ T s_acc[UPD_WARPS][32];
+    if (MODE != MODE_CONV) {
+        if (P.si[PGB_SI_STOP] != PGB_RUNNING) return;
+    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const int32_t *__restrict__ slice_ptr = h.slice_ptr;
+    const int32_t *__restrict__ slice_parts = h.slice_parts;
+    const int heavy_parts = h.heavy_parts;
+    RowUpdate<T, MODE, SYMDEG> update(P);
+    using Loaded = typename RowUpdate<T, MODE, SYMDEG>::Loaded;
+
+    // ---- heavy slices: one CTA each --------------------------------------------------------------
+    for (int hi = blockIdx.x; hi < h.n_heavy; hi += gridDim.x) {
+        const int64_t s = h.heavy_slices[hi];
+        const int p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
+        T acc = (T)0;
+        for (int j0 = p0 + wib * 32; j0 < p1; j0 += UPD_WARPS * 32) {
+            const int mine = (j0 + lane < p1) ? slice_parts[j0 + lane] : -1;
+            const int cnt = (p1 - j0 < 32) ? p1 - j0 : 32;
+            int t = 0;
+            for (; t + 8 <= cnt; t += 8) {
+                T x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t + u) * 32 + lane);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += x[u];
+            }
+            for (; t < cnt; ++t) acc += ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t) * 32 + lane);
+        }
+        s_acc[wib][lane] = acc;
+        __syncthreads();
+        if (wib == 0) {
+            T tot = (T)0;
+#pragma unroll
+            for (int w = 0; w < UPD_WARPS; ++w) tot += s_acc[w][lane];
+            const int64_t row = s * 32 + lane;
+            if (row < P.n) {
+                int deg = 0;
+                if (SYMDEG) deg = P.indptr[row + 1] - P.indptr[row];
+                update(row, tot, deg);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- the other slices: a warp takes 32 consecutive slices at a time -----------------------------
+    const int64_t warp = blockIdx.x * (int64_t)UPD_WARPS + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * UPD_WARPS;
+    const int64_t n_slices = h.n_slices;
+    for (int64_t s0 = warp * 32; s0 < n_slices; s0 += nwarps * 32) {
+        const int64_t sl = s0 + lane;
+        const int my_p0 = (sl <= n_slices) ? slice_ptr[sl] : 0;
+        int my_p1 = __shfl_down_sync(FULL, my_p0, 1);
+        if (lane == 31) my_p1 = (sl + 1 <= n_slices) ? slice_ptr[sl + 1] : my_p0;
+        const int cnt_here = (int)((n_slices - s0 < 32) ? n_slices - s0 : 32);
+        for (int k = 0; k < cnt_here; ++k) {
+            const int p0 = __shfl_sync(FULL, my_p0, k);
+            const int p1 = __shfl_sync(FULL, my_p1, k);
+            const int np = p1 - p0;
+            if (np > heavy_parts) continue;   // reduced by a CTA above
+            const int64_t row = (s0 + k) * 32 + lane;
+            const bool live = row < P.n;
+            int deg = 0;
+            if (SYMDEG && live) deg = P.indptr[row + 1] - P.indptr[row];
+            Loaded L;
+            if (live) L = update.load(row, deg);
+            const int mine = (lane < np) ? slice_parts[p0 + lane] : -1;
+            T acc = (T)0;
+            int t = 0;
+            for (; t + 4 <= np; t += 4) {
+                T x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t + u) * 32 + lane);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc += x[u];
+            }
+            for (; t < np; ++t) acc += ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t) * 32 + lane);
+            if (live) update.apply(row, acc, L);
+        }
+    }
+    if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
+}
+
+template <typename T>
+static int launch_gather(const pgb_hsell *h, const void *z, void *partials, const int32_t *stop, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = ((size_t)h->block_cols + 1) * sizeof(T);
+    if (smem > (size_t)HS_SMEM_LIMIT - 64) return fail("hsell: block_cols=%d does not fit in shared memory", h->block_cols);
+    if (!configured) {
+        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HS_SMEM_LIMIT - 64));
+        configured = true;
+    }
+    GatherParams G;
+    G.h = *h;
+    G.z = z;
+    G.partials = partials;
+    G.stop = stop;
+    G.tail_warps = g_tail_warps;
+    hsell_gather_kernel<T><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
+    PGB_LAUNCH_OK("hsell_gather_kernel");
+    return 0;
+}
+
+template <typename T>
+static int launch_reduce(const pgb_hsell *h, void *partials, const int32_t *stop, cudaStream_t st) {
+    if (h->n_reduce <= 0) return 0;
+    int64_t want = ceil_div(h->n_reduce, 8);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (want > cap) want = cap;
+    hsell_reduce_kernel<T><<<(int)want, 256, 0, st>>>(*h, (T *)partials, stop);
+    PGB_LAUNCH_OK("hsell_reduce_kernel");
+    return 0;
+}
+
+template <typename T, int MODE, bool SYMDEG>
+static int launch_update(const StepParams &P, const pgb_hsell *h, const void *partials, cudaStream_t st) {
+    int64_t want = ceil_div(h->n_slices, UPD_WARPS * 32);
+    if (want < h->n_heavy) want = h->n_heavy;
+    const int64_t cap = (int64_t)sm_count() * UPD_MIN_CTAS;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    hsell_update_kernel<T, MODE, SYMDEG><<<(int)want, UPD_BLOCK, 0, st>>>(P, *h, (const T *)partials);
+    PGB_LAUNCH_OK("hsell_update_kernel");
+    return 0;
+}
+
+// One fused step on the hsell form: gather (kernel A) + update (kernel B).  Called from spmv_fused.cu.
+template <int MODE>
+int hsell_step(const StepParams &P, const pgb_hsell *h, void *partials, int dtype, bool symdeg, cudaStream_t st) {
+    if (!partials) return fail("hsell: the workspace has no partials buffer");
+    if (h->n_rows != P.n) return fail("hsell: form built for %lld rows, graph has %lld", (long long)h->n_rows, (long long)P.n);
+    const int32_t *stop = (MODE == MODE_CONV) ? nullptr : P.si + PGB_SI_STOP;
+    if (dtype == PGB_F32) {
+        if (launch_gather<float>(h, P.zin, partials, stop, st)) return 1;
+        if (launch_reduce<float>(h, partials, stop, st)) return 1;
+        return symdeg ? launch_update<float, MODE, true>(P, h, partials, st)
+                      : launch_update<float, MODE, false>(P, h, partials, st);
+    } else if (dtype == PGB_F64) {
+        if (launch_gather<double>(h, P.zin, partials, stop, st)) return 1;
+        if (launch_reduce<double>(h, partials, stop, st)) return 1;
+        return symdeg ? launch_update<double, MODE, true>(P, h, partials, st)
+                      : launch_update<double, MODE, false>(P, h, partials, st);
+    }
+    return fail("unknown dtype %d", dtype);
+}
+
+template int hsell_step<MODE_CONV>(const StepParams &, const pgb_hsell *, void *, int, bool, cudaStream_t);
+template int hsell_step<MODE_AFFINE>(const StepParams &, const pgb_hsell *, void *, int, bool, cudaStream_t);
+template int hsell_step<MODE_POLY>(const StepParams &, const pgb_hsell *, void *, int, bool, cudaStream_t);
+
+}  // namespace pgb
+
+using namespace pgb;
+
+extern "C" {
+
+int pgb_hsell_max_block_cols(int dtype) {
+    const int bytes = dtype == PGB_F32 ? 4 : (dtype == PGB_F64 ? 8 : 0);
+    if (!bytes) return 0;
+    int cols = (HS_SMEM_LIMIT - 64) / bytes - 1;
+    if (cols > 65535) cols = 65535;
+    return cols & ~63;   // keeps every block start 16-byte aligned for the vector loader
+}
+
+int pgb_hsell_set_tail_warps(int warps) {
+    if (warps < 0 || warps > HS_WARPS) return fail("pgb_hsell_set_tail_warps: %d is not in 0..%d", warps, HS_WARPS);
+    g_tail_warps = warps;
+    return 0;
+}
+
+int pgb_hsell_count(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
+                    int32_t min_entries, int32_t *hub_rounds, int32_t *tail_rounds, void *stream) {
+    if (n <= 0) return 0;
+    if (block_cols < 1 || block_cols > 65535) return fail("pgb_hsell_count: block_cols must be in 1..65535");
+    if (n_blocks < 0 || (int64_t)n_blocks * block_cols >= (1ll << 31)) return fail("pgb_hsell_count: bad n_blocks");
+    const int64_t n_slices = ceil_div(n, 32);
+    const int grid = stride_grid(n_slices * 32, 256);
+    hsell_count_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n_slices, indptr, indices, block_cols, n_blocks,
+                                                            min_entries, hub_rounds, tail_rounds);
+    PGB_LAUNCH_OK("hsell_count_kernel");
+    return 0;
+}
+
+int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
+                   int32_t n_segments, int64_t seg_len, const int32_t *hub_rounds, const int32_t *tail_rounds,
+                   const int64_t *hub_round_base, const int64_t *hub_part_base, const int64_t *tail_round_base,
+                   const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
+                   int32_t *slice_parts, void *stream) {
+    if (n <= 0) return 0;
+    if (n_segments < 1 || block_cols % n_segments) return fail("pgb_hsell_fill: block_cols must be a multiple of n_segments");
+    const int64_t n_slices = ceil_div(n, 32);
+    const int grid = stride_grid(n_slices * 32, 256);
+    hsell_fill_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n_slices, indptr, indices, block_cols, n_blocks, n_segments,
+                                                           seg_len, hub_rounds, tail_rounds, hub_round_base, hub_part_base,
+                                                           tail_round_base, tail_part_base, slice_ptr, hub_words,
+                                                           tail_cols, slice_parts);
+    PGB_LAUNCH_OK("hsell_fill_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "step_common.cuh"
 
 namespace pgb {
 
@@ -36,137 +37,10 @@ constexpr int WARPS = BLOCK / 32;
 constexpr int SUB_ITEMS = 32 * IPT;       // v2: items one warp consumes per pass
 static_assert(TILE_ITEMS % SUB_ITEMS == 0, "a tile is a whole number of warp passes");
 
-enum { MODE_CONV = 0, MODE_AFFINE = 1, MODE_POLY = 2 };
-
-struct StepParams {
-    int64_t n, nnz;
-    const int32_t *indptr, *indices;
-    const void *values;
-    const int32_t *tile_row;
-    int32_t n_tiles;
-    const int32_t *istream;  // item-space index stream: row entries then the terminator -1-deg (v3)
-    const void *vstream;     // item-space weights (weighted graphs), same positions as istream
-    const void *zin;
-    void *zout;
-    int64_t out_offset;  // index of local row 0 inside the (full-length) z vectors
-    const void *w, *sq, *c, *q;
-    void *ranks;
-    const double *coef;
-    const void *rscale, *xlap;
-    const int32_t *out_perm;
-    double alpha;
-    double *sf;
-    int32_t *si;
-    double *err_hist;
-    double *span_acc;
-    uint32_t *span_cnt;
-    int finalize;
-};
-
-__device__ __forceinline__ void finalize_state(double *sf, int32_t *si, double *err_hist) {
-    volatile double *vsf = sf;
-    volatile int32_t *vsi = si;
-    const double tacc = vsf[PGB_SF_TACC], eacc = vsf[PGB_SF_EACC];
-    vsf[PGB_SF_TACC] = 0.0;
-    vsf[PGB_SF_EACC] = 0.0;
-    vsi[PGB_SI_TICKET] = 0;
-    const int k = vsi[PGB_SI_STEPS] + 1;  // _step calls done
-    vsi[PGB_SI_STEPS] = k;
-    const int it = k + 1;                 // ConvergenceManager.iteration at the next has_converged()
-    const double errv = eacc / vsf[PGB_SF_MEAN];
-    vsf[PGB_SF_LASTERR] = errv;
-    if (err_hist) err_hist[k] = errv;
-    int stop = PGB_RUNNING;
-    if (it >= vsi[PGB_SI_MAX_ITERS])                                    // convergence.py:86-90
-        stop = PGB_MAX_ITERS;
-    else if (vsi[PGB_SI_ERR_MODE] != PGB_ERR_ITERS && (it % vsi[PGB_SI_END_MODULO]) == 0 &&
-             errv <= vsf[PGB_SF_TOL])                                   // convergence.py:97-101
-        stop = PGB_CONVERGED;
-    if (stop != PGB_RUNNING) {
-        vsi[PGB_SI_ITERATION] = it;
-        vsi[PGB_SI_STOP] = stop;
-    } else if (vsi[PGB_SI_QUOTIENT]) {
-        // sum(next ranks) is linear in the current ranks: alpha * sum_i ranks_i*rowsum_i(M) + sum(bias)
-        vsf[PGB_SF_INVS] = 1.0 / (vsf[PGB_SF_ALPHA] * tacc + vsf[PGB_SF_BIAS]);
-    }
-    __threadfence();
-}
-
 __global__ void state_finalize_kernel(double *sf, int32_t *si, double *err_hist) {
     if (si[PGB_SI_STOP] != PGB_RUNNING) return;
     finalize_state(sf, si, err_hist);
 }
-
-template <typename T>
-struct RowMath;
-template <>
-struct RowMath<float> {
-    static __device__ __forceinline__ float inv(float d) { return 1.0f / d; }
-    static __device__ __forceinline__ float root(float d) { return sqrtf(d); }
-};
-template <>
-struct RowMath<double> {
-    static __device__ __forceinline__ double inv(double d) { return 1.0 / d; }
-    static __device__ __forceinline__ double root(double d) { return sqrt(d); }
-};
-
-template <typename T, int MODE, bool SYMDEG>
-struct RowUpdate {
-    const StepParams &P;
-    T alpha, invS, coef;
-    int err_mode;
-    double err, tsum;
-
-    __device__ __forceinline__ RowUpdate(const StepParams &p) : P(p), err(0.0), tsum(0.0) {
-        alpha = (T)p.alpha;
-        invS = (T)1;
-        coef = (T)0;
-        err_mode = PGB_ERR_MABS;
-        if (MODE != MODE_CONV) {
-            err_mode = p.si[PGB_SI_ERR_MODE];
-            invS = (T)p.sf[PGB_SF_INVS];
-            if (MODE == MODE_POLY) coef = (T)p.coef[p.si[PGB_SI_STEPS] + 1];
-        }
-    }
-
-    __device__ __forceinline__ void operator()(int64_t row, T acc, int deg) {
-        const int64_t own = P.out_offset + row;
-        if (MODE == MODE_CONV) {
-            T y = P.rscale ? ((const T *)P.rscale)[row] * acc : acc;
-            if (P.xlap) y = ((const T *)P.xlap)[row] - y;
-            ((T *)P.zout)[P.out_perm ? (int64_t)P.out_perm[row] : own] = y;
-            return;
-        }
-        T wi, sqi;
-        if (SYMDEG) {
-            wi = deg > 0 ? RowMath<T>::inv((T)deg) : (T)0;
-            sqi = deg > 0 ? RowMath<T>::root((T)deg) : (T)1;
-        } else {
-            wi = ld_stream((const T *)P.w + row);
-            sqi = ld_stream((const T *)P.sq + row);
-        }
-        const T zi = __ldg((const T *)P.zin + own);
-        if (MODE == MODE_AFFINE) {
-            // row-aligned streams are touched once per launch: evict-first keeps L1/L2 for the gathers
-            const T znew = (alpha * wi * acc + ld_stream((const T *)P.q + row)) * invS;
-            ((T *)P.zout)[own] = znew;
-            double d = (double)sqi * fabs((double)znew - (double)zi);
-            err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
-            tsum += (double)znew * (double)ld_stream((const T *)P.c + row);
-        } else {  // MODE_POLY
-            const T pw = sqi * zi;
-            if (coef != (T)0) {  // abstract_filters.py:226-228
-                const T prev = ((T *)P.ranks)[row];
-                const T cur = prev + pw * coef;
-                ((T *)P.ranks)[row] = cur;
-                // fp64: the literal |prev - cur| the reference's Mabs sees; fp32: the exact increment
-                double d = (sizeof(T) == 8) ? fabs((double)prev - (double)cur) : fabs((double)coef * (double)pw);
-                err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
-            }
-            ((T *)P.zout)[own] = wi * acc;
-        }
-    }
-};
 
 // Cross-tile row completion without a gpu-scope fence.  __threadfence() compiles to
 // MEMBAR.SC.GPU + CCTL.IVALL, and the CCTL invalidates the whole L1 of the SM — issued once or twice
@@ -812,12 +686,13 @@ __global__ void __launch_bounds__(BLOCK, 4) gather_probe_kernel(const int32_t *_
     if (acc == (T)-123456789) out[0] = acc;  // keeps the loads alive
 }
 
-static int g_kernel_variant = 3;  // 1 = CTA tiles, 2 = warp tiles over CSR, 3 = warp tiles over the item stream
+static int g_kernel_variant = 4;  // 1 = CTA tiles, 2 = warp tiles over CSR, 3 = warp tiles over the item stream,
+                                   // 4 = hsell when the graph carries that form, else 3
 
 template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
 static int launch_tiles(const StepParams &P, cudaStream_t st) {
     static int ctas_per_sm[4] = {0, 0, 0, 0};
-    int variant = g_kernel_variant;
+    int variant = g_kernel_variant > 3 ? 3 : g_kernel_variant;
     if (variant == 3 && (!P.istream || (WEIGHTED && !P.vstream)))
         return fail("the item-stream kernel needs pgb_csr.istream%s (pgb_build_item_stream)", WEIGHTED ? "/vstream" : "");
     if (ctas_per_sm[variant] == 0) {
@@ -878,6 +753,10 @@ static int launch_tiles(const StepParams &P, cudaStream_t st) {
 template <int MODE>
 static int dispatch(const StepParams &P, int dtype, bool symdeg, cudaStream_t st) {
     const bool weighted = P.values != nullptr;
+    if (P.hsell && g_kernel_variant >= 4) {
+        if (weighted) return fail("the hsell form is for unweighted graphs");
+        return hsell_step<MODE>(P, P.hsell, P.partials, dtype, symdeg, st);
+    }
     if (dtype == PGB_F32) {
         if (weighted) return launch_tiles<float, true, MODE, false>(P, st);
         if (symdeg) return launch_tiles<float, false, MODE, true>(P, st);
@@ -905,6 +784,7 @@ static int fill_graph(StepParams &P, const pgb_csr *g) {
     P.n_tiles = g->n_tiles;
     P.istream = g->istream;
     P.vstream = g->vstream;
+    P.hsell = g->hsell;
     return 0;
 }
 
@@ -951,7 +831,7 @@ int pgb_gather_probe(const pgb_csr *g, int dtype, const void *z, void *scratch, 
 }
 
 int pgb_set_kernel_variant(int variant) {
-    if (variant < 1 || variant > 3) return fail("pgb_set_kernel_variant: %d is not 1, 2 or 3", variant);
+    if (variant < 1 || variant > 4) return fail("pgb_set_kernel_variant: %d is not 1, 2, 3 or 4", variant);
     g_kernel_variant = variant;
     return 0;
 }
@@ -969,6 +849,7 @@ int pgb_spmv(const pgb_csr *g, int dtype, const void *z, const void *rscale, con
     P.out_perm = out_perm;
     P.span_acc = ws.acc;
     P.span_cnt = ws.cnt;
+    P.partials = ws.partials;
     return dispatch<MODE_CONV>(P, dtype, false, as_stream(stream));
 }
 
@@ -995,6 +876,7 @@ int pgb_affine_steps(const pgb_csr *g, int dtype, double alpha, const void *w, c
     P.err_hist = err_hist;
     P.span_acc = ws.acc;
     P.span_cnt = ws.cnt;
+    P.partials = ws.partials;
     P.finalize = finalize;
     void *buf[2] = {zbuf0, zbuf1};
     for (int j = 0; j < num_launches; ++j) {
@@ -1027,6 +909,7 @@ int pgb_poly_steps(const pgb_csr *g, int dtype, const void *w, const void *sq, c
     P.err_hist = err_hist;
     P.span_acc = ws.acc;
     P.span_cnt = ws.cnt;
+    P.partials = ws.partials;
     P.finalize = finalize;
     void *buf[2] = {zbuf0, zbuf1};
     for (int j = 0; j < num_launches; ++j) {

@@ -1,0 +1,189 @@
+// Shared by the per-iteration kernels (spmv_fused.cu: merge-path item stream; hsell.cu: hub-blocked
+// sliced-ELL): the launch parameters, the device-side ConvergenceManager and the fused row update.
+#pragma once
+#include "common.cuh"
+
+namespace pgb {
+
+enum { MODE_CONV = 0, MODE_AFFINE = 1, MODE_POLY = 2 };
+
+struct StepParams {
+    int64_t n, nnz;
+    const int32_t *indptr, *indices;
+    const void *values;
+    const int32_t *tile_row;
+    int32_t n_tiles;
+    const int32_t *istream;  // item-space index stream: row entries then the terminator -1-deg (v3)
+    const void *vstream;     // item-space weights (weighted graphs), same positions as istream
+    const void *zin;
+    void *zout;
+    int64_t out_offset;  // index of local row 0 inside the (full-length) z vectors
+    const void *w, *sq, *c, *q;
+    void *ranks;
+    const double *coef;
+    const void *rscale, *xlap;
+    const int32_t *out_perm;
+    double alpha;
+    double *sf;
+    int32_t *si;
+    double *err_hist;
+    double *span_acc;
+    uint32_t *span_cnt;
+    int finalize;
+    const pgb_hsell *hsell;  // host pointer: hub-blocked sliced-ELL form of the same graph (or NULL)
+    void *partials;          // its per-filter workspace
+};
+
+__device__ __forceinline__ void finalize_state(double *sf, int32_t *si, double *err_hist) {
+    volatile double *vsf = sf;
+    volatile int32_t *vsi = si;
+    const double tacc = vsf[PGB_SF_TACC], eacc = vsf[PGB_SF_EACC];
+    vsf[PGB_SF_TACC] = 0.0;
+    vsf[PGB_SF_EACC] = 0.0;
+    vsi[PGB_SI_TICKET] = 0;
+    const int k = vsi[PGB_SI_STEPS] + 1;  // _step calls done
+    vsi[PGB_SI_STEPS] = k;
+    const int it = k + 1;                 // ConvergenceManager.iteration at the next has_converged()
+    const double errv = eacc / vsf[PGB_SF_MEAN];
+    vsf[PGB_SF_LASTERR] = errv;
+    if (err_hist) err_hist[k] = errv;
+    int stop = PGB_RUNNING;
+    if (it >= vsi[PGB_SI_MAX_ITERS])                                    // convergence.py:86-90
+        stop = PGB_MAX_ITERS;
+    else if (vsi[PGB_SI_ERR_MODE] != PGB_ERR_ITERS && (it % vsi[PGB_SI_END_MODULO]) == 0 &&
+             errv <= vsf[PGB_SF_TOL])                                   // convergence.py:97-101
+        stop = PGB_CONVERGED;
+    if (stop != PGB_RUNNING) {
+        vsi[PGB_SI_ITERATION] = it;
+        vsi[PGB_SI_STOP] = stop;
+    } else if (vsi[PGB_SI_QUOTIENT]) {
+        // sum(next ranks) is linear in the current ranks: alpha * sum_i ranks_i*rowsum_i(M) + sum(bias)
+        vsf[PGB_SF_INVS] = 1.0 / (vsf[PGB_SF_ALPHA] * tacc + vsf[PGB_SF_BIAS]);
+    }
+    __threadfence();
+}
+
+template <typename T>
+struct RowMath;
+template <>
+struct RowMath<float> {
+    static __device__ __forceinline__ float inv(float d) { return 1.0f / d; }
+    static __device__ __forceinline__ float root(float d) { return sqrtf(d); }
+};
+template <>
+struct RowMath<double> {
+    static __device__ __forceinline__ double inv(double d) { return 1.0 / d; }
+    static __device__ __forceinline__ double root(double d) { return sqrt(d); }
+};
+
+template <typename T, int MODE, bool SYMDEG>
+struct RowUpdate {
+    const StepParams &P;
+    T alpha, invS, coef;
+    int err_mode;
+    double err, tsum;
+
+    __device__ __forceinline__ RowUpdate(const StepParams &p) : P(p), err(0.0), tsum(0.0) {
+        alpha = (T)p.alpha;
+        invS = (T)1;
+        coef = (T)0;
+        err_mode = PGB_ERR_MABS;
+        if (MODE != MODE_CONV) {
+            err_mode = p.si[PGB_SI_ERR_MODE];
+            invS = (T)p.sf[PGB_SF_INVS];
+            if (MODE == MODE_POLY) coef = (T)p.coef[p.si[PGB_SI_STEPS] + 1];
+        }
+    }
+
+    // Everything the update of one row reads besides the gathered sum: issued BEFORE the sum is
+    // known so that these loads overlap the gather (hsell update pass).
+    struct Loaded {
+        T wi, sqi, zi, a, b;   // a: q (affine) / previous ranks (poly) / rscale (conv); b: c (affine) / xlap (conv)
+    };
+
+    __device__ __forceinline__ Loaded load(int64_t row, int deg) const {
+        Loaded L;
+        L.wi = L.sqi = L.zi = L.a = L.b = (T)0;
+        if (MODE == MODE_CONV) {
+            L.a = P.rscale ? ((const T *)P.rscale)[row] : (T)1;
+            if (P.xlap) L.b = ((const T *)P.xlap)[row];
+            return L;
+        }
+        if (SYMDEG) {
+            L.wi = deg > 0 ? RowMath<T>::inv((T)deg) : (T)0;
+            L.sqi = deg > 0 ? RowMath<T>::root((T)deg) : (T)1;
+        } else {
+            L.wi = ld_stream((const T *)P.w + row);
+            L.sqi = ld_stream((const T *)P.sq + row);
+        }
+        L.zi = __ldg((const T *)P.zin + P.out_offset + row);
+        if (MODE == MODE_AFFINE) {
+            // row-aligned streams are touched once per launch: evict-first keeps L1/L2 for the gathers
+            L.a = ld_stream((const T *)P.q + row);
+            L.b = ld_stream((const T *)P.c + row);
+        } else if (coef != (T)0) {
+            L.a = ((T *)P.ranks)[row];
+        }
+        return L;
+    }
+
+    __device__ __forceinline__ void apply(int64_t row, T acc, const Loaded &L) {
+        const int64_t own = P.out_offset + row;
+        if (MODE == MODE_CONV) {
+            T y = P.rscale ? L.a * acc : acc;
+            if (P.xlap) y = L.b - y;
+            ((T *)P.zout)[P.out_perm ? (int64_t)P.out_perm[row] : own] = y;
+            return;
+        }
+        if (MODE == MODE_AFFINE) {
+            const T znew = (alpha * L.wi * acc + L.a) * invS;
+            ((T *)P.zout)[own] = znew;
+            double d = (double)L.sqi * fabs((double)znew - (double)L.zi);
+            err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+            tsum += (double)znew * (double)L.b;
+        } else {  // MODE_POLY
+            const T pw = L.sqi * L.zi;
+            if (coef != (T)0) {  // abstract_filters.py:226-228
+                const T prev = L.a;
+                const T cur = prev + pw * coef;
+                ((T *)P.ranks)[row] = cur;
+                // fp64: the literal |prev - cur| the reference's Mabs sees; fp32: the exact increment
+                double d = (sizeof(T) == 8) ? fabs((double)prev - (double)cur) : fabs((double)coef * (double)pw);
+                err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+            }
+            ((T *)P.zout)[own] = L.wi * acc;
+        }
+    }
+
+    __device__ __forceinline__ void operator()(int64_t row, T acc, int deg) {
+        const Loaded L = load(row, deg);
+        apply(row, acc, L);
+    }
+};
+
+// Grid-level end of a step: one fp64 atomic per CTA for the error numerator and the next normaliser;
+// the last CTA plays ConvergenceManager (or just resets the ticket in deferred multi-GPU mode).
+template <typename U>
+__device__ __forceinline__ void step_epilogue(const StepParams &P, U &update, double *s_red) {
+    const double err = block_sum(update.err, s_red);
+    const double tsum = block_sum(update.tsum, s_red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&P.sf[PGB_SF_EACC], err);
+        atomicAdd(&P.sf[PGB_SF_TACC], tsum);
+        __threadfence();
+        const int ticket = atomicAdd(&P.si[PGB_SI_TICKET], 1);
+        if (ticket == (int)gridDim.x - 1) {
+            __threadfence();
+            if (P.finalize)
+                finalize_state(P.sf, P.si, P.err_hist);
+            else
+                P.si[PGB_SI_TICKET] = 0;
+        }
+    }
+}
+
+// hsell.cu: one fused step (gather kernel + update kernel) on the hub-blocked sliced-ELL form
+template <int MODE>
+int hsell_step(const StepParams &P, const pgb_hsell *h, void *partials, int dtype, bool symdeg, cudaStream_t st);
+
+}  // namespace pgb

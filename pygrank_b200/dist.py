@@ -172,7 +172,7 @@ class DistGraph:
             r_full = torch.empty(self.n_global, dtype=f64, device=self.view.indptr.device)
             dist.all_gather_into_tensor(r_full, self.vec("R", f64).contiguous(), group=self.group)
             out = torch.empty(self.n_local, dtype=f64, device=r_full.device)
-            cs = self.view.cstruct(f64)
+            cs = self.view.cstruct(f64, hsell=False)
             C.check(lib.pgb_spmv(ctypes.byref(cs), dtype_code(f64), C.ptr(r_full), C.ptr(self.vec("R", f64)), None,
                                  None, C.ptr(out), span_struct(self.view.span_ws()), C.stream_ptr()))
         elif name == "c":
@@ -251,7 +251,7 @@ class DistPageRank:
         dist.all_reduce(state_f64[C.SF_TACC:C.SF_TACC + 1], group=g.group)
         C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
         C.count_launches(2)
-        cs = g.view.cstruct(dtype)
+        cs = g.view.cstruct(dtype, hsell=False)
         ws = g.view.new_span_ws()
         acc = state_f64[C.SF_TACC:C.SF_EACC + 1]
 

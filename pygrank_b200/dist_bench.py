@@ -97,7 +97,7 @@ def run(args):
     zfull = [torch.rand(g.n_global, dtype=dtype, device=dev), torch.rand(g.n_global, dtype=dtype, device=dev)]
     q = torch.zeros(n_loc, dtype=dtype, device=dev)
     cvec = g.vec("c", dtype)
-    cs = g.view.cstruct(dtype)
+    cs = g.view.cstruct(dtype, hsell=False)
     ws = g.view.new_span_ws()
     err_hist = torch.zeros(128, dtype=torch.float64, device=dev)
     reps = 20

@@ -273,7 +273,7 @@ class RecursiveGraphFilter(GraphFilter):
         w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
         sq_arg = None if symdeg else sq
         view = g.in_view
-        cs = view.cstruct(dtype)
+        cs = view.cstruct(dtype, hsell=False)                 # the panel kernel reads the item stream
         err_code = _error_code(cm.error_type)
         tol = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))
         perm = None if g.perm is None else g.perm.long()
@@ -375,7 +375,7 @@ class RecursiveGraphFilter(GraphFilter):
         C.count_launches(3)                                   # init, init_finish, final unscale
         view = g.in_view
         cs = view.cstruct(dtype)
-        ws = view.new_span_ws()
+        ws = view.new_span_ws(dtype)
         symdeg = g.symdeg and w_run is None
         w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
         sq_arg = None if symdeg else sq
@@ -384,7 +384,7 @@ class RecursiveGraphFilter(GraphFilter):
             C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, float(alpha), C.ptr(w), C.ptr(sq_arg), C.ptr(c),
                                          C.ptr(q), C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(state_f64),
                                          C.ptr(state_i32), C.ptr(err_hist), span_struct(ws), first, count, 1, st))
-            C.count_launches(count)
+            C.count_launches(count * (2 if cs.hsell else 1))
 
         steps = self._drive(launch, state_i32, err_hist)
         out = torch.empty(n, dtype=dtype, device=dev)
@@ -465,7 +465,7 @@ class ClosedFormGraphFilter(GraphFilter):
         C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
         view = g.in_view
         cs = view.cstruct(dtype)
-        ws = view.new_span_ws()
+        ws = view.new_span_ws(dtype)
         symdeg = g.symdeg
         w = None if symdeg else g.vec("w", dtype)
         sq_arg = None if symdeg else sq
@@ -474,7 +474,7 @@ class ClosedFormGraphFilter(GraphFilter):
             C.check(lib.pgb_poly_steps(ctypes.byref(cs), code, C.ptr(w), C.ptr(sq_arg), C.ptr(coef_dev), C.ptr(ranks),
                                        C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(state_f64), C.ptr(state_i32),
                                        C.ptr(err_hist), span_struct(ws), first, count, 1, st))
-            C.count_launches(count)
+            C.count_launches(count * (2 if cs.hsell else 1))
 
         C.count_launches(3)
         self._drive(launch, state_i32, err_hist)

@@ -22,6 +22,7 @@ HBM layout (all torch CUDA tensors, owned here, handed to libpgb200 as raw point
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import numpy as np
@@ -68,6 +69,183 @@ def build_csr(n: int, row: torch.Tensor, col: torch.Tensor, val: Optional[torch.
     return indptr, indices, values
 
 
+def _env_int(name: str, default: int) -> int:
+    v = os.environ.get(name)
+    return int(v) if v not in (None, "") else default
+
+
+def hsell_config() -> dict:
+    """Knobs of the hub-blocked sliced-ELL builder (environment overrides are for tests/experiments):
+    block_cols 0 = the most the gather kernel can keep in shared memory for the dtype."""
+    return {
+        "enabled": _env_int("PGB_HSELL", 1) != 0,
+        "block_cols": _env_int("PGB_HSELL_BLOCK_COLS", 0),
+        "max_blocks": _env_int("PGB_HSELL_BLOCKS", 16),
+        "min_entries": _env_int("PGB_HSELL_MIN_ENTRIES", 16),
+        "heavy_parts": min(max(_env_int("PGB_HSELL_HEAVY_PARTS", 32), 1), 32),
+    }
+
+
+class HsellForm:
+    """Device arrays of one pgb_hsell (kept alive here; the C struct holds raw pointers)."""
+
+    def __init__(self, view: "CsrView", dtype: torch.dtype, n_segments: int = 1, seg_len: Optional[int] = None,
+                 cfg: Optional[dict] = None):
+        lib = C.lib()
+        cfg = dict(hsell_config(), **(cfg or {}))
+        code = dtype_code(dtype)
+        st = C.stream_ptr()
+        dev = view.indptr.device
+        n = view.n
+        n_cols = view.n_cols
+        seg_len = int(seg_len) if seg_len is not None else n_cols
+        i64 = torch.int64
+        cap = lib.pgb_hsell_max_block_cols(code)
+        H = cfg["block_cols"] if cfg["block_cols"] > 0 else cap
+        H = min(H, cap)
+        H -= H % (4 * n_segments)                        # equal 16-byte aligned parts per segment
+        if H < 4 * n_segments:
+            raise Exception("hsell: block_cols too small")
+        Hs = H // n_segments
+        K = max(min(cfg["max_blocks"], -(-seg_len // Hs)), 0)
+        if n_segments > 1 and K * Hs > seg_len:
+            K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail
+        S = (n + 31) // 32
+        CH = C.HSELL_CHUNK
+        hub_rounds = torch.zeros(max(K * S, 1), dtype=torch.int32, device=dev)
+        tail_rounds = torch.zeros(max(S, 1), dtype=torch.int32, device=dev)
+        C.check(lib.pgb_hsell_count(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, cfg["min_entries"],
+                                    C.ptr(hub_rounds), C.ptr(tail_rounds), st))
+
+        def stream_layout(rounds, base):
+            """rounds: int64 [B, S] (units in stream order, every row padded to whole chunks).  Returns the
+            first round and first partial row of every unit, the chunk descriptors and the counts."""
+            Bn = rounds.shape[0]
+            per_row = rounds.sum(1)
+            row_pad = (per_row + (CH - 1)) // CH * CH
+            row_base = torch.cumsum(row_pad, 0) - row_pad
+            g0 = (row_base[:, None] + torch.cumsum(rounds, 1) - rounds).reshape(-1)
+            r = rounds.reshape(-1)
+            g1 = g0 + r
+            ex = r > 0
+            n_chunks = int(row_pad.sum()) // CH
+            aligned = ex & (g1 % CH == 0)
+            unit_rank = torch.cumsum(ex.to(i64), 0) - ex.to(i64)
+            b_before = torch.cumsum(aligned.to(i64), 0) - aligned.to(i64)
+            p0 = base + unit_rank + g0 // CH - b_before
+            pieces = torch.where(ex, (g1 - 1) // CH - g0 // CH + 1, torch.zeros_like(g0))
+            g1e = g1[ex]
+            starts = torch.arange(n_chunks, device=dev, dtype=i64) * CH
+            u = torch.searchsorted(g1e, starts, right=True)
+            bcum = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(aligned[ex].to(i64), 0)])
+            p_first = base + u + torch.arange(n_chunks, device=dev, dtype=i64) - bcum[u]
+            endmask = torch.zeros(max(n_chunks, 1), dtype=i64, device=dev)
+            if g1e.numel():
+                endmask.index_add_(0, (g1e - 1) // CH, torch.ones_like(g1e) << ((g1e - 1) % CH))
+            n_parts = int(ex.sum()) + n_chunks - int(aligned.sum())
+            desc = torch.stack([p_first, endmask[:n_chunks]], 1)
+            desc = torch.where(desc >= 2 ** 31, desc - 2 ** 32, desc).to(torch.int32).contiguous()
+            chunk_begin = torch.cat([row_base, row_pad.sum().reshape(1)]) // CH
+            return g0.contiguous(), p0.contiguous(), pieces, desc, n_chunks, n_parts, chunk_begin
+
+        hr = hub_rounds[:K * S].to(i64).view(K, S) if K > 0 else torch.zeros((0, S), dtype=i64, device=dev)
+        tr = tail_rounds[:S].to(i64).view(1, S)
+        if K > 0:
+            hub_g0, hub_p0, hub_pieces, self.hub_chunks, n_hub_chunks, n_hub_parts, bcb = stream_layout(hr, 0)
+        else:
+            hub_g0 = hub_p0 = torch.zeros(1, dtype=i64, device=dev)
+            hub_pieces = torch.zeros(0, dtype=i64, device=dev)
+            self.hub_chunks = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+            n_hub_chunks = n_hub_parts = 0
+            bcb = torch.zeros(1, dtype=i64, device=dev)
+        tail_g0, tail_p0, tail_pieces, self.tail_chunks, n_tail_chunks, n_tail_parts, _ = stream_layout(tr, n_hub_parts)
+        n_partials = n_hub_parts + n_tail_parts
+        per_slice = tail_pieces + (hub_pieces.view(K, S).sum(0) if K > 0 else 0)
+        slice_ptr64 = torch.zeros(S + 1, dtype=i64, device=dev)
+        torch.cumsum(per_slice, 0, out=slice_ptr64[1:])
+        n_parts_listed = int(slice_ptr64[-1])
+        n_hub_words, n_tail_words = n_hub_chunks * CH * 32, n_tail_chunks * CH * 32
+        if max(n_hub_words, n_tail_words) >= 2 ** 31 or max(n_partials, n_parts_listed) >= 2 ** 31:
+            raise Exception("hsell: graph exceeds the 32-bit offsets of one device; row-partition it")
+        self.slice_ptr = slice_ptr64.to(torch.int32)
+        pad_word = (H | (H << 16))
+        pad_word = pad_word - 2 ** 32 if pad_word >= 2 ** 31 else pad_word
+        self.hub_words = torch.full((max(n_hub_words, 1),), pad_word, dtype=torch.int32, device=dev)
+        self.tail_cols = torch.full((max(n_tail_words, 1),), -1, dtype=torch.int32, device=dev)
+        self.slice_parts = torch.empty(max(n_parts_listed, 1), dtype=torch.int32, device=dev)
+        C.check(lib.pgb_hsell_fill(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, n_segments, seg_len,
+                                   C.ptr(hub_rounds), C.ptr(tail_rounds), C.ptr(hub_g0), C.ptr(hub_p0),
+                                   C.ptr(tail_g0), C.ptr(tail_p0), C.ptr(self.slice_ptr), C.ptr(self.hub_words),
+                                   C.ptr(self.tail_cols), C.ptr(self.slice_parts), st))
+        # slices with many pieces (hub rows) are reduced in two levels: groups of 32 first-level partial
+        # rows -> one second-level row each (kernel B1), which the slice then lists instead
+        heavy_parts = cfg["heavy_parts"]
+        big = torch.nonzero(per_slice > heavy_parts).reshape(-1)
+        n_reduce = 0
+        self.reduce_items = torch.zeros(3, dtype=torch.int32, device=dev)
+        self.reduce_parts = self.slice_parts
+        if big.numel():
+            cnt1 = per_slice[big]
+            groups = (cnt1 + 31) // 32
+            n_reduce = int(groups.sum())
+            owner = torch.repeat_interleave(torch.arange(big.numel(), device=dev), groups)       # item -> big slice
+            first_item = torch.cumsum(groups, 0) - groups
+            k = torch.arange(n_reduce, device=dev, dtype=i64) - first_item[owner]                # group index in slice
+            start = slice_ptr64[big][owner] + 32 * k
+            count = torch.clamp(cnt1[owner] - 32 * k, max=32)
+            out_row = n_partials + torch.arange(n_reduce, device=dev, dtype=i64)
+            self.reduce_items = torch.stack([start, count, out_row], 1).to(torch.int32).contiguous()
+            self.reduce_parts = self.slice_parts                                                  # first-level lists
+            # final lists: big slices list their second-level rows
+            per_final = per_slice.clone()
+            per_final[big] = groups
+            final_ptr = torch.zeros(S + 1, dtype=i64, device=dev)
+            torch.cumsum(per_final, 0, out=final_ptr[1:])
+            final_parts = torch.empty(max(int(final_ptr[-1]), 1), dtype=torch.int32, device=dev)
+            is_big = torch.zeros(S, dtype=torch.bool, device=dev)
+            is_big[big] = True
+            src_slice = torch.repeat_interleave(torch.arange(S, device=dev), per_slice)          # first-level entry -> slice
+            keep = ~is_big[src_slice]
+            pos_in_slice = torch.arange(n_parts_listed, device=dev, dtype=i64) - slice_ptr64[:-1][src_slice]
+            final_parts[(final_ptr[:-1][src_slice] + pos_in_slice)[keep]] = self.slice_parts[:n_parts_listed][keep]
+            final_parts[final_ptr[:-1][big][owner] + k] = out_row.to(torch.int32)
+            self.first_level_ptr, self.first_level_parts = self.slice_ptr, self.slice_parts
+            self.slice_ptr, self.slice_parts = final_ptr.to(torch.int32), final_parts
+            per_slice = per_final
+            n_partials += n_reduce
+        self.heavy_slices = torch.nonzero(per_slice > heavy_parts).reshape(-1).to(torch.int32)
+        n_heavy = int(self.heavy_slices.numel())
+        if n_heavy == 0:
+            self.heavy_slices = torch.zeros(1, dtype=torch.int32, device=dev)
+        # schedule: chunks are uniform work, so every CTA gets a contiguous, equally long range of each stream
+        n_ctas = lib.pgb_device_sm_count(dev.index if dev.index is not None else torch.cuda.current_device())
+        if n_ctas <= 0:
+            raise Exception("pgb200: " + lib.pgb_last_error().decode())
+
+        def cut(count):
+            return ((torch.arange(n_ctas + 1, device=dev, dtype=i64) * count) // n_ctas).to(torch.int32)
+
+        self.cta_hub_begin = cut(n_hub_chunks)
+        self.cta_tail_begin = cut(n_tail_chunks)
+        self.block_chunk_begin = bcb.to(torch.int32)
+        self.n_partials, self.block_cols, self.n_blocks, self.n_ctas = n_partials, H, K, n_ctas
+        self.n_hub_chunks, self.n_tail_chunks, self.n_heavy = n_hub_chunks, n_tail_chunks, n_heavy
+        self.n_reduce, self.n_first_level = n_reduce, n_hub_parts + n_tail_parts
+        self.n_hub_words, self.n_tail_words = n_hub_words, n_tail_words
+        self.n_slices, self.n_segments, self.seg_len = S, n_segments, seg_len
+        self.dtype = dtype
+        self.struct = C.Hsell(n, S, n_partials, seg_len, n_segments, H, K, n_ctas, n_hub_chunks, n_tail_chunks,
+                              n_heavy, heavy_parts, n_reduce, 0, C.ptr(self.hub_chunks), C.ptr(self.tail_chunks),
+                              C.ptr(self.hub_words), C.ptr(self.tail_cols), C.ptr(self.slice_ptr),
+                              C.ptr(self.slice_parts), C.ptr(self.heavy_slices), C.ptr(self.reduce_items),
+                              C.ptr(self.reduce_parts), C.ptr(self.block_chunk_begin),
+                              C.ptr(self.cta_hub_begin), C.ptr(self.cta_tail_begin))
+
+    def nbytes(self) -> int:
+        return sum(int(t.numel()) * t.element_size() for t in (self.hub_chunks, self.tail_chunks, self.hub_words,
+                                                               self.tail_cols, self.slice_ptr, self.slice_parts))
+
+
 class CsrView:
     """One CSR structure in HBM with its merge-path partition and cross-tile workspace."""
 
@@ -86,6 +264,17 @@ class CsrView:
         self._ws = None
         self._istream = None
         self._vstream = {}
+        self._hsell = {}
+        self.n_cols = self.n          # length of the gather vector (larger than n for a row-partitioned slice)
+        self.hsell_segments = (1, None)
+
+    def hsell(self, dtype: torch.dtype) -> Optional[HsellForm]:
+        """Hub-blocked sliced-ELL form for this dtype (unweighted graphs; None when disabled)."""
+        if self.weighted or self.nnz == 0 or not hsell_config()["enabled"]:
+            return None
+        if dtype not in self._hsell:
+            self._hsell[dtype] = HsellForm(self, dtype, self.hsell_segments[0], self.hsell_segments[1])
+        return self._hsell[dtype]
 
     def istream(self) -> torch.Tensor:
         """Item-space index stream (row entries + terminator -1-deg) read by the fused kernels."""
@@ -122,22 +311,28 @@ class CsrView:
             self._values[dtype] = self._values[torch.float64].to(dtype)
         return self._values[dtype]
 
-    def cstruct(self, dtype: torch.dtype) -> C.Csr:
+    def cstruct(self, dtype: torch.dtype, hsell: bool = True) -> C.Csr:
+        form = self.hsell(dtype) if hsell else None
         return C.Csr(self.n, self.nnz, C.ptr(self.indptr), C.ptr(self.indices), C.ptr(self.values(dtype)),
                      C.ptr(self.tile_row), self.n_tiles, self.tile_items, C.ptr(self.istream()),
-                     C.ptr(self.vstream(dtype)))
+                     C.ptr(self.vstream(dtype)), ctypes.addressof(form.struct) if form is not None else None)
 
-    def new_span_ws(self):
-        """Zeroed cross-tile workspace (one per concurrently running filter)."""
+    def new_span_ws(self, dtype: Optional[torch.dtype] = None):
+        """Zeroed cross-tile workspace (one per concurrently running filter); with a dtype also the
+        partial-row buffer of the hsell form."""
         dev = self.indptr.device
         acc = torch.zeros(max(self.n_tiles, 1), dtype=torch.float64, device=dev)
         cnt = torch.zeros(max(self.n_tiles, 1), dtype=torch.int32, device=dev)
-        return (acc, cnt)
+        form = self.hsell(dtype) if dtype is not None else None
+        partials = torch.empty(max(form.n_partials, 1) * 32, dtype=dtype, device=dev) if form is not None else None
+        return (acc, cnt, partials)
 
-    def span_ws(self):
+    def span_ws(self, dtype: Optional[torch.dtype] = None):
         if self._ws is None:
-            self._ws = self.new_span_ws()
-        return self._ws
+            self._ws = {}
+        if dtype not in self._ws:
+            self._ws[dtype] = self.new_span_ws(dtype)
+        return self._ws[dtype]
 
     def with_values(self, values64: torch.Tensor) -> "CsrView":
         other = object.__new__(CsrView)
@@ -146,11 +341,12 @@ class CsrView:
         other.weighted = True
         other._ws = None
         other._vstream = {}
+        other._hsell = {}
         return other
 
 
 def span_struct(ws) -> C.SpanWs:
-    return C.SpanWs(C.ptr(ws[0]), C.ptr(ws[1]))
+    return C.SpanWs(C.ptr(ws[0]), C.ptr(ws[1]), C.ptr(ws[2]) if len(ws) > 2 else None)
 
 
 class IdentityNodeMap:
@@ -385,13 +581,16 @@ class DeviceGraph:
         return out
 
     def _spmv_raw(self, view: CsrView, z: torch.Tensor, rscale: Optional[torch.Tensor], dtype, out_perm=None,
-                  out=None) -> torch.Tensor:
+                  out=None, hsell: bool = False) -> torch.Tensor:
+        """One plain gather pass.  ``hsell``: use (and if needed build) the hub-blocked form — worth it for
+        repeated calls (the plugin route's conv), not for the one-off passes of the preprocessor."""
         lib = C.lib()
         if out is None:
             out = torch.empty(self.n, dtype=dtype, device=z.device)
-        cs = view.cstruct(dtype)
+        cs = view.cstruct(dtype, hsell=hsell)
         C.check(lib.pgb_spmv(ctypes.byref(cs), dtype_code(dtype), C.ptr(z), C.ptr(rscale), None, C.ptr(out_perm),
-                             C.ptr(out), span_struct(view.span_ws()), C.stream_ptr()))
+                             C.ptr(out), span_struct(view.span_ws(dtype)), C.stream_ptr()))
+        C.count_launches(2 if cs.hsell else 1)
         return out
 
     # ------------------------------------------------------------------ backend operations
@@ -407,7 +606,7 @@ class DeviceGraph:
         C.check(lib.pgb_scale(self.n, code, C.ptr(x), C.ptr(self.vec("L", dtype)), 1.0, C.ptr(self.perm), C.ptr(z),
                               C.stream_ptr()))
         rscale = None if self.normalization in ("none", "col") else self.vec("R", dtype)
-        y = self._spmv_raw(self.in_view, z, rscale, dtype, out_perm=self.perm)
+        y = self._spmv_raw(self.in_view, z, rscale, dtype, out_perm=self.perm, hsell=True)
         if self.normalization == "laplacian":                 # preprocessing.py:122: -M + I
             y = x - y
         return y

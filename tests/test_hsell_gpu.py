@@ -1,0 +1,218 @@
+"""The hub-blocked sliced-ELL form (csrc/hsell.cu): the device builder must re-encode the CSR
+losslessly (bit-exact structure), its schedule must cover every unit exactly once, and the two-kernel
+step on it must match the oracle / golden vectors with blocks, tails and unit pieces forced to appear on
+small graphs (environment knobs of pygrank_b200.graph.hsell_config)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_GRAPHS, load_golden, rel_l1
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-10
+FP32_TOL = 1e-5
+
+# (block_cols, max_blocks, min_entries, heavy_parts): tiny blocks -> many blocks + a real tail + heavy slices
+SHAPES = [(64, 3, 1, 2), (128, 16, 16, 32), (256, 2, 40, 1), (0, 16, 16, 32)]
+
+
+@pytest.fixture(scope="module")
+def pgb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import pygrank_b200
+    pygrank_b200.lib()
+    return pygrank_b200
+
+
+def _set_shape(monkeypatch, shape):
+    names = ["PGB_HSELL_BLOCK_COLS", "PGB_HSELL_BLOCKS", "PGB_HSELL_MIN_ENTRIES", "PGB_HSELL_HEAVY_PARTS"]
+    for k, v in zip(names, shape):
+        monkeypatch.setenv(k, str(v))
+
+
+def decode(form):
+    """hsell arrays -> sorted (row, col) pairs + schedule checks, in numpy."""
+    CH = 32
+    H, K, S = form.block_cols, form.n_blocks, form.n_slices
+    final_ptr = form.slice_ptr.cpu().numpy().astype(np.int64)
+    final_parts = form.slice_parts.cpu().numpy().astype(np.int64)[:final_ptr[-1]]
+    n1 = form.n_first_level                                   # partial rows written by the gather kernel
+    if form.n_reduce:
+        slice_ptr = form.first_level_ptr.cpu().numpy().astype(np.int64)
+        parts = form.first_level_parts.cpu().numpy().astype(np.int64)[:slice_ptr[-1]]
+        items = form.reduce_items.cpu().numpy().astype(np.int64).reshape(-1, 3)
+        assert len(items) == form.n_reduce and form.n_partials == n1 + form.n_reduce
+        assert np.array_equal(items[:, 2], n1 + np.arange(form.n_reduce)) and (items[:, 1] >= 1).all() and (items[:, 1] <= 32).all()
+        big = np.nonzero(np.diff(slice_ptr) > form.struct.heavy_parts)[0]
+        covered = np.concatenate([np.arange(a, a + c) for a, c, _ in items])
+        want = np.concatenate([np.arange(slice_ptr[b], slice_ptr[b + 1]) for b in big])
+        assert np.array_equal(covered, want)                  # groups tile the first-level lists of the big slices
+        # final lists: big slices name their second-level rows (in group order), the others are unchanged
+        owner = np.searchsorted(slice_ptr, items[:, 0], side="right") - 1
+        for b in big:
+            assert np.array_equal(final_parts[final_ptr[b]:final_ptr[b + 1]], items[owner == b, 2])
+        small = np.setdiff1d(np.arange(S), big)
+        for b in small[:200]:
+            assert np.array_equal(final_parts[final_ptr[b]:final_ptr[b + 1]], parts[slice_ptr[b]:slice_ptr[b + 1]])
+    else:
+        slice_ptr, parts = final_ptr, final_parts
+        assert form.n_partials == n1
+    assert slice_ptr[0] == 0 and (np.diff(slice_ptr) >= 0).all()
+    assert len(np.unique(parts)) == len(parts) and (parts >= 0).all() and (parts < n1).all()
+    part2slice = np.full(n1, -1, dtype=np.int64)
+    part2slice[parts] = np.repeat(np.arange(S, dtype=np.int64), np.diff(slice_ptr))
+    heavy = form.heavy_slices.cpu().numpy()[:form.n_heavy]
+    assert np.array_equal(heavy, np.nonzero(np.diff(final_ptr) > form.struct.heavy_parts)[0])
+    bcb = form.block_chunk_begin.cpu().numpy()
+    assert len(bcb) == K + 1 and bcb[0] == 0 and bcb[-1] == form.n_hub_chunks and (np.diff(bcb) >= 0).all()
+    for begin, count in ((form.cta_hub_begin, form.n_hub_chunks), (form.cta_tail_begin, form.n_tail_chunks)):
+        cb = begin.cpu().numpy()
+        assert len(cb) == form.n_ctas + 1 and cb[0] == 0 and cb[-1] == count and (np.diff(cb) >= 0).all()
+
+    def pieces_of(desc, n_chunks):
+        d = desc.cpu().numpy().view(np.uint32).reshape(-1, 2)[:n_chunks].astype(np.int64)
+        r = np.arange(CH)
+        ends = ((d[:, 1:2] >> r[None, :]) & 1) | (r[None, :] == CH - 1)
+        return d[:, 0:1] + np.cumsum(ends, axis=1) - ends          # piece (partial row) of every round
+
+    rows, cols, written = [], [], []
+    if form.n_hub_chunks:
+        piece = pieces_of(form.hub_chunks, form.n_hub_chunks)                       # [chunks, CH]
+        written.append(np.unique(piece))
+        w = form.hub_words.cpu().numpy().view(np.uint32)[:form.n_hub_chunks * CH * 32].reshape(-1, CH, 32)
+        blk = (np.searchsorted(bcb, np.arange(form.n_hub_chunks), side="right") - 1).astype(np.int64)
+        for part in (w & 0xffff, w >> 16):
+            c_idx, r_idx, lane = np.nonzero(part != H)
+            loc = part[c_idx, r_idx, lane].astype(np.int64)
+            assert (loc < H).all()
+            sl = part2slice[piece[c_idx, r_idx]]
+            assert (sl >= 0).all()                       # real entries only in pieces some slice lists
+            rows.append(sl * 32 + lane)
+            cols.append(blk[c_idx] * H + loc)
+    if form.n_tail_chunks:
+        piece = pieces_of(form.tail_chunks, form.n_tail_chunks)
+        written.append(np.unique(piece))
+        c = form.tail_cols.cpu().numpy()[:form.n_tail_chunks * CH * 32].reshape(-1, CH, 32)
+        c_idx, r_idx, lane = np.nonzero(c >= 0)
+        sl = part2slice[piece[c_idx, r_idx]]
+        assert (sl >= 0).all()
+        rows.append(sl * 32 + lane)
+        cols.append(c[c_idx, r_idx, lane].astype(np.int64))
+    # every partial row is written by exactly one piece, and every listed part is written
+    written = np.concatenate(written) if written else np.zeros(0, np.int64)
+    assert np.array_equal(np.sort(written), np.arange(n1))
+    rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+    cols = np.concatenate(cols) if cols else np.zeros(0, np.int64)
+    order = np.lexsort((cols, rows))
+    return rows[order], cols[order]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype_name", ["float32", "float64"])
+def test_builder_is_lossless(pgb, monkeypatch, shape, dtype_name):
+    import torch
+    from pygrank_b200 import device_synthetic
+    _set_shape(monkeypatch, shape)
+    scale = 13
+    n = 1 << scale
+    src, dst = device_synthetic.rmat_edges_device(scale, 16, seed=2)
+    g = pgb.DeviceGraph.from_edges(n, src, dst, directed=False, drop_self_loops=True, binary=True,
+                                   normalization="symmetric")
+    view = g.in_view
+    form = view.hsell(getattr(torch, dtype_name))
+    assert form is not None
+    rows, cols = decode(form)
+    indptr = view.indptr.cpu().numpy().astype(np.int64)
+    indices = view.indices.cpu().numpy().astype(np.int64)
+    ref_rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    assert rows.size == indices.size
+    assert np.array_equal(rows, ref_rows) and np.array_equal(cols, indices)
+    if shape[0]:
+        assert form.block_cols == shape[0] and form.n_blocks == min(shape[1], -(-n // shape[0]))
+
+
+@pytest.mark.parametrize("name", ["ba2000", "rmat10", "gnp600d"])
+@pytest.mark.parametrize("shape", SHAPES[:3])
+def test_builder_lossless_on_golden_graphs(pgb, monkeypatch, name, shape):
+    import torch
+    _set_shape(monkeypatch, shape)
+    z, A, directed = load_golden(name)
+    g = pgb.DeviceGraph.from_scipy(A, directed=directed, normalization="auto")
+    for view in {id(g.in_view): g.in_view, id(g.out_view): g.out_view}.values():
+        form = view.hsell(torch.float64)
+        rows, cols = decode(form)
+        indptr = view.indptr.cpu().numpy().astype(np.int64)
+        assert np.array_equal(rows, np.repeat(np.arange(view.n, dtype=np.int64), np.diff(indptr)))
+        assert np.array_equal(cols, view.indices.cpu().numpy().astype(np.int64))
+
+
+def _runs(P):
+    return {
+        "ppr85": ("auto", lambda kw: P.PageRank(0.85, tol=1e-9, max_iters=1000, **kw)),
+        "ppr85_col": ("col", lambda kw: P.PageRank(0.85, tol=1e-9, max_iters=1000, **kw)),
+        "ppr90_noq": ("auto", lambda kw: P.PageRank(0.9, tol=1e-9, use_quotient=False, max_iters=1000, **kw)),
+        "heat3_tol9": ("auto", lambda kw: P.HeatKernel(3, tol=1e-9, **kw)),
+        "gen40": ("auto", lambda kw: P.GenericGraphFilter([0.9 ** k for k in range(40)], error_type="iters",
+                                                          max_iters=41, **kw)),
+        "absorb85": ("auto", lambda kw: P.AbsorbingWalks(0.85, tol=1e-9, max_iters=1000, **kw)),
+    }
+
+
+@pytest.mark.parametrize("name", ["ba2000", "rmat10", "gnp600d"])
+@pytest.mark.parametrize("run", ["ppr85", "ppr85_col", "ppr90_noq", "heat3_tol9", "gen40", "absorb85"])
+@pytest.mark.parametrize("shape", SHAPES[:3])
+def test_filters_on_forced_shapes_match_golden(pgb, monkeypatch, name, run, shape):
+    """Same bars as test_gpu_parity (iteration counts equal, fp64 <= 1e-10, fp32 <= 1e-5) with the hsell
+    form cut into many small blocks / unit pieces / a real tail."""
+    import torch
+    _set_shape(monkeypatch, shape)
+    z, A, directed = load_golden(name)
+    norm, make = _runs(pgb)[run]
+    g = pgb.DeviceGraph.from_scipy(A, directed=directed, normalization=norm)
+    P = z["P"]
+    for c in range(min(P.shape[1], 2)):
+        alg = make({"dtype": torch.float64})
+        r = alg(g, P[:, c])
+        assert g.in_view.hsell(torch.float64) is not None
+        assert alg.convergence.iteration == int(z[f"run_{run}_iters"][c]), (name, run, c)
+        assert rel_l1(r.numpy(), z[f"run_{run}_scores"][:, c]) <= FP64_TOL, (name, run, c)
+        alg32 = make({"dtype": torch.float32})
+        r32 = alg32(g, P[:, c])
+        assert abs(alg32.convergence.iteration - int(z[f"run_{run}_iters"][c])) <= 1
+        assert rel_l1(r32.numpy(), z[f"run_{run}_scores"][:, c]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[3], (4096, 4, 16, 4)])
+def test_hsell_equals_item_stream_kernel_rmat17(pgb, monkeypatch, shape):
+    """The two per-iteration kernels are interchangeable: same conv, same PPR iterates (fp64 to rounding),
+    on a graph with hubs, 38 % empty rows and units cut into pieces."""
+    import torch
+    from pygrank_b200 import _capi as C
+    from pygrank_b200 import device_synthetic
+    _set_shape(monkeypatch, shape)
+    scale = 17
+    n = 1 << scale
+    src, dst = device_synthetic.rmat_edges_device(scale, 16, seed=4)
+    g = pgb.DeviceGraph.from_edges(n, src, dst, directed=False, drop_self_loops=True, binary=True,
+                                   normalization="symmetric")
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen)
+    p = torch.zeros(n, dtype=torch.float64, device="cuda")
+    p[torch.randint(0, n, (10,), device="cuda", generator=gen)] = 1.0
+    lib = C.lib()
+    try:
+        y4 = g.conv(x)
+        a4 = pgb.PageRank(0.85, tol=1e-9, max_iters=1000)
+        r4 = a4(g, p).np
+        C.check(lib.pgb_set_kernel_variant(3))
+        y3 = g.conv(x)
+        a3 = pgb.PageRank(0.85, tol=1e-9, max_iters=1000)
+        r3 = a3(g, p).np
+    finally:
+        C.check(lib.pgb_set_kernel_variant(4))
+    assert float((y4 - y3).abs().sum()) <= 1e-14 * float(y3.abs().sum())
+    assert a4.convergence.iteration == a3.convergence.iteration
+    assert float((r4 - r3).abs().sum()) <= 1e-13 * float(r3.abs().sum())
+    e4, e3 = a4.convergence.errors.cpu().numpy(), a3.convergence.errors.cpu().numpy()
+    assert np.allclose(e4, e3, rtol=1e-9, atol=0)
