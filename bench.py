@@ -173,6 +173,8 @@ def run_single(args):
         p = torch.zeros(n, dtype=dtype, device=dev)
         p[torch.from_numpy(s).to(dev)] = 1.0
         pers.append(p)
+    if args.kernel_only:
+        return kernel_leg(args, g, pers[0], dtype, None)
     for i in range(args.warmup):
         alg(g, pers[i])
     torch.cuda.synchronize()
@@ -212,7 +214,29 @@ def run_single(args):
     e2e_value = nnz * e2e_calls / e2e_s / 1e9
     clocks = sampler.stop()
 
-    # ---- the dominant kernel alone: fixed-iteration fused PPR steps, CUDA events on the launch stream
+    kern = kernel_leg(args, g, pers[0], dtype, None)
+    kernel_ms, probe_ms, alg_bytes, achieved, form, symdeg = (kern[k] for k in
+                                                              ("kernel_ms", "probe_ms", "alg_bytes", "achieved", "form", "symdeg"))
+    peak, peak_src = hbm_peak()
+
+    cpu = None
+    if not args.no_cpu:
+        gt, _, sample = cpu_reference_leg(2, 1)
+        cpu = {"value": gt, "unit": "GTEPS", "cores": 1, "kind": "port", "sample": sample}
+    return finish_line(args, locals())
+
+
+def kernel_leg(args, g, pers0, dtype, _unused):
+    """The dominant kernel alone: fixed-iteration fused PPR steps, CUDA events on the launch stream."""
+    import ctypes
+
+    import torch
+
+    from pygrank_b200 import _capi as C
+    from pygrank_b200.graph import dtype_code, span_struct
+    dev = pers0.device
+    n, nnz = g.n, g.nnz
+    w = 4 if dtype == torch.float32 else 8
     lib = C.lib()
     code = dtype_code(dtype)
     st = C.stream_ptr()
@@ -228,7 +252,7 @@ def run_single(args):
     sq, cvec = g.vec("sq", dtype), g.vec("c", dtype)
     zbuf = [torch.empty(n, dtype=dtype, device=dev), torch.empty(n, dtype=dtype, device=dev)]
     q = torch.empty(n, dtype=dtype, device=dev)
-    C.check(lib.pgb_affine_init(n, code, C.ptr(pers[0]), None, C.ptr(sq), C.ptr(cvec), 1 - ALPHA, None, C.ptr(g.perm), 0,
+    C.check(lib.pgb_affine_init(n, code, C.ptr(pers0), None, C.ptr(sq), C.ptr(cvec), 1 - ALPHA, None, C.ptr(g.perm), 0,
                                 C.ptr(zbuf[0]), C.ptr(q), C.ptr(state_f64), st))
     C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
     cs = g.in_view.cstruct(dtype)
@@ -265,13 +289,24 @@ def run_single(args):
     probe_ms = p0.elapsed_time(p1) / 10
     alg_bytes = nnz * 4 + (n + 1) * 4 + 5 * n * w
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    peak, peak_src = hbm_peak()
+    out = {"kernel_ms": kernel_ms, "probe_ms": probe_ms, "alg_bytes": alg_bytes, "achieved": achieved, "form": form,
+           "symdeg": symdeg}
+    if args.kernel_only:
+        print(json.dumps({"kernel_ms": kernel_ms, "gteps": nnz / (kernel_ms * 1e-3) / 1e9, "achieved_gbs": achieved,
+                          "probe_ms": probe_ms, "n": n, "nnz": nnz,
+                          "hsell": None if form is None else {"block_cols": form.block_cols, "n_blocks": form.n_blocks,
+                                                              "hub_chunks": form.n_hub_chunks,
+                                                              "tail_chunks": form.n_tail_chunks,
+                                                              "partial_rows": form.n_partials}}))
+    return out
 
-    cpu = None
-    if not args.no_cpu:
-        gt, _, sample = cpu_reference_leg(2, 1)
-        cpu = {"value": gt, "unit": "GTEPS", "cores": 1, "kind": "port", "sample": sample}
 
+def finish_line(args, v):
+    n, nnz, w, scale = v["n"], v["nnz"], v["w"], v["scale"]
+    value, dev_ms, conv_calls, build_s = v["value"], v["dev_ms"], v["conv_calls"], v["build_s"]
+    e2e_value, launches, achieved, peak, peak_src = v["e2e_value"], v["launches"], v["achieved"], v["peak"], v["peak_src"]
+    form, symdeg, kernel_ms, alg_bytes, probe_ms, cpu, clocks = (v["form"], v["symdeg"], v["kernel_ms"], v["alg_bytes"],
+                                                                 v["probe_ms"], v["cpu"], v["clocks"])
     line = {
         "metric": "PPR GTEPS", "value": value, "unit": "GTEPS", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -311,6 +346,8 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--relabel", default="degree", choices=["degree", "none"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="experiments: time only the fused step (no solves, no e2e, no CPU leg) and print a short line")
     args = ap.parse_args()
     if args.scale is None:
         args.scale = 24 + max(int(np.log2(max(args.gpus, 1))), 0)

@@ -85,14 +85,16 @@ typedef struct pgb_csr {
  * block-local columns (block_cols = padding), a tail round one 32-bit global column per lane (-1 =
  * padding).  The units of a block (slices ascending), then of the next block, form one stream of rounds
  * (each block padded to a whole chunk); the tail units form a second stream.  Streams are cut into
- * CHUNKS of PGB_HSELL_CHUNK rounds, the unit of work of one warp: chunk c starts at word c*32*CHUNK,
- * carries the rounds at which a unit ends inside it (endmask) and the partial row its first piece
- * writes (p_first); a piece ends at every unit end and at the chunk end, and every piece writes one
- * partial row of 32 sums.  slice_parts[slice_ptr[s] .. slice_ptr[s+1]) lists the partial rows of slice
- * s for the update pass.  A slice whose pieces number more than heavy_parts (hub rows: their units span
- * many chunks) is first reduced by groups of 32 partial rows into second-level partial rows
- * (reduce_items / reduce_parts) and lists those instead; if it still lists more than heavy_parts it is
- * also named in heavy_slices (one CTA adds them).  Chunks are dealt to
+ * CHUNKS of PGB_HSELL_CHUNK rounds, the unit of work of one warp: chunk c starts at word c*32*CHUNK and
+ * carries the rounds at which a unit ends inside it (endmask) and the number of its first PIECE
+ * (p_first; pieces are numbered in stream order, hub stream first).  A piece ends at every unit end and
+ * at the chunk end and yields one row of 32 partial sums, written to partial row piece_row[piece].
+ * Partial rows are slice-major: the update pass reads upd_rows[s] = (first row, count) of slice s as one
+ * contiguous run.  A slice with more than heavy_parts pieces (hub rows: their units span many chunks) is
+ * first reduced by groups of 32 consecutive rows into second-level rows (reduce_items; stored after the
+ * first-level rows) and upd_rows names those; if it still has more than heavy_parts it is also listed in
+ * heavy_slices (one CTA adds them).  The padding pieces at the end of a block's stream write the last
+ * (dump) row.  Chunks are dealt to
  * n_ctas CTAs in contiguous ranges (cta_*_begin).  With n_segments > 1 (row-partitioned multi-GPU) the
  * gather vector is n_segments ranges of seg_len entries (one per rank, each degree-ranked), hub block b
  * is the union of entries [b*block_cols/n_segments, ...) of every range, and the CSR given to the
@@ -114,11 +116,10 @@ typedef struct pgb_hsell {
     const uint32_t *tail_chunks;      /* [n_tail_chunks][2]: p_first, endmask                       */
     const uint32_t *hub_words;        /* [n_hub_chunks*CHUNK*32]                                    */
     const int32_t *tail_cols;         /* [n_tail_chunks*CHUNK*32]                                   */
-    const int32_t *slice_ptr;         /* [n_slices+1]                                               */
-    const int32_t *slice_parts;       /* [slice_ptr[n_slices]] partial rows of each slice           */
+    const int32_t *piece_row;         /* [pieces] partial row written by each piece                 */
+    const int32_t *upd_rows;          /* [n_slices][2]: first partial row, count read by the update pass */
     const int32_t *heavy_slices;      /* [n_heavy]                                                  */
-    const int32_t *reduce_items;      /* [n_reduce][3]: first entry of reduce_parts, count, output partial row */
-    const int32_t *reduce_parts;      /* partial rows (first level) of the slices reduced in two levels */
+    const int32_t *reduce_items;      /* [n_reduce][3]: first row, count (<= 32), output row        */
     const int32_t *block_chunk_begin; /* [n_blocks+1] first hub chunk of each block                 */
     const int32_t *cta_hub_begin;     /* [n_ctas+1]                                                 */
     const int32_t *cta_tail_begin;    /* [n_ctas+1]                                                 */
@@ -209,15 +210,20 @@ int pgb_hsell_max_block_cols(int dtype);
  * tail); tail_rounds[s] = longest tail row of the slice. */
 int pgb_hsell_count(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
                     int32_t min_entries, int32_t *hub_rounds, int32_t *tail_rounds, void *stream);
-/* Pass 2 — writes the round data and slice_parts.  The caller supplies, per (block, slice) in
+/* Pass 2 — writes the round data and piece_row.  The caller supplies, per (block, slice) in
  * block-major order and per slice for the tail: the first round of the unit in its stream and the
- * partial row of its first piece (exclusive scans); hub_words must be pre-filled with the padding word
- * (block_cols | block_cols << 16). */
+ * number of its first piece (exclusive scans), and slice_ptr (first partial row of every slice: the
+ * pieces of a slice take consecutive rows, blocks ascending, then the tail).  hub_words must be
+ * pre-filled with the padding word (block_cols | block_cols << 16), tail_cols with -1 and piece_row
+ * with the dump row.  scratch (int32[nnz], or NULL) enables the bank-aware slot order:
+ * within a unit, entry position p of lane l gets a column of shared-memory bank (l + p) mod banks
+ * when the row has one (banks = 32 for fp32, 16 for fp64 vectors), which removes most bank conflicts
+ * of the gather kernel; the order of a row's entries has no other meaning. */
 int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
                    int32_t n_segments, int64_t seg_len, const int32_t *hub_rounds, const int32_t *tail_rounds,
                    const int64_t *hub_round_base, const int64_t *hub_part_base, const int64_t *tail_round_base,
                    const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
-                   int32_t *slice_parts, void *stream);
+                   int32_t *piece_row, int32_t *scratch, int32_t banks, void *stream);
 /* Experiment knob: warps (of 32) per CTA that prefer tail units (L2 gathers) over hub units. */
 int pgb_hsell_set_tail_warps(int warps);
 

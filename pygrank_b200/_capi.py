@@ -39,8 +39,8 @@ class Hsell(Structure):
                 ("n_hub_chunks", c_int32), ("n_tail_chunks", c_int32), ("n_heavy", c_int32), ("heavy_parts", c_int32),
                 ("n_reduce", c_int32), ("reserved0", c_int32),
                 ("hub_chunks", c_void_p), ("tail_chunks", c_void_p), ("hub_words", c_void_p), ("tail_cols", c_void_p),
-                ("slice_ptr", c_void_p), ("slice_parts", c_void_p), ("heavy_slices", c_void_p),
-                ("reduce_items", c_void_p), ("reduce_parts", c_void_p),
+                ("piece_row", c_void_p), ("upd_rows", c_void_p), ("heavy_slices", c_void_p),
+                ("reduce_items", c_void_p),
                 ("block_chunk_begin", c_void_p), ("cta_hub_begin", c_void_p), ("cta_tail_begin", c_void_p)]
 
 
@@ -59,7 +59,7 @@ _SIGNATURES = {
     "pgb_hsell_count": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "pgb_hsell_fill": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_void_p]),
+                               c_void_p, c_int32, c_void_p]),
     "pgb_build_item_stream": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "pgb_gather_probe": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p]),

@@ -36,7 +36,8 @@ constexpr int HS_THREADS = 1024;
 constexpr int HS_WARPS = HS_THREADS / 32;
 constexpr int HS_SMEM_LIMIT = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100a
 constexpr int UPD_BLOCK = 256;
-constexpr int UPD_MIN_CTAS = 6;
+constexpr int UPD_GROUP = 4;   // slices a warp of the update kernel handles together
+constexpr int UPD_AHEAD = 8;   // partial rows per slice requested before the first add
 
 static int g_tail_warps = 8;
 
@@ -110,7 +111,7 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                                   const int64_t *__restrict__ tail_round_base,
                                   const int64_t *__restrict__ tail_part_base, const int32_t *__restrict__ slice_ptr,
                                   uint32_t *__restrict__ hub_words, int32_t *__restrict__ tail_cols,
-                                  int32_t *__restrict__ slice_parts) {
+                                  int32_t *__restrict__ piece_row, int32_t *__restrict__ scratch, int banks) {
     constexpr int CH = PGB_HSELL_CHUNK;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -136,16 +137,75 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                 const int64_t g0 = hub_round_base[(int64_t)blk * n_slices + s];
                 const int64_t wb = g0 * 32;
                 const int base = blk * H;
-                for (int j = 0; j < R; ++j) {
-                    const int i0 = 2 * j, i1 = 2 * j + 1;
-                    const uint32_t lo = (i0 < len) ? (uint32_t)(indices[pos + i0] - base) : (uint32_t)H;
-                    const uint32_t hi = (i1 < len) ? (uint32_t)(indices[pos + i1] - base) : (uint32_t)H;
-                    hub_words[wb + (int64_t)j * 32 + lane] = lo | (hi << 16);
+                if (scratch == nullptr || len < 2) {
+                    for (int j = 0; j < R; ++j) {
+                        const int i0 = 2 * j, i1 = 2 * j + 1;
+                        const uint32_t lo = (i0 < len) ? (uint32_t)(indices[pos + i0] - base) : (uint32_t)H;
+                        const uint32_t hi = (i1 < len) ? (uint32_t)(indices[pos + i1] - base) : (uint32_t)H;
+                        hub_words[wb + (int64_t)j * 32 + lane] = lo | (hi << 16);
+                    }
+                } else {
+                    // Bank-aware slot order.  The 32 lanes of a round read shared memory together; with the
+                    // row's entries in column order their banks are random (measured 2.6 wavefronts per
+                    // LDS).  Entry position p of lane l is given a column of bank (l + p) mod `banks`
+                    // whenever the row has one left, so the lanes of one instruction mostly hit distinct
+                    // banks; the columns without a matching position fill the holes.
+                    const uint32_t HOLE = 0xffffu;
+                    int cnt[32], cur[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) cnt[q] = 0;
+                    for (int i = 0; i < len; ++i) ++cnt[(indices[pos + i] - base) & (banks - 1)];
+                    int run = 0;
+                    for (int q = 0; q < banks; ++q) {
+                        cur[q] = run;
+                        run += cnt[q];
+                    }
+                    for (int i = 0; i < len; ++i) {
+                        const int c = indices[pos + i] - base;
+                        scratch[pos + cur[c & (banks - 1)]++] = c;
+                    }
+                    // cur[q] is now the END of bucket q; the bucket starts cnt[q] earlier
+                    for (int q = 0; q < banks; ++q) cur[q] -= cnt[q];
+                    for (int j = 0; j < R; ++j) {
+                        uint32_t half[2];
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int pp = 2 * j + hh;
+                            if (pp >= len) {
+                                half[hh] = (uint32_t)H;
+                            } else {
+                                const int tb = (lane + pp) & (banks - 1);
+                                if (cnt[tb] > 0) {
+                                    half[hh] = (uint32_t)scratch[pos + cur[tb]++];
+                                    --cnt[tb];
+                                } else {
+                                    half[hh] = HOLE;
+                                }
+                            }
+                        }
+                        hub_words[wb + (int64_t)j * 32 + lane] = half[0] | (half[1] << 16);
+                    }
+                    int bb = 0;
+                    for (int j = 0; j < R; ++j) {
+                        uint32_t w = hub_words[wb + (int64_t)j * 32 + lane];
+                        bool changed = false;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            if (((w >> (16 * hh)) & 0xffffu) == HOLE) {
+                                while (cnt[bb] == 0) ++bb;
+                                const uint32_t v = (uint32_t)scratch[pos + cur[bb]++];
+                                --cnt[bb];
+                                w = (w & ~(0xffffu << (16 * hh))) | (v << (16 * hh));
+                                changed = true;
+                            }
+                        }
+                        if (changed) hub_words[wb + (int64_t)j * 32 + lane] = w;
+                    }
                 }
                 // pieces: the unit is cut at every chunk boundary of its stream
                 const int pieces = (int)((g0 + R - 1) / CH - g0 / CH) + 1;
                 const int64_t p0 = hub_part_base[(int64_t)blk * n_slices + s];
-                for (int p = lane; p < pieces; p += 32) slice_parts[first_part + ord + p] = (int32_t)(p0 + p);
+                for (int p = lane; p < pieces; p += 32) piece_row[p0 + p] = (int32_t)(first_part + ord + p);
                 ord += pieces;
             } else {
                 for (int i = 0; i < len; ++i, ++t)
@@ -158,7 +218,7 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
         if (TR > 0) {
             const int pieces = (int)((tg0 + TR - 1) / CH - tg0 / CH) + 1;
             const int64_t p0 = tail_part_base[s];
-            for (int p = lane; p < pieces; p += 32) slice_parts[first_part + ord + p] = (int32_t)(p0 + p);
+            for (int p = lane; p < pieces; p += 32) piece_row[p0 + p] = (int32_t)(first_part + ord + p);
         }
     }
 }
@@ -171,7 +231,9 @@ struct GatherParams {
     const void *z;
     void *partials;
     const int32_t *stop;   // device state word: run-ahead launches after convergence are no-ops (or NULL)
+    uint32_t *tail_queue;  // global counter of the tail stream (zero at launch; the update kernel resets it)
     int tail_warps;
+    int debug_skip;        // timing experiments only (PGB_HSELL_DEBUG_SKIP): 1 = skip hub chunks, 2 = skip tail chunks
 };
 
 constexpr int CH = PGB_HSELL_CHUNK;   // rounds per chunk
@@ -181,14 +243,17 @@ static_assert(CH == 32 && CH % BATCH == 0, "the end mask of a chunk is one 32-bi
 // One chunk of the hub stream: 32 rounds, two shared-memory gathers per lane and round.
 template <typename T>
 __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, int64_t chunk, uint32_t p_first,
-                                          uint32_t endmask, const T *s_z, T *__restrict__ partials, int lane) {
+                                          uint32_t endmask, const int32_t *__restrict__ piece_row, const T *s_z,
+                                          T *__restrict__ partials, int lane) {
     const uint32_t *d = words + chunk * (CH * 32) + lane;
     endmask |= 0x80000000u;   // the chunk end closes the last piece
+    // a chunk has at most 32 pieces: lane j fetches the partial row of piece j
+    const int my_row = (lane < __popc(endmask)) ? __ldg(piece_row + p_first + lane) : 0;
     uint32_t w[BATCH], nx[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; ++u) w[u] = ld_stream_u32(d + u * 32);
     T a0 = (T)0, a1 = (T)0;
-    int64_t p = p_first;
+    int p = 0;
 #pragma unroll
     for (int bt = 0; bt < CH / BATCH; ++bt) {
         if (bt + 1 < CH / BATCH) {
@@ -208,7 +273,7 @@ __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, in
                 a0 += s_z[w[u] & 0xffffu];
                 a1 += s_z[w[u] >> 16];
                 if ((m8 >> u) & 1u) {
-                    partials[p * 32 + lane] = a0 + a1;
+                    partials[(int64_t)__shfl_sync(0xffffffffu, my_row, p) * 32 + lane] = a0 + a1;
                     ++p;
                     a0 = a1 = (T)0;
                 }
@@ -222,15 +287,16 @@ __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, in
 // One chunk of the tail stream: 32 rounds, one L2 gather per lane and round (padding lanes are off).
 template <typename T>
 __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int64_t chunk, uint32_t p_first,
-                                           uint32_t endmask, const T *__restrict__ z, T *__restrict__ partials,
-                                           int lane) {
+                                           uint32_t endmask, const int32_t *__restrict__ piece_row,
+                                           const T *__restrict__ z, T *__restrict__ partials, int lane) {
     const int32_t *d = cols + chunk * (CH * 32) + lane;
     endmask |= 0x80000000u;
+    const int my_row = (lane < __popc(endmask)) ? __ldg(piece_row + p_first + lane) : 0;
     int32_t c[BATCH], nx[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; ++u) c[u] = ld_stream(d + u * 32);
     T a0 = (T)0, a1 = (T)0;
-    int64_t p = p_first;
+    int p = 0;
 #pragma unroll
     for (int bt = 0; bt < CH / BATCH; ++bt) {
         T x[BATCH];
@@ -252,7 +318,7 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
             for (int u = 0; u < BATCH; ++u) {
                 a0 += x[u];
                 if ((m8 >> u) & 1u) {
-                    partials[p * 32 + lane] = a0 + a1;
+                    partials[(int64_t)__shfl_sync(0xffffffffu, my_row, p) * 32 + lane] = a0 + a1;
                     ++p;
                     a0 = a1 = (T)0;
                 }
@@ -267,7 +333,7 @@ template <typename T>
 __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const GatherParams G) {
     extern __shared__ __align__(16) unsigned char hs_smem[];
     T *s_z = reinterpret_cast<T *>(hs_smem);   // [block_cols + 1]; the last entry is the padding target (0)
-    __shared__ int s_hub_next, s_tail_next;
+    __shared__ int s_hub_next;
 
     if (G.stop && *G.stop != PGB_RUNNING) return;
     const pgb_hsell &h = G.h;
@@ -277,18 +343,19 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
     T *__restrict__ partials = (T *)G.partials;
     const int cta = blockIdx.x;
     const int hub_lo = h.cta_hub_begin[cta], hub_hi = h.cta_hub_begin[cta + 1];
-    const int tail_hi = h.cta_tail_begin[cta + 1];
+    // hub chunks need this CTA's shared-memory block, so they are dealt statically (block-major ranges);
+    // tail chunks need nothing, so every warp of the grid takes them from one global queue: CTAs whose
+    // hub share is cheaper absorb more of the tail and all CTAs end together
+    const int tail_hi = h.n_tail_chunks;
     const bool tail_pref = warp < G.tail_warps;
     const int H = h.block_cols, N = h.n_segments;
     const int Hs = H / N;
-    if (tid == 0) {
-        s_tail_next = h.cta_tail_begin[cta];
-        s_z[H] = (T)0;
-    }
+    if (tid == 0) s_z[H] = (T)0;
 
     auto run_tail = [&](int u) {
+        if (G.debug_skip & 2) return;
         const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.tail_chunks) + u);
-        tail_chunk<T>(h.tail_cols, u, d.x, d.y, z, partials, lane);
+        tail_chunk<T>(h.tail_cols, u, d.x, d.y, h.piece_row, z, partials, lane);
     };
 
     int cur = hub_lo;
@@ -298,7 +365,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
         while (h.block_chunk_begin[blk + 1] <= cur) ++blk;
         const int blk_end = h.block_chunk_begin[blk + 1];
         const int seg_end = blk_end < hub_hi ? blk_end : hub_hi;
-        __syncthreads();   // every warp is done with the previous block (and s_tail_next is initialised)
+        __syncthreads();   // every warp is done with the previous block
         for (int sgm = 0; sgm < N; ++sgm) {
             const int64_t first = (int64_t)sgm * h.seg_len + (int64_t)blk * Hs;
             int64_t avail = h.seg_len - (int64_t)blk * Hs;
@@ -324,7 +391,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
             int kind = 0, u = 0;   // 0: nothing left in this segment, 1: hub chunk, 2: tail chunk
             if (lane == 0) {
                 if (tail_pref && *(volatile int *)&s_hub_next < seg_end) {
-                    u = atomicAdd(&s_tail_next, 1);
+                    u = (int)atomicAdd(G.tail_queue, 1u);
                     if (u < tail_hi) kind = 2;
                 }
                 if (kind == 0) {
@@ -336,8 +403,9 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
             u = __shfl_sync(FULL, u, 0);
             if (kind == 0) break;
             if (kind == 1) {
+                if (G.debug_skip & 1) continue;
                 const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.hub_chunks) + u);
-                hub_chunk<T>(h.hub_words, u, d.x, d.y, s_z, partials, lane);
+                hub_chunk<T>(h.hub_words, u, d.x, d.y, h.piece_row, s_z, partials, lane);
             } else {
                 run_tail(u);
             }
@@ -348,7 +416,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
     // ---- drain the tail queue ---------------------------------------------------------------------
     while (true) {
         int u = 0;
-        if (lane == 0) u = atomicAdd(&s_tail_next, 1);
+        if (lane == 0) u = (int)atomicAdd(G.tail_queue, 1u);
         u = __shfl_sync(FULL, u, 0);
         if (u >= tail_hi) break;
         run_tail(u);
@@ -362,38 +430,36 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
 // ---------------------------------------------------------------------------------------------
 constexpr int UPD_WARPS = UPD_BLOCK / 32;
 
-// Kernel B1 (only when some slice has more than heavy_parts partial rows): every group of <= 32
-// partial rows of such a slice is added by one warp into a second-level partial row, in list order
-// (deterministic); slice_parts of the slice then lists the second-level rows.
+// Kernel B1 (only when some slice has more than heavy_parts pieces): every group of <= 32 consecutive
+// partial rows of such a slice is added by one warp into a second-level row, in order (deterministic);
+// upd_rows of the slice names the second-level rows.
 template <typename T>
 __global__ void __launch_bounds__(256) hsell_reduce_kernel(const pgb_hsell h, T *__restrict__ partials,
                                                            const int32_t *stop) {
     if (stop && *stop != PGB_RUNNING) return;
     const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t it = warp; it < h.n_reduce; it += nwarps) {
         const int32_t start = h.reduce_items[it * 3], cnt = h.reduce_items[it * 3 + 1], out = h.reduce_items[it * 3 + 2];
-        const int mine = (lane < cnt) ? h.reduce_parts[start + lane] : -1;
+        const T *src = partials + (int64_t)start * 32 + lane;
+        T x[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) x[u] = (u < cnt) ? ld_stream(src + u * 32) : (T)0;
         T acc = (T)0;
-        int t = 0;
-        for (; t + 8 <= cnt; t += 8) {
-            T x[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t + u) * 32 + lane);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc += x[u];
-        }
-        for (; t < cnt; ++t) acc += ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t) * 32 + lane);
+        for (int u = 0; u < 32; ++u) acc += x[u];
         partials[(int64_t)out * 32 + lane] = acc;
     }
 }
 
-
+// Kernel B: add the partial rows of each slice (one contiguous run, see upd_rows), fused filter
+// update, convergence reduction.  Slices that still have more than heavy_parts rows are added by a
+// whole CTA first, in a fixed order; the others by one warp, UPD_GROUP slices at a time with all
+// their loads in flight together.
 template <typename T, int MODE, bool SYMDEG>
-__global__ void __launch_bounds__(UPD_BLOCK, UPD_MIN_CTAS) hsell_update_kernel(const StepParams P, const pgb_hsell h,
-                                                                  const T *__restrict__ partials) {
+__global__ void __launch_bounds__(UPD_BLOCK, sizeof(T) == 8 ? 2 : 3) hsell_update_kernel(const StepParams P, const pgb_hsell h,
+                                                                                          const T *__restrict__ partials) {
     __shared__ double s_red[32];
     __shared__ T s_acc[UPD_WARPS][32];
     if (MODE != MODE_CONV) {
@@ -401,8 +467,7 @@ __global__ void __launch_bounds__(UPD_BLOCK, UPD_MIN_CTAS) hsell_update_kernel(c
     }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    const int32_t *__restrict__ slice_ptr = h.slice_ptr;
-    const int32_t *__restrict__ slice_parts = h.slice_parts;
+    const int2 *__restrict__ upd_rows = reinterpret_cast<const int2 *>(h.upd_rows);
     const int heavy_parts = h.heavy_parts;
     RowUpdate<T, MODE, SYMDEG> update(P);
     using Loaded = typename RowUpdate<T, MODE, SYMDEG>::Loaded;
@@ -410,20 +475,15 @@ __global__ void __launch_bounds__(UPD_BLOCK, UPD_MIN_CTAS) hsell_update_kernel(c
     // ---- heavy slices: one CTA each --------------------------------------------------------------
     for (int hi = blockIdx.x; hi < h.n_heavy; hi += gridDim.x) {
         const int64_t s = h.heavy_slices[hi];
-        const int p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
+        const int2 rc = upd_rows[s];
         T acc = (T)0;
-        for (int j0 = p0 + wib * 32; j0 < p1; j0 += UPD_WARPS * 32) {
-            const int mine = (j0 + lane < p1) ? slice_parts[j0 + lane] : -1;
-            const int cnt = (p1 - j0 < 32) ? p1 - j0 : 32;
-            int t = 0;
-            for (; t + 8 <= cnt; t += 8) {
-                T x[8];
+        for (int j0 = wib * 8; j0 < rc.y; j0 += UPD_WARPS * 8) {
+            T x[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t + u) * 32 + lane);
+            for (int u = 0; u < 8; ++u)
+                x[u] = (j0 + u < rc.y) ? ld_stream(partials + (int64_t)(rc.x + j0 + u) * 32 + lane) : (T)0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc += x[u];
-            }
-            for (; t < cnt; ++t) acc += ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t) * 32 + lane);
+            for (int u = 0; u < 8; ++u) acc += x[u];
         }
         s_acc[wib][lane] = acc;
         __syncthreads();
@@ -441,46 +501,74 @@ __global__ void __launch_bounds__(UPD_BLOCK, UPD_MIN_CTAS) hsell_update_kernel(c
         __syncthreads();
     }
 
-    // ---- the other slices: a warp takes 32 consecutive slices at a time -----------------------------
+    // ---- the other slices: a warp takes UPD_GROUP consecutive slices; the first UPD_AHEAD rows of each
+    //      and everything the update reads are requested together (one exposed round trip) -------------
     const int64_t warp = blockIdx.x * (int64_t)UPD_WARPS + wib;
-    const int64_t nwarps = (int64_t)gridDim.x * UPD_WARPS;
+    const int64_t stride = (int64_t)gridDim.x * UPD_WARPS * UPD_GROUP;
     const int64_t n_slices = h.n_slices;
-    for (int64_t s0 = warp * 32; s0 < n_slices; s0 += nwarps * 32) {
-        const int64_t sl = s0 + lane;
-        const int my_p0 = (sl <= n_slices) ? slice_ptr[sl] : 0;
-        int my_p1 = __shfl_down_sync(FULL, my_p0, 1);
-        if (lane == 31) my_p1 = (sl + 1 <= n_slices) ? slice_ptr[sl + 1] : my_p0;
-        const int cnt_here = (int)((n_slices - s0 < 32) ? n_slices - s0 : 32);
-        for (int k = 0; k < cnt_here; ++k) {
-            const int p0 = __shfl_sync(FULL, my_p0, k);
-            const int p1 = __shfl_sync(FULL, my_p1, k);
-            const int np = p1 - p0;
-            if (np > heavy_parts) continue;   // reduced by a CTA above
-            const int64_t row = (s0 + k) * 32 + lane;
-            const bool live = row < P.n;
-            int deg = 0;
-            if (SYMDEG && live) deg = P.indptr[row + 1] - P.indptr[row];
-            Loaded L;
-            if (live) L = update.load(row, deg);
-            const int mine = (lane < np) ? slice_parts[p0 + lane] : -1;
-            T acc = (T)0;
-            int t = 0;
-            for (; t + 4 <= np; t += 4) {
-                T x[4];
+    auto load_rc = [&](int64_t s) -> int2 {
+        return (lane < UPD_GROUP && s + lane < n_slices) ? __ldg(upd_rows + s + lane) : make_int2(0, -1);
+    };
+    update.batch_sums = true;
+    int64_t s0 = warp * UPD_GROUP;
+    int2 rc_cur = load_rc(s0);
+    for (; s0 < n_slices; s0 += stride) {
+        const int2 rc_nxt = load_rc(s0 + stride);   // the next group's runs: one iteration ahead
+        int cnt[UPD_GROUP];
+        const T *prow[UPD_GROUP];
+        bool live[UPD_GROUP];
+        T x[UPD_GROUP][UPD_AHEAD];
+        Loaded L[UPD_GROUP];
+        int ip0[UPD_GROUP], ip1[UPD_GROUP];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t + u) * 32 + lane);
+        for (int k = 0; k < UPD_GROUP; ++k) {
+            cnt[k] = __shfl_sync(FULL, rc_cur.y, k);
+            live[k] = cnt[k] >= 0 && cnt[k] <= heavy_parts;   // else: past the end / added by a CTA above
+            if (!live[k]) cnt[k] = 0;
+            prow[k] = partials + (int64_t)__shfl_sync(FULL, rc_cur.x, k) * 32 + lane;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) acc += x[u];
-            }
-            for (; t < np; ++t) acc += ld_stream(partials + (int64_t)__shfl_sync(FULL, mine, t) * 32 + lane);
-            if (live) update.apply(row, acc, L);
+            for (int u = 0; u < UPD_AHEAD; ++u) x[k][u] = (u < cnt[k]) ? ld_stream(prow[k] + u * 32) : (T)0;
         }
+        const int64_t row0 = s0 * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < UPD_GROUP; ++k) {
+            const int64_t row = row0 + k * 32;
+            live[k] = live[k] && row < P.n;
+            ip0[k] = ip1[k] = 0;
+            if (live[k]) {
+                if (SYMDEG && MODE != MODE_CONV) {
+                    ip0[k] = P.indptr[row];
+                    ip1[k] = P.indptr[row + 1];
+                }
+                L[k] = update.load(row, 0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UPD_GROUP; ++k) {
+            T acc = x[k][0];
+#pragma unroll
+            for (int u = 1; u < UPD_AHEAD; ++u) acc += x[k][u];
+            for (int t = UPD_AHEAD; t < cnt[k]; t += 4) {   // slices with units in many blocks
+                T y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) y[u] = (t + u < cnt[k]) ? ld_stream(prow[k] + (t + u) * 32) : (T)0;
+                acc += (y[0] + y[1]) + (y[2] + y[3]);
+            }
+            if (live[k]) {
+                update.set_degree(L[k], ip1[k] - ip0[k]);
+                update.apply(row0 + k * 32, acc, L[k]);
+            }
+        }
+        update.flush_batch();
+        rc_cur = rc_nxt;
     }
+    if (threadIdx.x == 0 && blockIdx.x == 0 && P.span_cnt) P.span_cnt[0] = 0u;   // tail queue of the next gather
     if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
 }
 
 template <typename T>
-static int launch_gather(const pgb_hsell *h, const void *z, void *partials, const int32_t *stop, cudaStream_t st) {
+static int launch_gather(const pgb_hsell *h, const void *z, void *partials, const int32_t *stop, uint32_t *tail_queue,
+                         cudaStream_t st) {
     static bool configured = false;
     const size_t smem = ((size_t)h->block_cols + 1) * sizeof(T);
     if (smem > (size_t)HS_SMEM_LIMIT - 64) return fail("hsell: block_cols=%d does not fit in shared memory", h->block_cols);
@@ -494,7 +582,14 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, cons
     G.z = z;
     G.partials = partials;
     G.stop = stop;
+    G.tail_queue = tail_queue;
     G.tail_warps = g_tail_warps;
+    static int debug_skip = -1;
+    if (debug_skip < 0) {
+        const char *e = getenv("PGB_HSELL_DEBUG_SKIP");
+        debug_skip = e ? atoi(e) : 0;
+    }
+    G.debug_skip = debug_skip;
     hsell_gather_kernel<T><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
     PGB_LAUNCH_OK("hsell_gather_kernel");
     return 0;
@@ -513,9 +608,16 @@ static int launch_reduce(const pgb_hsell *h, void *partials, const int32_t *stop
 
 template <typename T, int MODE, bool SYMDEG>
 static int launch_update(const StepParams &P, const pgb_hsell *h, const void *partials, cudaStream_t st) {
-    int64_t want = ceil_div(h->n_slices, UPD_WARPS * 32);
+    int64_t want = ceil_div(h->n_slices, UPD_WARPS * UPD_GROUP);
     if (want < h->n_heavy) want = h->n_heavy;
-    const int64_t cap = (int64_t)sm_count() * UPD_MIN_CTAS;
+    static int ctas = 0;
+    if (ctas == 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_kernel<T, MODE, SYMDEG>, UPD_BLOCK, 0) != cudaSuccess || v < 1)
+            v = 2;
+        ctas = v;
+    }
+    const int64_t cap = (int64_t)sm_count() * ctas;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     hsell_update_kernel<T, MODE, SYMDEG><<<(int)want, UPD_BLOCK, 0, st>>>(P, *h, (const T *)partials);
@@ -527,15 +629,16 @@ static int launch_update(const StepParams &P, const pgb_hsell *h, const void *pa
 template <int MODE>
 int hsell_step(const StepParams &P, const pgb_hsell *h, void *partials, int dtype, bool symdeg, cudaStream_t st) {
     if (!partials) return fail("hsell: the workspace has no partials buffer");
+    if (!P.span_cnt) return fail("hsell: the workspace has no counter array");
     if (h->n_rows != P.n) return fail("hsell: form built for %lld rows, graph has %lld", (long long)h->n_rows, (long long)P.n);
     const int32_t *stop = (MODE == MODE_CONV) ? nullptr : P.si + PGB_SI_STOP;
     if (dtype == PGB_F32) {
-        if (launch_gather<float>(h, P.zin, partials, stop, st)) return 1;
+        if (launch_gather<float>(h, P.zin, partials, stop, P.span_cnt, st)) return 1;
         if (launch_reduce<float>(h, partials, stop, st)) return 1;
         return symdeg ? launch_update<float, MODE, true>(P, h, partials, st)
                       : launch_update<float, MODE, false>(P, h, partials, st);
     } else if (dtype == PGB_F64) {
-        if (launch_gather<double>(h, P.zin, partials, stop, st)) return 1;
+        if (launch_gather<double>(h, P.zin, partials, stop, P.span_cnt, st)) return 1;
         if (launch_reduce<double>(h, partials, stop, st)) return 1;
         return symdeg ? launch_update<double, MODE, true>(P, h, partials, st)
                       : launch_update<double, MODE, false>(P, h, partials, st);
@@ -584,15 +687,17 @@ int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int
                    int32_t n_segments, int64_t seg_len, const int32_t *hub_rounds, const int32_t *tail_rounds,
                    const int64_t *hub_round_base, const int64_t *hub_part_base, const int64_t *tail_round_base,
                    const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
-                   int32_t *slice_parts, void *stream) {
+                   int32_t *piece_row, int32_t *scratch, int32_t banks, void *stream) {
     if (n <= 0) return 0;
+    if (scratch && (banks < 1 || banks > 32 || (banks & (banks - 1)))) return fail("pgb_hsell_fill: banks must be a power of two <= 32");
+    if (scratch && block_cols >= 0xffff) return fail("pgb_hsell_fill: bank-aware ordering needs block_cols < 65535");
     if (n_segments < 1 || block_cols % n_segments) return fail("pgb_hsell_fill: block_cols must be a multiple of n_segments");
     const int64_t n_slices = ceil_div(n, 32);
     const int grid = stride_grid(n_slices * 32, 256);
     hsell_fill_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n_slices, indptr, indices, block_cols, n_blocks, n_segments,
                                                            seg_len, hub_rounds, tail_rounds, hub_round_base, hub_part_base,
                                                            tail_round_base, tail_part_base, slice_ptr, hub_words,
-                                                           tail_cols, slice_parts);
+                                                           tail_cols, piece_row, scratch, banks);
     PGB_LAUNCH_OK("hsell_fill_kernel");
     return 0;
 }

@@ -82,8 +82,17 @@ struct RowUpdate {
     T alpha, invS, coef;
     int err_mode;
     double err, tsum;
+    T berr, btsum;      // fp32 batch sums (see apply)
+    bool batch_sums;
 
-    __device__ __forceinline__ RowUpdate(const StepParams &p) : P(p), err(0.0), tsum(0.0) {
+    __device__ __forceinline__ void flush_batch() {
+        err += (double)berr;
+        tsum += (double)btsum;
+        berr = btsum = (T)0;
+    }
+
+    __device__ __forceinline__ RowUpdate(const StepParams &p) : P(p), err(0.0), tsum(0.0), berr((T)0), btsum((T)0),
+                                                                batch_sums(false) {
         alpha = (T)p.alpha;
         invS = (T)1;
         coef = (T)0;
@@ -127,6 +136,15 @@ struct RowUpdate {
         return L;
     }
 
+    // load() may be called with deg = 0 before the row pointers have arrived (so that its loads are not
+    // queued behind them); set_degree() then completes the degree-derived factors.
+    __device__ __forceinline__ void set_degree(Loaded &L, int deg) const {
+        if (SYMDEG && MODE != MODE_CONV) {
+            L.wi = deg > 0 ? RowMath<T>::inv((T)deg) : (T)0;
+            L.sqi = deg > 0 ? RowMath<T>::root((T)deg) : (T)1;
+        }
+    }
+
     __device__ __forceinline__ void apply(int64_t row, T acc, const Loaded &L) {
         const int64_t own = P.out_offset + row;
         if (MODE == MODE_CONV) {
@@ -138,9 +156,17 @@ struct RowUpdate {
         if (MODE == MODE_AFFINE) {
             const T znew = (alpha * L.wi * acc + L.a) * invS;
             ((T *)P.zout)[own] = znew;
-            double d = (double)L.sqi * fabs((double)znew - (double)L.zi);
-            err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
-            tsum += (double)znew * (double)L.b;
+            if (sizeof(T) == 4 && batch_sums) {
+                // fp32 mode inside the hsell update pass: a few rows are summed in fp32 and flushed to the
+                // fp64 accumulators once per group (flush_batch) — one DADD pair per group instead of per row
+                const T d = L.sqi * fabsf((float)(znew - L.zi));
+                berr += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+                btsum += znew * L.b;
+            } else {
+                double d = (double)L.sqi * fabs((double)znew - (double)L.zi);
+                err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+                tsum += (double)znew * (double)L.b;
+            }
         } else {  // MODE_POLY
             const T pw = L.sqi * L.zi;
             if (coef != (T)0) {  // abstract_filters.py:226-228

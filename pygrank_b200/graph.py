@@ -75,14 +75,17 @@ def _env_int(name: str, default: int) -> int:
 
 
 def hsell_config() -> dict:
-    """Knobs of the hub-blocked sliced-ELL builder (environment overrides are for tests/experiments):
-    block_cols 0 = the most the gather kernel can keep in shared memory for the dtype."""
+    """Knobs of the hub-blocked sliced-ELL builder (environment overrides are for tests/experiments).
+    block_cols 0 = 128 KB of the gather vector per block: measured best on B200 — the rest of the SM's
+    256 KB stays L1, which the L2 gathers of the tail need for their in-flight lines (with the full
+    227 KB in shared memory the same tail ran 2x slower)."""
     return {
         "enabled": _env_int("PGB_HSELL", 1) != 0,
         "block_cols": _env_int("PGB_HSELL_BLOCK_COLS", 0),
-        "max_blocks": _env_int("PGB_HSELL_BLOCKS", 16),
-        "min_entries": _env_int("PGB_HSELL_MIN_ENTRIES", 16),
+        "max_blocks": _env_int("PGB_HSELL_BLOCKS", 64),
+        "min_entries": _env_int("PGB_HSELL_MIN_ENTRIES", 32),
         "heavy_parts": min(max(_env_int("PGB_HSELL_HEAVY_PARTS", 32), 1), 32),
+        "bank_order": _env_int("PGB_HSELL_BANK_ORDER", 1) != 0,
     }
 
 
@@ -101,7 +104,7 @@ class HsellForm:
         seg_len = int(seg_len) if seg_len is not None else n_cols
         i64 = torch.int64
         cap = lib.pgb_hsell_max_block_cols(code)
-        H = cfg["block_cols"] if cfg["block_cols"] > 0 else cap
+        H = cfg["block_cols"] if cfg["block_cols"] > 0 else (128 * 1024) // (4 if dtype == torch.float32 else 8)
         H = min(H, cap)
         H -= H % (4 * n_segments)                        # equal 16-byte aligned parts per segment
         if H < 4 * n_segments:
@@ -159,31 +162,27 @@ class HsellForm:
             n_hub_chunks = n_hub_parts = 0
             bcb = torch.zeros(1, dtype=i64, device=dev)
         tail_g0, tail_p0, tail_pieces, self.tail_chunks, n_tail_chunks, n_tail_parts, _ = stream_layout(tr, n_hub_parts)
-        n_partials = n_hub_parts + n_tail_parts
+        n_pieces = n_hub_parts + n_tail_parts                       # pieces in stream order (hub stream, then tail)
         per_slice = tail_pieces + (hub_pieces.view(K, S).sum(0) if K > 0 else 0)
         slice_ptr64 = torch.zeros(S + 1, dtype=i64, device=dev)
         torch.cumsum(per_slice, 0, out=slice_ptr64[1:])
-        n_parts_listed = int(slice_ptr64[-1])
+        n_rows1 = int(slice_ptr64[-1])                              # first-level partial rows, slice-major
         n_hub_words, n_tail_words = n_hub_chunks * CH * 32, n_tail_chunks * CH * 32
-        if max(n_hub_words, n_tail_words) >= 2 ** 31 or max(n_partials, n_parts_listed) >= 2 ** 31:
+        if max(n_hub_words, n_tail_words) >= 2 ** 31 or max(n_pieces, n_rows1) >= 2 ** 31 - 2 ** 20:
             raise Exception("hsell: graph exceeds the 32-bit offsets of one device; row-partition it")
         self.slice_ptr = slice_ptr64.to(torch.int32)
         pad_word = (H | (H << 16))
         pad_word = pad_word - 2 ** 32 if pad_word >= 2 ** 31 else pad_word
         self.hub_words = torch.full((max(n_hub_words, 1),), pad_word, dtype=torch.int32, device=dev)
         self.tail_cols = torch.full((max(n_tail_words, 1),), -1, dtype=torch.int32, device=dev)
-        self.slice_parts = torch.empty(max(n_parts_listed, 1), dtype=torch.int32, device=dev)
-        C.check(lib.pgb_hsell_fill(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, n_segments, seg_len,
-                                   C.ptr(hub_rounds), C.ptr(tail_rounds), C.ptr(hub_g0), C.ptr(hub_p0),
-                                   C.ptr(tail_g0), C.ptr(tail_p0), C.ptr(self.slice_ptr), C.ptr(self.hub_words),
-                                   C.ptr(self.tail_cols), C.ptr(self.slice_parts), st))
-        # slices with many pieces (hub rows) are reduced in two levels: groups of 32 first-level partial
-        # rows -> one second-level row each (kernel B1), which the slice then lists instead
+        # slices with many pieces (hub rows) are reduced in two levels: groups of 32 consecutive
+        # first-level rows -> one second-level row each (kernel B1); the slice then reads those
         heavy_parts = cfg["heavy_parts"]
         big = torch.nonzero(per_slice > heavy_parts).reshape(-1)
+        upd_begin = slice_ptr64[:-1].clone()
+        upd_count = per_slice.clone()
         n_reduce = 0
         self.reduce_items = torch.zeros(3, dtype=torch.int32, device=dev)
-        self.reduce_parts = self.slice_parts
         if big.numel():
             cnt1 = per_slice[big]
             groups = (cnt1 + 31) // 32
@@ -193,27 +192,22 @@ class HsellForm:
             k = torch.arange(n_reduce, device=dev, dtype=i64) - first_item[owner]                # group index in slice
             start = slice_ptr64[big][owner] + 32 * k
             count = torch.clamp(cnt1[owner] - 32 * k, max=32)
-            out_row = n_partials + torch.arange(n_reduce, device=dev, dtype=i64)
+            out_row = n_rows1 + torch.arange(n_reduce, device=dev, dtype=i64)
             self.reduce_items = torch.stack([start, count, out_row], 1).to(torch.int32).contiguous()
-            self.reduce_parts = self.slice_parts                                                  # first-level lists
-            # final lists: big slices list their second-level rows
-            per_final = per_slice.clone()
-            per_final[big] = groups
-            final_ptr = torch.zeros(S + 1, dtype=i64, device=dev)
-            torch.cumsum(per_final, 0, out=final_ptr[1:])
-            final_parts = torch.empty(max(int(final_ptr[-1]), 1), dtype=torch.int32, device=dev)
-            is_big = torch.zeros(S, dtype=torch.bool, device=dev)
-            is_big[big] = True
-            src_slice = torch.repeat_interleave(torch.arange(S, device=dev), per_slice)          # first-level entry -> slice
-            keep = ~is_big[src_slice]
-            pos_in_slice = torch.arange(n_parts_listed, device=dev, dtype=i64) - slice_ptr64[:-1][src_slice]
-            final_parts[(final_ptr[:-1][src_slice] + pos_in_slice)[keep]] = self.slice_parts[:n_parts_listed][keep]
-            final_parts[final_ptr[:-1][big][owner] + k] = out_row.to(torch.int32)
-            self.first_level_ptr, self.first_level_parts = self.slice_ptr, self.slice_parts
-            self.slice_ptr, self.slice_parts = final_ptr.to(torch.int32), final_parts
-            per_slice = per_final
-            n_partials += n_reduce
-        self.heavy_slices = torch.nonzero(per_slice > heavy_parts).reshape(-1).to(torch.int32)
+            upd_begin[big] = n_rows1 + first_item
+            upd_count[big] = groups
+        dump_row = n_rows1 + n_reduce                               # written by the padding pieces of the streams
+        n_partials = dump_row + 1
+        self.upd_rows = torch.stack([upd_begin, upd_count], 1).to(torch.int32).contiguous()
+        self.piece_row = torch.full((max(n_pieces, 1),), dump_row, dtype=torch.int32, device=dev)
+        scratch = torch.empty(max(view.nnz, 1), dtype=torch.int32, device=dev) if cfg["bank_order"] else None
+        C.check(lib.pgb_hsell_fill(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, n_segments, seg_len,
+                                   C.ptr(hub_rounds), C.ptr(tail_rounds), C.ptr(hub_g0), C.ptr(hub_p0),
+                                   C.ptr(tail_g0), C.ptr(tail_p0), C.ptr(self.slice_ptr), C.ptr(self.hub_words),
+                                   C.ptr(self.tail_cols), C.ptr(self.piece_row), C.ptr(scratch),
+                                   32 if dtype == torch.float32 else 16, st))
+        del scratch
+        self.heavy_slices = torch.nonzero(upd_count > heavy_parts).reshape(-1).to(torch.int32)
         n_heavy = int(self.heavy_slices.numel())
         if n_heavy == 0:
             self.heavy_slices = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -230,20 +224,21 @@ class HsellForm:
         self.block_chunk_begin = bcb.to(torch.int32)
         self.n_partials, self.block_cols, self.n_blocks, self.n_ctas = n_partials, H, K, n_ctas
         self.n_hub_chunks, self.n_tail_chunks, self.n_heavy = n_hub_chunks, n_tail_chunks, n_heavy
-        self.n_reduce, self.n_first_level = n_reduce, n_hub_parts + n_tail_parts
+        self.n_reduce, self.n_pieces, self.n_rows1 = n_reduce, n_pieces, n_rows1
         self.n_hub_words, self.n_tail_words = n_hub_words, n_tail_words
         self.n_slices, self.n_segments, self.seg_len = S, n_segments, seg_len
         self.dtype = dtype
         self.struct = C.Hsell(n, S, n_partials, seg_len, n_segments, H, K, n_ctas, n_hub_chunks, n_tail_chunks,
                               n_heavy, heavy_parts, n_reduce, 0, C.ptr(self.hub_chunks), C.ptr(self.tail_chunks),
-                              C.ptr(self.hub_words), C.ptr(self.tail_cols), C.ptr(self.slice_ptr),
-                              C.ptr(self.slice_parts), C.ptr(self.heavy_slices), C.ptr(self.reduce_items),
-                              C.ptr(self.reduce_parts), C.ptr(self.block_chunk_begin),
+                              C.ptr(self.hub_words), C.ptr(self.tail_cols), C.ptr(self.piece_row),
+                              C.ptr(self.upd_rows), C.ptr(self.heavy_slices), C.ptr(self.reduce_items),
+                              C.ptr(self.block_chunk_begin),
                               C.ptr(self.cta_hub_begin), C.ptr(self.cta_tail_begin))
 
     def nbytes(self) -> int:
         return sum(int(t.numel()) * t.element_size() for t in (self.hub_chunks, self.tail_chunks, self.hub_words,
-                                                               self.tail_cols, self.slice_ptr, self.slice_parts))
+                                                               self.tail_cols, self.slice_ptr, self.piece_row,
+                                                               self.upd_rows))
 
 
 class CsrView:

@@ -35,35 +35,37 @@ def decode(form):
     """hsell arrays -> sorted (row, col) pairs + schedule checks, in numpy."""
     CH = 32
     H, K, S = form.block_cols, form.n_blocks, form.n_slices
-    final_ptr = form.slice_ptr.cpu().numpy().astype(np.int64)
-    final_parts = form.slice_parts.cpu().numpy().astype(np.int64)[:final_ptr[-1]]
-    n1 = form.n_first_level                                   # partial rows written by the gather kernel
+    slice_ptr = form.slice_ptr.cpu().numpy().astype(np.int64)            # first-level rows, slice-major
+    n1 = form.n_rows1
+    assert slice_ptr[0] == 0 and slice_ptr[-1] == n1 and (np.diff(slice_ptr) >= 0).all()
+    dump = n1 + form.n_reduce
+    assert form.n_partials == dump + 1
+    piece_row = form.piece_row.cpu().numpy().astype(np.int64)[:form.n_pieces]
+    real = piece_row[piece_row != dump]
+    assert np.array_equal(np.sort(real), np.arange(n1))                  # every first-level row has exactly one writer
+    row2slice = np.repeat(np.arange(S, dtype=np.int64), np.diff(slice_ptr))
+    part2slice = np.where(piece_row == dump, -1, row2slice[np.minimum(piece_row, max(n1 - 1, 0))]) if n1 else \
+        np.full(form.n_pieces, -1, dtype=np.int64)
+    upd = form.upd_rows.cpu().numpy().astype(np.int64).reshape(-1, 2)
+    per_slice = np.diff(slice_ptr)
+    big = np.nonzero(per_slice > form.struct.heavy_parts)[0]
+    small = np.setdiff1d(np.arange(S), big)
+    assert np.array_equal(upd[small, 0], slice_ptr[:-1][small]) and np.array_equal(upd[small, 1], per_slice[small])
     if form.n_reduce:
-        slice_ptr = form.first_level_ptr.cpu().numpy().astype(np.int64)
-        parts = form.first_level_parts.cpu().numpy().astype(np.int64)[:slice_ptr[-1]]
         items = form.reduce_items.cpu().numpy().astype(np.int64).reshape(-1, 3)
-        assert len(items) == form.n_reduce and form.n_partials == n1 + form.n_reduce
+        assert len(items) == form.n_reduce
         assert np.array_equal(items[:, 2], n1 + np.arange(form.n_reduce)) and (items[:, 1] >= 1).all() and (items[:, 1] <= 32).all()
-        big = np.nonzero(np.diff(slice_ptr) > form.struct.heavy_parts)[0]
         covered = np.concatenate([np.arange(a, a + c) for a, c, _ in items])
         want = np.concatenate([np.arange(slice_ptr[b], slice_ptr[b + 1]) for b in big])
-        assert np.array_equal(covered, want)                  # groups tile the first-level lists of the big slices
-        # final lists: big slices name their second-level rows (in group order), the others are unchanged
+        assert np.array_equal(covered, want)                  # groups tile the first-level rows of the big slices
         owner = np.searchsorted(slice_ptr, items[:, 0], side="right") - 1
         for b in big:
-            assert np.array_equal(final_parts[final_ptr[b]:final_ptr[b + 1]], items[owner == b, 2])
-        small = np.setdiff1d(np.arange(S), big)
-        for b in small[:200]:
-            assert np.array_equal(final_parts[final_ptr[b]:final_ptr[b + 1]], parts[slice_ptr[b]:slice_ptr[b + 1]])
+            mine = items[owner == b, 2]
+            assert upd[b, 0] == mine[0] and upd[b, 1] == len(mine) and np.array_equal(mine, mine[0] + np.arange(len(mine)))
     else:
-        slice_ptr, parts = final_ptr, final_parts
-        assert form.n_partials == n1
-    assert slice_ptr[0] == 0 and (np.diff(slice_ptr) >= 0).all()
-    assert len(np.unique(parts)) == len(parts) and (parts >= 0).all() and (parts < n1).all()
-    part2slice = np.full(n1, -1, dtype=np.int64)
-    part2slice[parts] = np.repeat(np.arange(S, dtype=np.int64), np.diff(slice_ptr))
+        assert len(big) == 0
     heavy = form.heavy_slices.cpu().numpy()[:form.n_heavy]
-    assert np.array_equal(heavy, np.nonzero(np.diff(final_ptr) > form.struct.heavy_parts)[0])
+    assert np.array_equal(heavy, np.nonzero(upd[:, 1] > form.struct.heavy_parts)[0])
     bcb = form.block_chunk_begin.cpu().numpy()
     assert len(bcb) == K + 1 and bcb[0] == 0 and bcb[-1] == form.n_hub_chunks and (np.diff(bcb) >= 0).all()
     for begin, count in ((form.cta_hub_begin, form.n_hub_chunks), (form.cta_tail_begin, form.n_tail_chunks)):
@@ -101,7 +103,7 @@ def decode(form):
         cols.append(c[c_idx, r_idx, lane].astype(np.int64))
     # every partial row is written by exactly one piece, and every listed part is written
     written = np.concatenate(written) if written else np.zeros(0, np.int64)
-    assert np.array_equal(np.sort(written), np.arange(n1))
+    assert np.array_equal(np.sort(written), np.arange(form.n_pieces))
     rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
     cols = np.concatenate(cols) if cols else np.zeros(0, np.int64)
     order = np.lexsort((cols, rows))
