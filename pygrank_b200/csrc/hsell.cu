@@ -37,7 +37,7 @@ constexpr int HS_WARPS = HS_THREADS / 32;
 constexpr int HS_SMEM_LIMIT = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100a
 constexpr int UPD_BLOCK = 256;
 constexpr int UPD_GROUP = 4;   // slices a warp of the update kernel handles together
-constexpr int UPD_AHEAD = 8;   // partial rows per slice requested before the first add
+constexpr int UPD_AHEAD = 5;   // partial rows per slice requested before the first add
 
 static int g_tail_warps = 8;
 
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(UPD_BLOCK, sizeof(T) == 8 ? 2 : 3) hsell_updat
     for (; s0 < n_slices; s0 += stride) {
         const int2 rc_nxt = load_rc(s0 + stride);   // the next group's runs: one iteration ahead
         int cnt[UPD_GROUP];
-        const T *prow[UPD_GROUP];
+        uint32_t prow[UPD_GROUP];   // element offset of the slice's first partial row (+ lane): 32-bit on purpose
         bool live[UPD_GROUP];
         T x[UPD_GROUP][UPD_AHEAD];
         Loaded L[UPD_GROUP];
@@ -525,9 +525,9 @@ __global__ void __launch_bounds__(UPD_BLOCK, sizeof(T) == 8 ? 2 : 3) hsell_updat
             cnt[k] = __shfl_sync(FULL, rc_cur.y, k);
             live[k] = cnt[k] >= 0 && cnt[k] <= heavy_parts;   // else: past the end / added by a CTA above
             if (!live[k]) cnt[k] = 0;
-            prow[k] = partials + (int64_t)__shfl_sync(FULL, rc_cur.x, k) * 32 + lane;
+            prow[k] = (uint32_t)__shfl_sync(FULL, rc_cur.x, k) * 32u + (uint32_t)lane;
 #pragma unroll
-            for (int u = 0; u < UPD_AHEAD; ++u) x[k][u] = (u < cnt[k]) ? ld_stream(prow[k] + u * 32) : (T)0;
+            for (int u = 0; u < UPD_AHEAD; ++u) x[k][u] = (u < cnt[k]) ? ld_stream(partials + (prow[k] + u * 32u)) : (T)0;
         }
         const int64_t row0 = s0 * 32 + lane;
 #pragma unroll
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(UPD_BLOCK, sizeof(T) == 8 ? 2 : 3) hsell_updat
             for (int t = UPD_AHEAD; t < cnt[k]; t += 4) {   // slices with units in many blocks
                 T y[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) y[u] = (t + u < cnt[k]) ? ld_stream(prow[k] + (t + u) * 32) : (T)0;
+                for (int u = 0; u < 4; ++u) y[u] = (t + u < cnt[k]) ? ld_stream(partials + (prow[k] + (uint32_t)(t + u) * 32u)) : (T)0;
                 acc += (y[0] + y[1]) + (y[2] + y[3]);
             }
             if (live[k]) {

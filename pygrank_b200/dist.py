@@ -70,6 +70,39 @@ def local_entries(src: torch.Tensor, dst: torch.Tensor, new_id: torch.Tensor, ra
     return rows.to(torch.int32), cols.to(torch.int32)
 
 
+def virtual_columns(cols: torch.Tensor, n_local: int, world: int, block_cols: int, n_blocks: int) -> torch.Tensor:
+    """Global column id (``rank * n_local + position``) -> the virtual column the hsell builders expect
+    (include/pgb200.h, pgb_hsell with n_segments > 1): hub block b gathers positions
+    ``[b*Hs, (b+1)*Hs)`` of EVERY rank's range (Hs = block_cols / world), laid out rank-major inside the
+    block; positions past the hub blocks form the tail, rank-major.  A bijection of ``[0, world*n_local)``;
+    ``real_columns`` (and hsell_real_col in csrc/hsell.cu) is its inverse."""
+    cols = cols.long()
+    hs = block_cols // world
+    rnk = cols // n_local
+    pos = cols - rnk * n_local
+    blk = pos // hs
+    hub = blk < n_blocks
+    v_hub = blk * block_cols + rnk * hs + (pos - blk * hs)
+    tl = n_local - n_blocks * hs
+    v_tail = n_blocks * block_cols + rnk * tl + (pos - n_blocks * hs)
+    return torch.where(hub, v_hub, v_tail)
+
+
+def real_columns(vcols: torch.Tensor, n_local: int, world: int, block_cols: int, n_blocks: int) -> torch.Tensor:
+    v = vcols.long()
+    hs = block_cols // world
+    span = n_blocks * block_cols
+    blk = v // block_cols
+    local = v - blk * block_cols
+    rnk_h = local // hs
+    hub_col = rnk_h * n_local + blk * hs + (local - rnk_h * hs)
+    tl = max(n_local - n_blocks * hs, 1)
+    vt = v - span
+    rnk_t = vt // tl
+    tail_col = rnk_t * n_local + n_blocks * hs + (vt - rnk_t * tl)
+    return torch.where(v < span, hub_col, tail_col)
+
+
 # ------------------------------------------------------------------------------------------------
 class DistGraph:
     """This rank's rows of a symmetric-normalised, unweighted, undirected graph."""
@@ -149,6 +182,31 @@ class DistGraph:
         dist.all_reduce(tot, group=group)
         g.nnz_global = int(tot.item())
         return g
+
+    def hsell(self, dtype: torch.dtype):
+        """Hub-blocked sliced-ELL form of this rank's rows (csrc/hsell.cu) against the all-gathered
+        vector: built once per dtype from a copy of the CSR whose columns are relabelled so that every hub
+        block is one contiguous column range (``virtual_columns``); the copy is dropped afterwards."""
+        from .graph import CsrView, HsellForm, build_csr, hsell_config, hsell_shape
+        if dtype in self.view._hsell:
+            return self.view._hsell[dtype]
+        if not hsell_config()["enabled"] or self.view.nnz == 0:
+            return None
+        lib = C.lib()
+        H, K = hsell_shape(dtype, self.world, self.n_local)
+        dev = self.view.indptr.device
+        rows = torch.empty(self.view.nnz, dtype=torch.int32, device=dev)
+        C.check(lib.pgb_csr_expand_rows(self.n_local, self.view.nnz, C.ptr(self.view.indptr), C.ptr(rows), C.stream_ptr()))
+        vcols = virtual_columns(self.view.indices, self.n_local, self.world, H, K).to(torch.int32)
+        indptr, indices, _ = build_csr(self.n_global, rows, vcols, None, 0)
+        del rows, vcols
+        tmp = CsrView(self.n_local, indptr[: self.n_local + 1].clone(), indices, None)
+        tmp.n_cols = self.n_global
+        form = HsellForm(tmp, dtype, self.world, self.n_local, cfg={"block_cols": H, "max_blocks": K})
+        del tmp
+        self.view._hsell[dtype] = form
+        self.view.n_cols = self.n_global
+        return form
 
     # per-dtype node vectors for the local rows ------------------------------------------------
     def vec(self, name: str, dtype: torch.dtype) -> torch.Tensor:
@@ -251,8 +309,10 @@ class DistPageRank:
         dist.all_reduce(state_f64[C.SF_TACC:C.SF_TACC + 1], group=g.group)
         C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
         C.count_launches(2)
-        cs = g.view.cstruct(dtype, hsell=False)
-        ws = g.view.new_span_ws()
+        form = g.hsell(dtype)
+        cs = g.view.cstruct(dtype, hsell=form is not None)
+        ws = g.view.new_span_ws(dtype if form is not None else None)
+        kernels_per_step = g.view.kernels_per_step(dtype, form is not None)
         acc = state_f64[C.SF_TACC:C.SF_EACC + 1]
 
         budget, done = self.max_iters - 1, 0
@@ -269,7 +329,7 @@ class DistPageRank:
                 dist.all_gather_into_tensor(out, out[off:off + n_loc], group=g.group)
                 dist.all_reduce(acc, group=g.group)
                 C.check(lib.pgb_state_finalize(C.ptr(state_f64), C.ptr(state_i32), C.ptr(err_hist), st))
-            C.count_launches(2 * count)
+            C.count_launches((kernels_per_step + 1) * count)
             done += count
             host = state_i32.cpu()
             stop, steps, iteration = int(host[C.SI_STOP]), int(host[C.SI_STEPS]), int(host[C.SI_ITERATION])

@@ -97,8 +97,9 @@ def run(args):
     zfull = [torch.rand(g.n_global, dtype=dtype, device=dev), torch.rand(g.n_global, dtype=dtype, device=dev)]
     q = torch.zeros(n_loc, dtype=dtype, device=dev)
     cvec = g.vec("c", dtype)
-    cs = g.view.cstruct(dtype, hsell=False)
-    ws = g.view.new_span_ws()
+    form = g.hsell(dtype)
+    cs = g.view.cstruct(dtype, hsell=form is not None)
+    ws = g.view.new_span_ws(dtype if form is not None else None)
     err_hist = torch.zeros(128, dtype=torch.float64, device=dev)
     reps = 20
 
@@ -135,7 +136,9 @@ def run(args):
                     "d2h_bytes_per_step": g.n_local * w * world + 64 * 2},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "item_stream_kernel<%s,unweighted,AFFINE,SYMDEG> (per rank, max over ranks)" % args.dtype,
+                         "traffic": None,
+                         "kernel": ("hsell gather+reduce+update<%s> (one step, per rank, max over ranks)" if form is not None
+                                    else "item_stream_kernel<%s,unweighted,AFFINE,SYMDEG> (per rank, max over ranks)") % args.dtype,
                          "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
             "cpu_baseline": None,
             "clocks": clocks,

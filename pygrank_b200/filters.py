@@ -384,7 +384,7 @@ class RecursiveGraphFilter(GraphFilter):
             C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, float(alpha), C.ptr(w), C.ptr(sq_arg), C.ptr(c),
                                          C.ptr(q), C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(state_f64),
                                          C.ptr(state_i32), C.ptr(err_hist), span_struct(ws), first, count, 1, st))
-            C.count_launches(count * (2 if cs.hsell else 1))
+            C.count_launches(count * view.kernels_per_step(dtype))
 
         steps = self._drive(launch, state_i32, err_hist)
         out = torch.empty(n, dtype=dtype, device=dev)
@@ -474,7 +474,7 @@ class ClosedFormGraphFilter(GraphFilter):
             C.check(lib.pgb_poly_steps(ctypes.byref(cs), code, C.ptr(w), C.ptr(sq_arg), C.ptr(coef_dev), C.ptr(ranks),
                                        C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(state_f64), C.ptr(state_i32),
                                        C.ptr(err_hist), span_struct(ws), first, count, 1, st))
-            C.count_launches(count * (2 if cs.hsell else 1))
+            C.count_launches(count * view.kernels_per_step(dtype))
 
         C.count_launches(3)
         self._drive(launch, state_i32, err_hist)

@@ -89,6 +89,23 @@ def hsell_config() -> dict:
     }
 
 
+def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional[dict] = None):
+    """(block_cols, n_blocks) the builder will use for a gather vector of ``n_segments`` ranges of
+    ``seg_len`` entries (pure arithmetic: the row-partitioned path needs it before it relabels columns)."""
+    cfg = dict(hsell_config(), **(cfg or {}))
+    cap = C.lib().pgb_hsell_max_block_cols(dtype_code(dtype))
+    H = cfg["block_cols"] if cfg["block_cols"] > 0 else (128 * 1024) // (4 if dtype == torch.float32 else 8)
+    H = min(H, cap)
+    H -= H % (4 * n_segments)                        # equal 16-byte aligned parts per segment
+    if H < 4 * n_segments:
+        raise Exception("hsell: block_cols too small")
+    Hs = H // n_segments
+    K = max(min(cfg["max_blocks"], -(-seg_len // Hs)), 0)
+    if n_segments > 1 and K * Hs > seg_len:
+        K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail
+    return H, K
+
+
 class HsellForm:
     """Device arrays of one pgb_hsell (kept alive here; the C struct holds raw pointers)."""
 
@@ -96,23 +113,13 @@ class HsellForm:
                  cfg: Optional[dict] = None):
         lib = C.lib()
         cfg = dict(hsell_config(), **(cfg or {}))
-        code = dtype_code(dtype)
         st = C.stream_ptr()
         dev = view.indptr.device
         n = view.n
         n_cols = view.n_cols
         seg_len = int(seg_len) if seg_len is not None else n_cols
         i64 = torch.int64
-        cap = lib.pgb_hsell_max_block_cols(code)
-        H = cfg["block_cols"] if cfg["block_cols"] > 0 else (128 * 1024) // (4 if dtype == torch.float32 else 8)
-        H = min(H, cap)
-        H -= H % (4 * n_segments)                        # equal 16-byte aligned parts per segment
-        if H < 4 * n_segments:
-            raise Exception("hsell: block_cols too small")
-        Hs = H // n_segments
-        K = max(min(cfg["max_blocks"], -(-seg_len // Hs)), 0)
-        if n_segments > 1 and K * Hs > seg_len:
-            K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail
+        H, K = hsell_shape(dtype, n_segments, seg_len, cfg)
         S = (n + 31) // 32
         CH = C.HSELL_CHUNK
         hub_rounds = torch.zeros(max(K * S, 1), dtype=torch.int32, device=dev)
@@ -198,6 +205,8 @@ class HsellForm:
             upd_count[big] = groups
         dump_row = n_rows1 + n_reduce                               # written by the padding pieces of the streams
         n_partials = dump_row + 1
+        if n_partials >= 2 ** 27:
+            raise Exception("hsell: more than 2^27 partial rows; row-partition the graph")
         self.upd_rows = torch.stack([upd_begin, upd_count], 1).to(torch.int32).contiguous()
         self.piece_row = torch.full((max(n_pieces, 1),), dump_row, dtype=torch.int32, device=dev)
         scratch = torch.empty(max(view.nnz, 1), dtype=torch.int32, device=dev) if cfg["bank_order"] else None
@@ -311,6 +320,12 @@ class CsrView:
         return C.Csr(self.n, self.nnz, C.ptr(self.indptr), C.ptr(self.indices), C.ptr(self.values(dtype)),
                      C.ptr(self.tile_row), self.n_tiles, self.tile_items, C.ptr(self.istream()),
                      C.ptr(self.vstream(dtype)), ctypes.addressof(form.struct) if form is not None else None)
+
+    def kernels_per_step(self, dtype: torch.dtype, hsell: bool = True) -> int:
+        """Kernels one fused step launches (bench.py counts its own launches): gather + update on the hsell
+        form, plus the second-level reduction when some slice needs it; one on the item stream."""
+        form = self._hsell.get(dtype) if hsell else None
+        return 1 if form is None else (3 if form.n_reduce else 2)
 
     def new_span_ws(self, dtype: Optional[torch.dtype] = None):
         """Zeroed cross-tile workspace (one per concurrently running filter); with a dtype also the
@@ -585,7 +600,7 @@ class DeviceGraph:
         cs = view.cstruct(dtype, hsell=hsell)
         C.check(lib.pgb_spmv(ctypes.byref(cs), dtype_code(dtype), C.ptr(z), C.ptr(rscale), None, C.ptr(out_perm),
                              C.ptr(out), span_struct(view.span_ws(dtype)), C.stream_ptr()))
-        C.count_launches(2 if cs.hsell else 1)
+        C.count_launches(view.kernels_per_step(dtype, hsell))
         return out
 
     # ------------------------------------------------------------------ backend operations

@@ -120,3 +120,28 @@ def test_two_rank_partition_and_ppr(tmp_path):
     ref, iters, _ = orc.pagerank(M, p, 0.85, tol=1e-9, max_iters=1000)
     assert int(z["iteration"]) == iters
     assert np.abs(z["scores"] - ref).sum() / np.abs(ref).sum() < 1e-10
+
+
+def test_virtual_columns_are_a_bijection_with_contiguous_hub_blocks():
+    """Host arithmetic of the multi-GPU hsell form (pygrank_b200.dist.virtual_columns): every hub block
+    is one contiguous virtual range holding the same positions of every rank, rank-major; the map is
+    a bijection and real_columns (mirrored by hsell_real_col in csrc/hsell.cu) inverts it."""
+    import torch
+    from pygrank_b200.dist import real_columns, virtual_columns
+    for world, n_local, H, K in [(2, 1000, 64, 5), (4, 4096, 256, 16), (8, 777, 64, 0), (2, 640, 128, 10), (1, 500, 64, 3)]:
+        n = world * n_local
+        cols = torch.arange(n)
+        v = virtual_columns(cols, n_local, world, H, K)
+        assert sorted(v.tolist()) == list(range(n)) or (K * H > 0 and v.max() < max(n, K * H + world * max(n_local - K * (H // world), 0)))
+        assert len(set(v.tolist())) == n
+        assert torch.equal(real_columns(v, n_local, world, H, K), cols)
+        hs = H // world
+        for b in range(K):
+            inside = (v >= b * H) & (v < (b + 1) * H)
+            pos = cols[inside] % n_local
+            assert int(inside.sum()) == world * hs and int(pos.min()) == b * hs and int(pos.max()) == (b + 1) * hs - 1
+            # rank-major inside the block: local index = rank*hs + (pos - b*hs)
+            rnk = cols[inside] // n_local
+            assert torch.equal(v[inside] - b * H, rnk * hs + (pos - b * hs))
+        tail = v >= K * H
+        assert int(tail.sum()) == world * (n_local - K * hs)
