@@ -318,7 +318,8 @@ def finish_line(args, v):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None,
-                     "kernel": ("hsell_gather_kernel<%s> + hsell_update_kernel<%s,AFFINE,SYMDEG=%s> (one step)"
+                     "kernel": ("one fused step = hsell_gather_kernel<%s> (dominant, ~2/3 of the step) + hsell_reduce_kernel"
+                                " + hsell_update_kernel<%s,AFFINE,SYMDEG=%s>"
                                 if form is not None else "item_stream_kernel<%s,unweighted,AFFINE,SYMDEG=%s>")
                      % ((args.dtype, args.dtype, symdeg) if form is not None else (args.dtype, symdeg)),
                      "kernel_ms": kernel_ms, "kernel_gteps": nnz / (kernel_ms * 1e-3) / 1e9,

@@ -248,8 +248,18 @@ class RecursiveGraphFilter(GraphFilter):
         return self._affine(g, p, norm, warm, **self._affine_args(g, **kwargs))
 
     def _can_batch(self, g, warm_start=None, graph_dropout: float = 0, **kwargs) -> bool:
-        # the panel kernel streams no edge values (every BASELINE config is unweighted)
-        return (not g.in_view.weighted) and warm_start is None and graph_dropout == 0 and not g.pathological
+        # The panel kernel streams no edge values (every BASELINE config is unweighted).  It gathers from
+        # L2/HBM (8 columns per 32-byte sector); measured on RMAT-24 it advances a column-iteration in
+        # 1.09 ms, the hub-blocked single-vector kernel (csrc/hsell.cu) in 0.67 ms, so propagate() runs the
+        # columns one after the other through hsell whenever that form exists and uses the panel kernel
+        # otherwise (PGB_PANEL=1 forces it: parity tests and A/B timing).
+        if g.in_view.weighted or warm_start is not None or graph_dropout != 0 or g.pathological:
+            return False
+        import os
+        forced = os.environ.get("PGB_PANEL")
+        if forced not in (None, ""):
+            return forced != "0"
+        return g.in_view.hsell(self.dtype) is None
 
     def _propagate_batched(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
         """All feature columns through ``pgb_affine_steps_batched``: panels of ``pgb_panel_width``

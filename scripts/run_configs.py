@@ -6,8 +6,9 @@ against the oracle at a size the CPU finishes in seconds.  Writes gpurun_out/con
 
 C1  PageRank(0.85, tol 1e-9) symmetric on Barabási–Albert n=100k m=5, 10 seed sets (fp64), vs oracle
 C2  HeatKernel(t=3) and GenericGraphFilter K=40 on RMAT scale 22, fp64 and fp32
+C3  256 seed sets through propagate() (panel SpMM kernel) on RMAT scale 24, fp32
 C5  32 alphas of PageRank + AbsorbingWalks on Barabási–Albert n=10M m=8 (fp32)
-(C3 batched and C4 multi-GPU are measured by their own entry points.)
+(C4, multi-GPU, is measured by bench.py --gpus N.)
 """
 import argparse
 import json
@@ -107,6 +108,53 @@ def main():
                                  "rel_l1_fp64": rel_l1(r64, ref), "rel_l1_fp32": rel_l1(r32, ref)}
     report["C2"] = c2
     print("C2", c2, flush=True)
+
+    # ---------------------------------------------------------------- C3
+    scale, B = (14, 16) if args.quick else (24, 256)
+    g = device_synthetic.rmat_graph_device(scale, 16, seed=1)
+    n = g.n
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    P = torch.zeros((n, B), dtype=torch.float32, device="cuda")
+    idx = torch.randint(0, n, (10, B), device="cuda", generator=gen)
+    P[idx, torch.arange(B, device="cuda")[None, :].expand(10, B)] = 1.0
+    alg = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=torch.float32)
+    alg.propagate(g, P[:, :8].contiguous())
+    dt, out = timed(lambda: alg.propagate(g, P))            # default route: columns one by one through hsell
+    its = list(alg.convergence.iterations)
+    calls = sum(i - 1 for i in its)
+    os.environ["PGB_PANEL"] = "1"                            # the 8-column panel kernel (pgb_affine_steps_batched)
+    alg.propagate(g, P[:, :8].contiguous())
+    dt_panel, out_panel = timed(lambda: alg.propagate(g, P))
+    panel_vs_default = rel_l1(out_panel[:, 1].cpu().numpy(), out[:, 1].cpu().numpy().astype(np.float64))
+    del out_panel
+    os.environ.pop("PGB_PANEL")
+    one = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=torch.float32)
+    one(g, P[:, 0].contiguous())
+    dt1, r1 = timed(lambda: one(g, P[:, 0].contiguous()).np)
+    c3 = {"graph": f"RMAT scale {scale} (n {n}, nnz {g.nnz})", "seed_sets": B, "propagate_s": dt,
+          "panel_kernel_s": dt_panel, "panel_edge_column_gteps": g.nnz * calls / dt_panel / 1e9,
+          "col1_rel_l1_panel_vs_default": panel_vs_default,
+          "column_iterations_min_max": [min(its), max(its)], "edge_column_gteps": g.nnz * calls / dt / 1e9,
+          "single_column_s": dt1, "single_column_gteps": g.nnz * (one.convergence.iteration - 1) / dt1 / 1e9,
+          "col0_rel_l1_propagate_vs_single": rel_l1(out[:, 0].cpu().numpy(), r1.cpu().numpy().astype(np.float64))}
+    del P, out
+    ps = 14
+    gs = device_synthetic.rmat_graph_device(ps, 16, seed=1)
+    Ms = orc.to_sparse_matrix(synthetic.rmat_graph_host(ps, 16, seed=1), "symmetric", False)
+    Pp = np.zeros((1 << ps, 12))
+    for c, sset in enumerate(synthetic.seed_sets(1 << ps, 12, 10, seed=3)):
+        Pp[sset, c] = 1.0
+    a64 = pgb.PageRank(0.85, tol=1e-9, max_iters=1000)
+    o64 = a64.propagate(gs, torch.from_numpy(Pp).cuda()).cpu().numpy()
+    worst, same = 0.0, True
+    for c in range(12):
+        ref, iters, _ = orc.pagerank(Ms, Pp[:, c], 0.85, tol=1e-9, max_iters=1000)
+        worst = max(worst, rel_l1(o64[:, c], ref))
+        same &= a64.convergence.iterations[c] == iters
+    c3["parity"] = {"scale": ps, "columns": 12, "iterations_equal": bool(same), "worst_rel_l1_fp64": worst}
+    report["C3"] = c3
+    print("C3", c3, flush=True)
+    del g, gs
 
     # ---------------------------------------------------------------- C5
     n, m = (200_000, 8) if args.quick else (10_000_000, 8)

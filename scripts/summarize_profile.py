@@ -19,6 +19,28 @@ out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
 
+def step_list():
+    """Per-launch durations of the three kernels of one step (ncu -k regex:hsell_ over bench.py --kernel-only)."""
+    path = os.path.join(ROOT, "gpurun_out", f"launches_{tag}_step.csv")
+    if not os.path.exists(path):
+        return
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = defaultdict(list)
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r.get("Metric Unit", "ns"), 1e-6)
+        agg[r["Kernel Name"].split("(")[0]].append(float(r["Metric Value"].replace(",", "")) * scale)
+    tot = sum(sum(v) / len(v) for v in agg.values()) or 1.0
+    with open(os.path.join(out_dir, f"step_{tag}.md"), "w") as f:
+        f.write(f"# Kernels of one fused PPR step ({tag}), RMAT scale 24 fp32: `ncu --metrics gpu__time_duration.sum "
+                "--clock-control none -k regex:hsell_` over `bench.py --kernel-only`\n\n")
+        f.write("Serialised, cold-cache profiler times: read the SHARES.\n\n| kernel | launches | avg ms | share of the step |\n|---|---:|---:|---:|\n")
+        for name, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write(f"| `{name}` | {len(v)} | {sum(v) / len(v):.4f} | {100 * (sum(v) / len(v)) / tot:.1f}% |\n")
+    print("wrote step list")
+
+
 def launch_list():
     path = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
     if not os.path.exists(path):
@@ -46,6 +68,8 @@ def launch_list():
 
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__inst_executed_op_shared_ld.sum", "sm__cycles_active.avg", "sm__cycles_active.min", "sm__cycles_active.max",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum",
@@ -97,5 +121,10 @@ def kernel_summary(rep, title, fname):
 
 
 launch_list()
+step_list()
 kernel_summary(f"prof_{tag}.ncu-rep", f"Dominant kernel ({tag}): fused PPR step on RMAT scale 24, fp32", f"kernel_{tag}.md")
 kernel_summary(f"prof_{tag}_probe.ncu-rep", f"Gather probe ({tag}): index stream + gathers only, same graph", f"probe_{tag}.md")
+kernel_summary(f"prof_{tag}_gather.ncu-rep",
+               f"Dominant kernel ({tag}): hsell_gather_kernel<float> — one PPR step on RMAT scale 24, fp32", f"kernel_{tag}_gather.md")
+kernel_summary(f"prof_{tag}_update.ncu-rep",
+               f"Second kernel of the step ({tag}): hsell_update_kernel<float, AFFINE, SYMDEG>, same step", f"kernel_{tag}_update.md")

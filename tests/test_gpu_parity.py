@@ -251,10 +251,11 @@ def test_custom_absorption_and_propagate(pgb, torch_cuda, name):
 @pytest.mark.parametrize("run", ["ppr85", "ppr90_noq", "ppr85_col", "ppr85_l1", "ppr85_msq", "ppr85_tol6_mod3",
                                  "absorb85", "absorb85_col"])
 @pytest.mark.parametrize("relabel", ["degree", "none"])
-def test_batched_propagate_matches_golden(pgb, torch_cuda, name, run, relabel):
+def test_batched_propagate_matches_golden(pgb, torch_cuda, monkeypatch, name, run, relabel):
     """propagate() through the panel kernel (pgb_affine_steps_batched): every column must stop at the
     reference's own iteration count and match its scores (signals.py:225-226 runs them one by one)."""
     torch = torch_cuda
+    monkeypatch.setenv("PGB_PANEL", "1")
     z, A, directed = load_golden(name)
     norm, make, _ = _runs(pgb)[run]
     g = _graph(pgb, A, directed, norm, relabel)
@@ -274,10 +275,11 @@ def test_batched_propagate_matches_golden(pgb, torch_cuda, name, run, relabel):
 
 
 @pytest.mark.parametrize("dtype_name,tol", [("float64", 1e-12), ("float32", 2e-6)])
-def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, dtype_name, tol):
+def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, monkeypatch, dtype_name, tol):
     """11 columns (one full panel + a ragged one), one all-zero column, columns that converge at
     different iterations; the batched result must equal the single-column fused path."""
     torch = torch_cuda
+    monkeypatch.setenv("PGB_PANEL", "1")
     from pygrank_b200 import synthetic, device_synthetic
     dtype = getattr(torch, dtype_name)
     scale = 17
