@@ -287,6 +287,32 @@ int pgb_affine_steps_batched(const pgb_csr *g, int dtype, double alpha, const vo
                              int32_t *state_i32, double *err_hist, int32_t hist_stride, pgb_span_ws ws,
                              int first_step, int num_launches, void *stream);
 
+/* ---- row-partitioned multi-GPU: the exchange fused into the step (no reference counterpart) ----------
+ * Every rank keeps the full gather vector (both buffers) and a slot array for the convergence sums in
+ * PEER-MAPPED memory (e.g. torch symmetric memory over NVLink / NVSwitch).  The update kernel then
+ * writes each new z_i straight into the buffers of all ranks — one multimem.st through the NVSwitch
+ * multicast address when mc_zbuf* is set, else one store per peer — and its last CTA writes this rank's
+ * (normaliser, error) sums into slot `rank` of every peer's acc array, so the per-iteration all-gather
+ * and all-reduce disappear; the caller only needs a cross-device barrier before the next step
+ * (which pgb_state_finalize_peer must follow: it adds the slots in rank order, identically everywhere). */
+#define PGB_MAX_PEERS 16
+typedef struct pgb_peers {
+    int32_t n, rank;
+    void *zbuf0[PGB_MAX_PEERS];  /* peer-mapped address of every rank's gather-vector buffer 0 (own included) */
+    void *zbuf1[PGB_MAX_PEERS];
+    void *mc_zbuf0, *mc_zbuf1;   /* multicast addresses of the same buffers, or NULL                          */
+    double *acc[PGB_MAX_PEERS];  /* peer-mapped [n][2] slot arrays                                            */
+} pgb_peers;
+/* pgb_affine_steps for ONE step (step k reads zbuf[(k-1)&1] locally, writes zbuf[k&1] everywhere);
+ * zbuf0/zbuf1 are this rank's own mappings of the buffers named in `peers`. */
+int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *w, const void *sq, const void *c,
+                         const void *q, void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64,
+                         int32_t *state_i32, double *err_hist, pgb_span_ws ws, int step, const pgb_peers *peers,
+                         void *stream);
+/* acc_slots: this rank's own [n][2] slot array (filled by every rank's update kernel). */
+int pgb_state_finalize_peer(double *state_f64, int32_t *state_i32, double *err_hist, const double *acc_slots,
+                            int32_t n, void *stream);
+
 /* One-thread state update for the deferred (multi-GPU) mode. */
 int pgb_state_finalize(double *state_f64, int32_t *state_i32, double *err_hist, void *stream);
 

@@ -44,6 +44,15 @@ class Hsell(Structure):
                 ("block_chunk_begin", c_void_p), ("cta_hub_begin", c_void_p), ("cta_tail_begin", c_void_p)]
 
 
+MAX_PEERS = 16
+
+
+class Peers(Structure):
+    """pgb_peers (include/pgb200.h): peer-mapped buffers of the fused multi-GPU exchange."""
+    _fields_ = [("n", c_int32), ("rank", c_int32), ("zbuf0", c_void_p * MAX_PEERS), ("zbuf1", c_void_p * MAX_PEERS),
+                ("mc_zbuf0", c_void_p), ("mc_zbuf1", c_void_p), ("acc", c_void_p * MAX_PEERS)]
+
+
 class SpanWs(Structure):
     _fields_ = [("acc", c_void_p), ("cnt", c_void_p), ("partials", c_void_p)]
 
@@ -90,6 +99,10 @@ _SIGNATURES = {
                                          c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, SpanWs,
                                          c_int, c_int, c_void_p]),
     "pgb_state_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgb_affine_step_peer": (c_int, [POINTER(Csr), c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, POINTER(Peers),
+                                     c_void_p]),
+    "pgb_state_finalize_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "pgb_scale": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "pgb_unscale": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "pgb_reduce3": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -921,6 +921,67 @@ int pgb_poly_steps(const pgb_csr *g, int dtype, const void *w, const void *sq, c
     return 0;
 }
 
+int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *w, const void *sq, const void *c,
+                         const void *q, void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64,
+                         int32_t *state_i32, double *err_hist, pgb_span_ws ws, int step, const pgb_peers *peers,
+                         void *stream) {
+    StepParams P;
+    memset(&P, 0, sizeof(P));
+    if (fill_graph(P, g)) return 1;
+    if (P.n == 0) return 0;
+    if (!peers || peers->n < 1 || peers->n > PGB_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->n)
+        return fail("pgb_affine_step_peer: bad peer description");
+    const bool symdeg = (w == nullptr && sq == nullptr);
+    if (!symdeg && (!w || !sq)) return fail("pgb_affine_step_peer: w and sq must both be given or both be NULL");
+    if (symdeg && g->values) return fail("pgb_affine_step_peer: degree-derived scales need an unweighted graph");
+    if (step < 1) return fail("pgb_affine_step_peer: step must be >= 1");
+    P.alpha = alpha;
+    P.w = w;
+    P.sq = sq;
+    P.c = c;
+    P.q = q;
+    P.out_offset = out_offset;
+    P.sf = state_f64;
+    P.si = state_i32;
+    P.err_hist = err_hist;
+    P.span_acc = ws.acc;
+    P.span_cnt = ws.cnt;
+    P.partials = ws.partials;
+    P.finalize = 0;
+    void *buf[2] = {zbuf0, zbuf1};
+    P.zin = buf[(step - 1) & 1];
+    P.zout = buf[step & 1];
+    P.n_peers = peers->n;
+    P.peer_rank = peers->rank;
+    for (int r = 0; r < peers->n; ++r) {
+        P.peer_zout[r] = (step & 1) ? peers->zbuf1[r] : peers->zbuf0[r];
+        P.peer_acc[r] = peers->acc[r];
+        if (!P.peer_zout[r] || !P.peer_acc[r]) return fail("pgb_affine_step_peer: peer %d has no buffer", r);
+    }
+    P.mc_zout = (step & 1) ? peers->mc_zbuf1 : peers->mc_zbuf0;
+    return dispatch<MODE_AFFINE>(P, dtype, symdeg, as_stream(stream));
+}
+
+__global__ void state_finalize_peer_kernel(double *sf, int32_t *si, double *err_hist, const double *slots, int n) {
+    if (si[PGB_SI_STOP] != PGB_RUNNING) return;
+    double t = 0.0, e = 0.0;
+    for (int r = 0; r < n; ++r) {   // rank order: the same sum on every rank
+        t += ((const volatile double *)slots)[2 * r];
+        e += ((const volatile double *)slots)[2 * r + 1];
+    }
+    sf[PGB_SF_TACC] = t;
+    sf[PGB_SF_EACC] = e;
+    finalize_state(sf, si, err_hist);
+}
+
+int pgb_state_finalize_peer(double *state_f64, int32_t *state_i32, double *err_hist, const double *acc_slots,
+                            int32_t n, void *stream) {
+    if (!acc_slots || n < 1) return fail("pgb_state_finalize_peer: no slots");
+    state_finalize_peer_kernel<<<1, 1, 0, as_stream(stream)>>>(state_f64, state_i32, err_hist, acc_slots, n);
+    PGB_LAUNCH_OK("state_finalize_peer_kernel");
+    return 0;
+}
+
 int pgb_state_finalize(double *state_f64, int32_t *state_i32, double *err_hist, void *stream) {
     state_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(state_f64, state_i32, err_hist);
     PGB_LAUNCH_OK("state_finalize_kernel");

@@ -32,7 +32,20 @@ struct StepParams {
     int finalize;
     const pgb_hsell *hsell;  // host pointer: hub-blocked sliced-ELL form of the same graph (or NULL)
     void *partials;          // its per-filter workspace
+    // row-partitioned multi-GPU with the exchange fused into the step (pgb_affine_step_peer)
+    int n_peers, peer_rank;
+    void *peer_zout[PGB_MAX_PEERS];
+    void *mc_zout;
+    double *peer_acc[PGB_MAX_PEERS];
 };
+
+// store to a multicast (multimem) address: NVSwitch replicates it into every peer's buffer
+__device__ __forceinline__ void multimem_store(float *mc, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_store(double *mc, double v) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+}
 
 __device__ __forceinline__ void finalize_state(double *sf, int32_t *si, double *err_hist) {
     volatile double *vsf = sf;
@@ -145,6 +158,17 @@ struct RowUpdate {
         }
     }
 
+    // the new iterate: local buffer, or every rank's buffer when the exchange is fused into the step
+    __device__ __forceinline__ void store_z(int64_t own, T v) const {
+        if (P.n_peers == 0) {
+            ((T *)P.zout)[own] = v;
+        } else if (P.mc_zout) {
+            multimem_store((T *)P.mc_zout + own, v);
+        } else {
+            for (int r = 0; r < P.n_peers; ++r) ((T *)P.peer_zout[r])[own] = v;
+        }
+    }
+
     __device__ __forceinline__ void apply(int64_t row, T acc, const Loaded &L) {
         const int64_t own = P.out_offset + row;
         if (MODE == MODE_CONV) {
@@ -155,7 +179,7 @@ struct RowUpdate {
         }
         if (MODE == MODE_AFFINE) {
             const T znew = (alpha * L.wi * acc + L.a) * invS;
-            ((T *)P.zout)[own] = znew;
+            store_z(own, znew);
             if (sizeof(T) == 4 && batch_sums) {
                 // fp32 mode inside the hsell update pass: a few rows are summed in fp32 and flushed to the
                 // fp64 accumulators once per group (flush_batch) — one DADD pair per group instead of per row
@@ -177,7 +201,7 @@ struct RowUpdate {
                 double d = (sizeof(T) == 8) ? fabs((double)prev - (double)cur) : fabs((double)coef * (double)pw);
                 err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
             }
-            ((T *)P.zout)[own] = L.wi * acc;
+            store_z(own, L.wi * acc);
         }
     }
 
@@ -200,12 +224,26 @@ __device__ __forceinline__ void step_epilogue(const StepParams &P, U &update, do
         const int ticket = atomicAdd(&P.si[PGB_SI_TICKET], 1);
         if (ticket == (int)gridDim.x - 1) {
             __threadfence();
-            if (P.finalize)
+            if (P.finalize) {
                 finalize_state(P.sf, P.si, P.err_hist);
-            else
+            } else {
                 P.si[PGB_SI_TICKET] = 0;
+                if (P.n_peers > 0) {
+                    // hand this rank's sums to every rank (slot = our rank); pgb_state_finalize_peer adds the slots
+                    volatile double *vsf = P.sf;
+                    const double t = vsf[PGB_SF_TACC], e = vsf[PGB_SF_EACC];
+                    vsf[PGB_SF_TACC] = 0.0;
+                    vsf[PGB_SF_EACC] = 0.0;
+                    for (int r = 0; r < P.n_peers; ++r) {
+                        P.peer_acc[r][2 * P.peer_rank] = t;
+                        P.peer_acc[r][2 * P.peer_rank + 1] = e;
+                    }
+                    __threadfence_system();
+                }
+            }
         }
     }
+    if (P.n_peers > 0) __threadfence_system();   // peer stores of this thread are performed before the kernel ends
 }
 
 // hsell.cu: one fused step (gather kernel + update kernel) on the hub-blocked sliced-ELL form

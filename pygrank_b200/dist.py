@@ -208,6 +208,49 @@ class DistGraph:
         self.view.n_cols = self.n_global
         return form
 
+    def peer_buffers(self, dtype: torch.dtype):
+        """Peer-mapped buffers for the exchange fused into the step (``pgb_affine_step_peer``): both
+        gather-vector buffers and the convergence-sum slots in torch symmetric memory, so that every rank's
+        update kernel writes its slice straight into all ranks (NVSwitch multicast when available).
+        Returns None when symmetric memory cannot be set up (then the NCCL all-gather path runs);
+        ``PGB_PEER=0`` disables it.  Per-peer NVLink stores are the default: measured on 2 and 8 B200 they are
+        as fast as or faster than the multicast path (1221 vs 1153 GTEPS at N=2, 1865 vs 1835 at N=8), which
+        ``PGB_PEER_MULTICAST=1`` selects."""
+        import os
+        key = ("peer", dtype)
+        if key in self._cache:
+            return self._cache[key]
+        out = None
+        if os.environ.get("PGB_PEER", "1") != "0" and self.world > 1 and self.world <= C.MAX_PEERS:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                dev = self.view.indptr.device
+                group = self.group if self.group is not None else dist.group.WORLD
+                w = 4 if dtype == torch.float32 else 8
+                zsym = symm.empty(2 * self.n_global, dtype=dtype, device=dev)
+                hz = symm.rendezvous(zsym, group)
+                asym = symm.empty(2 * 2 * C.MAX_PEERS, dtype=torch.float64, device=dev)
+                ha = symm.rendezvous(asym, group)
+                asym.zero_()
+                mc = int(hz.multicast_ptr) if os.environ.get("PGB_PEER_MULTICAST", "0") == "1" else 0
+                peers = []
+                for parity in (0, 1):
+                    ps = C.Peers()
+                    ps.n, ps.rank = self.world, self.rank
+                    for r in range(self.world):
+                        ps.zbuf0[r] = int(hz.buffer_ptrs[r])
+                        ps.zbuf1[r] = int(hz.buffer_ptrs[r]) + self.n_global * w
+                        ps.acc[r] = int(ha.buffer_ptrs[r]) + parity * 2 * C.MAX_PEERS * 8
+                    ps.mc_zbuf0 = mc if mc else None
+                    ps.mc_zbuf1 = (mc + self.n_global * w) if mc else None
+                    peers.append(ps)
+                out = {"z": zsym, "hz": hz, "acc": asym, "ha": ha, "peers": peers, "multicast": bool(mc)}
+            except Exception as exc:   # no symmetric memory on this system: the NCCL path is the product there
+                self._peer_error = repr(exc)
+                out = None
+        self._cache[key] = out
+        return out
+
     # per-dtype node vectors for the local rows ------------------------------------------------
     def vec(self, name: str, dtype: torch.dtype) -> torch.Tensor:
         from .graph import dtype_code, span_struct
@@ -300,7 +343,11 @@ class DistPageRank:
         err_hist = torch.zeros(self.max_iters + 2, dtype=torch.float64, device=dev)
 
         sq, cvec = g.vec("sq", dtype), g.vec("c", dtype)
-        zfull = [torch.empty(g.n_global, dtype=dtype, device=dev), torch.empty(g.n_global, dtype=dtype, device=dev)]
+        peer = g.peer_buffers(dtype)
+        if peer is not None:
+            zfull = [peer["z"][:g.n_global], peer["z"][g.n_global:]]
+        else:
+            zfull = [torch.empty(g.n_global, dtype=dtype, device=dev), torch.empty(g.n_global, dtype=dtype, device=dev)]
         q = torch.empty(n_loc, dtype=dtype, device=dev)
         C.check(lib.pgb_affine_init(n_loc, code, C.ptr(p), None, C.ptr(sq), C.ptr(cvec), 1 - self.alpha, None, None,
                                     off, C.ptr(zfull[0]), C.ptr(q), C.ptr(state_f64), st))
@@ -322,6 +369,18 @@ class DistPageRank:
             count = min(chunk, budget - done)
             for j in range(count):
                 k = done + 1 + j
+                if peer is not None:
+                    # exchange fused into the step: the update kernel writes z' and the convergence sums into
+                    # every rank; a symmetric-memory barrier (one small kernel) replaces all-gather + all-reduce
+                    C.check(lib.pgb_affine_step_peer(ctypes.byref(cs), code, float(self.alpha), None, None,
+                                                     C.ptr(cvec), C.ptr(q), C.ptr(zfull[0]), C.ptr(zfull[1]), off,
+                                                     C.ptr(state_f64), C.ptr(state_i32), C.ptr(err_hist),
+                                                     span_struct(ws), k, ctypes.byref(peer["peers"][k & 1]), st))
+                    peer["hz"].barrier(channel=0)
+                    C.check(lib.pgb_state_finalize_peer(C.ptr(state_f64), C.ptr(state_i32), C.ptr(err_hist),
+                                                        peer["acc"].data_ptr() + (k & 1) * 2 * C.MAX_PEERS * 8,
+                                                        g.world, st))
+                    continue
                 C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, float(self.alpha), None, None, C.ptr(cvec),
                                              C.ptr(q), C.ptr(zfull[0]), C.ptr(zfull[1]), off, C.ptr(state_f64),
                                              C.ptr(state_i32), C.ptr(err_hist), span_struct(ws), k, 1, 0, st))
@@ -342,6 +401,8 @@ class DistPageRank:
         self.errors = err_hist[1:steps + 1]
         if stop == C.MAX_ITERS and err_code != C.ERR_ITERS:
             raise Exception("Could not converge within " + str(self.max_iters) + " iterations")
+        if peer is not None:
+            peer["hz"].barrier(channel=1)   # nobody starts the next solve (overwriting buffer 0) before all have read
         result = torch.empty(n_loc, dtype=dtype, device=dev)
         zl = zfull[steps & 1][off:off + n_loc]
         C.check(lib.pgb_unscale(n_loc, code, C.ptr(zl.contiguous()), C.ptr(sq), None, norm, None, C.ptr(result), st))

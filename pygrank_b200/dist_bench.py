@@ -123,6 +123,13 @@ def run(args):
     peak, peak_src = B.hbm_peak()
     nnz_all = [None] * world
     dist.all_gather_object(nnz_all, g.nnz_local)
+    peer = g.peer_buffers(dtype)
+    if peer is None:
+        exchange = "NCCL all_gather_into_tensor of n/N rank-vector slices + 16-byte all_reduce per iteration"
+    else:
+        exchange = ("fused into the update kernel: z' and the convergence sums written into every rank's symmetric "
+                    "memory (%s) + one barrier kernel per iteration; no NCCL in the loop"
+                    % ("NVSwitch multicast, multimem.st" if peer["multicast"] else "one NVLink store per peer"))
     if rank == 0:
         line = {
             "metric": "PPR GTEPS", "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
@@ -130,7 +137,7 @@ def run(args):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": dict(B.workload_config(world, scale), n=g.n_nodes, nnz=g.nnz_global,
                            nnz_per_rank=[int(x) for x in nnz_all], conv_calls_per_solve=conv_calls / args.steps,
-                           exchange="NCCL all_gather_into_tensor of n/N rank-vector slices + 16-byte all_reduce per iteration",
+                           exchange=exchange,
                            graph_build_s=round(build_s, 2)),
             "e2e": {"value": e2e_value, "unit": "GTEPS", "h2d_bytes_per_step": 10 * 8 + 10 * 8,
                     "d2h_bytes_per_step": g.n_local * w * world + 64 * 2},

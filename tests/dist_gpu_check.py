@@ -24,6 +24,10 @@ def main():
     from pygrank_b200.dist import DistGraph, DistPageRank
     n = 1 << scale
     g = DistGraph.rmat(scale, 16, seed=1)
+    peer = g.peer_buffers(torch.float64)
+    if rank == 0:
+        print("peer exchange:", "off (" + getattr(g, "_peer_error", "disabled") + ")" if peer is None else
+              ("multicast" if peer["multicast"] else "unicast stores"))
     seeds = synthetic.seed_sets(n, 2, 10, seed=0)
     ok = True
     single = device_synthetic.rmat_graph_device(scale, 16, seed=1) if rank == 0 else None
