@@ -309,6 +309,11 @@ int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *
                          const void *q, void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64,
                          int32_t *state_i32, double *err_hist, pgb_span_ws ws, int step, const pgb_peers *peers,
                          void *stream);
+/* pgb_affine_init whose start vector z0 (this rank's rows) is written into buffer 0 of EVERY rank — replaces
+ * the all-gather of the start vector; the caller puts a cross-device barrier before the first step. */
+int pgb_affine_init_peer(int64_t n, int dtype, const void *p, const void *warm, const void *sq, const void *c,
+                         double coef, const void *coefvec, const int32_t *perm, int64_t out_offset, void *q,
+                         double *state_f64, const pgb_peers *peers, void *stream);
 /* acc_slots: this rank's own [n][2] slot array (filled by every rank's update kernel). */
 int pgb_state_finalize_peer(double *state_f64, int32_t *state_i32, double *err_hist, const double *acc_slots,
                             int32_t n, void *stream);

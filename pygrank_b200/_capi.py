@@ -103,6 +103,8 @@ _SIGNATURES = {
                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, POINTER(Peers),
                                      c_void_p]),
     "pgb_state_finalize_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "pgb_affine_init_peer": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
+                                     c_void_p, c_int64, c_void_p, c_void_p, POINTER(Peers), c_void_p]),
     "pgb_scale": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "pgb_unscale": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "pgb_reduce3": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -36,7 +36,6 @@ constexpr int HS_THREADS = 1024;
 constexpr int HS_WARPS = HS_THREADS / 32;
 constexpr int HS_SMEM_LIMIT = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100a
 constexpr int UPD_BLOCK = 256;
-constexpr int UPD_GROUP = 4;   // slices a warp of the update kernel handles together
 constexpr int UPD_AHEAD = 5;   // partial rows per slice requested before the first add
 
 static int g_tail_warps = 8;
@@ -233,6 +232,7 @@ struct GatherParams {
     const int32_t *stop;   // device state word: run-ahead launches after convergence are no-ops (or NULL)
     uint32_t *tail_queue;  // global counter of the tail stream (zero at launch; the update kernel resets it)
     int tail_warps;
+    int tail_batch;        // tail chunks taken per grab of the global queue
     int debug_skip;        // timing experiments only (PGB_HSELL_DEBUG_SKIP): 1 = skip hub chunks, 2 = skip tail chunks
 };
 
@@ -352,10 +352,14 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
     const int Hs = H / N;
     if (tid == 0) s_z[H] = (T)0;
 
-    auto run_tail = [&](int u) {
+    const int TB = G.tail_batch;
+    auto run_tail = [&](int u0) {   // a grab of the global queue: TB consecutive tail chunks
         if (G.debug_skip & 2) return;
-        const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.tail_chunks) + u);
-        tail_chunk<T>(h.tail_cols, u, d.x, d.y, h.piece_row, z, partials, lane);
+        const int u1 = (u0 + TB < tail_hi) ? u0 + TB : tail_hi;
+        for (int u = u0; u < u1; ++u) {
+            const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.tail_chunks) + u);
+            tail_chunk<T>(h.tail_cols, u, d.x, d.y, h.piece_row, z, partials, lane);
+        }
     };
 
     int cur = hub_lo;
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
             int kind = 0, u = 0;   // 0: nothing left in this segment, 1: hub chunk, 2: tail chunk
             if (lane == 0) {
                 if (tail_pref && *(volatile int *)&s_hub_next < seg_end) {
-                    u = (int)atomicAdd(G.tail_queue, 1u);
+                    u = (int)atomicAdd(G.tail_queue, (unsigned)TB);
                     if (u < tail_hi) kind = 2;
                 }
                 if (kind == 0) {
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
     // ---- drain the tail queue ---------------------------------------------------------------------
     while (true) {
         int u = 0;
-        if (lane == 0) u = (int)atomicAdd(G.tail_queue, 1u);
+        if (lane == 0) u = (int)atomicAdd(G.tail_queue, (unsigned)TB);
         u = __shfl_sync(FULL, u, 0);
         if (u >= tail_hi) break;
         run_tail(u);
@@ -457,8 +461,8 @@ __global__ void __launch_bounds__(256) hsell_reduce_kernel(const pgb_hsell h, T 
 // update, convergence reduction.  Slices that still have more than heavy_parts rows are added by a
 // whole CTA first, in a fixed order; the others by one warp, UPD_GROUP slices at a time with all
 // their loads in flight together.
-template <typename T, int MODE, bool SYMDEG>
-__global__ void __launch_bounds__(UPD_BLOCK, sizeof(T) == 8 ? 2 : 3) hsell_update_kernel(const StepParams P, const pgb_hsell h,
+template <typename T, int MODE, bool SYMDEG, int UPD_GROUP>
+__global__ void __launch_bounds__(UPD_BLOCK, (sizeof(T) == 8 ? 2 : 3) * (UPD_GROUP == 2 ? 2 : 1)) hsell_update_kernel(const StepParams P, const pgb_hsell h,
                                                                                           const T *__restrict__ partials) {
     __shared__ double s_red[32];
     __shared__ T s_acc[UPD_WARPS][32];
@@ -590,6 +594,13 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, cons
         debug_skip = e ? atoi(e) : 0;
     }
     G.debug_skip = debug_skip;
+    static int tail_batch = -1;
+    if (tail_batch < 0) {
+        const char *e = getenv("PGB_HSELL_TAIL_BATCH");
+        tail_batch = e ? atoi(e) : 1;
+        if (tail_batch < 1) tail_batch = 1;
+    }
+    G.tail_batch = tail_batch;
     hsell_gather_kernel<T><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
     PGB_LAUNCH_OK("hsell_gather_kernel");
     return 0;
@@ -606,23 +617,35 @@ static int launch_reduce(const pgb_hsell *h, void *partials, const int32_t *stop
     return 0;
 }
 
-template <typename T, int MODE, bool SYMDEG>
-static int launch_update(const StepParams &P, const pgb_hsell *h, const void *partials, cudaStream_t st) {
-    int64_t want = ceil_div(h->n_slices, UPD_WARPS * UPD_GROUP);
+template <typename T, int MODE, bool SYMDEG, int GROUP>
+static int launch_update_g(const StepParams &P, const pgb_hsell *h, const void *partials, cudaStream_t st) {
+    int64_t want = ceil_div(h->n_slices, UPD_WARPS * GROUP);
     if (want < h->n_heavy) want = h->n_heavy;
     static int ctas = 0;
     if (ctas == 0) {
         int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_kernel<T, MODE, SYMDEG>, UPD_BLOCK, 0) != cudaSuccess || v < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_kernel<T, MODE, SYMDEG, GROUP>, UPD_BLOCK, 0) != cudaSuccess || v < 1)
             v = 2;
         ctas = v;
     }
     const int64_t cap = (int64_t)sm_count() * ctas;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    hsell_update_kernel<T, MODE, SYMDEG><<<(int)want, UPD_BLOCK, 0, st>>>(P, *h, (const T *)partials);
+    hsell_update_kernel<T, MODE, SYMDEG, GROUP><<<(int)want, UPD_BLOCK, 0, st>>>(P, *h, (const T *)partials);
     PGB_LAUNCH_OK("hsell_update_kernel");
     return 0;
+}
+
+// slices a warp of the update kernel handles together: 4 (fewer, fatter warps) or 2 (PGB_HSELL_UPD_GROUP)
+template <typename T, int MODE, bool SYMDEG>
+static int launch_update(const StepParams &P, const pgb_hsell *h, const void *partials, cudaStream_t st) {
+    static int group = 0;
+    if (group == 0) {
+        const char *e = getenv("PGB_HSELL_UPD_GROUP");
+        group = (e && atoi(e) == 2) ? 2 : 4;
+    }
+    return group == 2 ? launch_update_g<T, MODE, SYMDEG, 2>(P, h, partials, st)
+                      : launch_update_g<T, MODE, SYMDEG, 4>(P, h, partials, st);
 }
 
 // One fused step on the hsell form: gather (kernel A) + update (kernel B).  Called from spmv_fused.cu.

@@ -50,11 +50,17 @@ __global__ void reduce3_kernel(int64_t n, const T *__restrict__ x, const T *__re
     }
 }
 
+struct PeerOut {
+    int n;
+    void *z[PGB_MAX_PEERS];
+};
+
 template <typename T>
 __global__ void affine_init_kernel(int64_t n, const T *__restrict__ p, const T *__restrict__ warm,
                                    const T *__restrict__ sq, const T *__restrict__ c, double coef,
                                    const T *__restrict__ coefvec, const int32_t *__restrict__ perm,
-                                   int64_t out_offset, T *__restrict__ z0, T *__restrict__ q, double *sf) {
+                                   int64_t out_offset, T *__restrict__ z0, T *__restrict__ q, double *sf,
+                                   const PeerOut peers) {
     __shared__ double scratch[32];
     const double norm = sf[PGB_SF_NORM];
     double tacc = 0.0, bacc = 0.0;
@@ -65,7 +71,11 @@ __global__ void affine_init_kernel(int64_t n, const T *__restrict__ p, const T *
         const T sqi = sq[i];
         const T zi = start / sqi;
         const T qi = (T)((coefvec ? (double)coefvec[i] : coef) * (double)pn) / sqi;
-        z0[out_offset + i] = zi;
+        if (peers.n == 0) {
+            z0[out_offset + i] = zi;
+        } else {   // row-partitioned multi-GPU: the start vector goes straight into every rank's buffer
+            for (int r = 0; r < peers.n; ++r) ((T *)peers.z[r])[out_offset + i] = zi;
+        }
         if (q) q[i] = qi;
         if (c) tacc += (double)zi * (double)c[i];
         bacc += (double)qi * (double)sqi;
@@ -76,6 +86,7 @@ __global__ void affine_init_kernel(int64_t n, const T *__restrict__ p, const T *
         atomicAdd(&sf[PGB_SF_TACC], tacc);
         atomicAdd(&sf[PGB_SF_BIAS], bacc);
     }
+    if (peers.n > 0) __threadfence_system();
 }
 
 __global__ void affine_init_finish_kernel(double *sf, int32_t *si) {
@@ -136,24 +147,46 @@ int pgb_reduce3(int64_t n, int dtype, const void *x, const void *y, double *sums
     return 0;
 }
 
-int pgb_affine_init(int64_t n, int dtype, const void *p, const void *warm, const void *sq, const void *c,
-                    double coef, const void *coefvec, const int32_t *perm, int64_t out_offset, void *z0, void *q,
-                    double *state_f64, void *stream) {
+static int affine_init_impl(int64_t n, int dtype, const void *p, const void *warm, const void *sq, const void *c,
+                            double coef, const void *coefvec, const int32_t *perm, int64_t out_offset, void *z0,
+                            void *q, double *state_f64, const pgb_peers *peers, void *stream) {
     if (n <= 0) return 0;
     if (!sq) return fail("pgb_affine_init: the sq vector is required");
+    PeerOut po;
+    memset(&po, 0, sizeof(po));
+    if (peers) {
+        if (peers->n < 1 || peers->n > PGB_MAX_PEERS) return fail("pgb_affine_init_peer: bad peer description");
+        po.n = peers->n;
+        for (int r = 0; r < peers->n; ++r) po.z[r] = peers->zbuf0[r];
+    }
     const int grid = stride_grid(n, 256) < 592 ? stride_grid(n, 256) : 592;
     if (dtype == PGB_F32)
         affine_init_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
             n, (const float *)p, (const float *)warm, (const float *)sq, (const float *)c, coef,
-            (const float *)coefvec, perm, out_offset, (float *)z0, (float *)q, state_f64);
+            (const float *)coefvec, perm, out_offset, (float *)z0, (float *)q, state_f64, po);
     else if (dtype == PGB_F64)
         affine_init_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
             n, (const double *)p, (const double *)warm, (const double *)sq, (const double *)c, coef,
-            (const double *)coefvec, perm, out_offset, (double *)z0, (double *)q, state_f64);
+            (const double *)coefvec, perm, out_offset, (double *)z0, (double *)q, state_f64, po);
     else
         return fail("pgb_affine_init: unknown dtype %d", dtype);
     PGB_LAUNCH_OK("affine_init_kernel");
     return 0;
+}
+
+int pgb_affine_init(int64_t n, int dtype, const void *p, const void *warm, const void *sq, const void *c,
+                    double coef, const void *coefvec, const int32_t *perm, int64_t out_offset, void *z0, void *q,
+                    double *state_f64, void *stream) {
+    return affine_init_impl(n, dtype, p, warm, sq, c, coef, coefvec, perm, out_offset, z0, q, state_f64, nullptr,
+                            stream);
+}
+
+int pgb_affine_init_peer(int64_t n, int dtype, const void *p, const void *warm, const void *sq, const void *c,
+                         double coef, const void *coefvec, const int32_t *perm, int64_t out_offset, void *q,
+                         double *state_f64, const pgb_peers *peers, void *stream) {
+    if (!peers) return fail("pgb_affine_init_peer: no peers");
+    return affine_init_impl(n, dtype, p, warm, sq, c, coef, coefvec, perm, out_offset, nullptr, q, state_f64, peers,
+                            stream);
 }
 
 int pgb_affine_init_finish(double *state_f64, int32_t *state_i32, void *stream) {

@@ -349,9 +349,15 @@ class DistPageRank:
         else:
             zfull = [torch.empty(g.n_global, dtype=dtype, device=dev), torch.empty(g.n_global, dtype=dtype, device=dev)]
         q = torch.empty(n_loc, dtype=dtype, device=dev)
-        C.check(lib.pgb_affine_init(n_loc, code, C.ptr(p), None, C.ptr(sq), C.ptr(cvec), 1 - self.alpha, None, None,
-                                    off, C.ptr(zfull[0]), C.ptr(q), C.ptr(state_f64), st))
-        dist.all_gather_into_tensor(zfull[0], zfull[0][off:off + n_loc], group=g.group)
+        if peer is not None:
+            # start vector straight into every rank's buffer 0 (no all-gather); the barrier orders it before step 1
+            C.check(lib.pgb_affine_init_peer(n_loc, code, C.ptr(p), None, C.ptr(sq), C.ptr(cvec), 1 - self.alpha, None,
+                                             None, off, C.ptr(q), C.ptr(state_f64), ctypes.byref(peer["peers"][0]), st))
+            peer["hz"].barrier(channel=2)
+        else:
+            C.check(lib.pgb_affine_init(n_loc, code, C.ptr(p), None, C.ptr(sq), C.ptr(cvec), 1 - self.alpha, None, None,
+                                        off, C.ptr(zfull[0]), C.ptr(q), C.ptr(state_f64), st))
+            dist.all_gather_into_tensor(zfull[0], zfull[0][off:off + n_loc], group=g.group)
         dist.all_reduce(state_f64[C.SF_BIAS:C.SF_BIAS + 1], group=g.group)
         dist.all_reduce(state_f64[C.SF_TACC:C.SF_TACC + 1], group=g.group)
         C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))

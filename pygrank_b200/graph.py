@@ -82,7 +82,7 @@ def hsell_config() -> dict:
     return {
         "enabled": _env_int("PGB_HSELL", 1) != 0,
         "block_cols": _env_int("PGB_HSELL_BLOCK_COLS", 0),
-        "max_blocks": _env_int("PGB_HSELL_BLOCKS", 64),
+        "max_blocks": _env_int("PGB_HSELL_BLOCKS", 0),
         "min_entries": _env_int("PGB_HSELL_MIN_ENTRIES", 32),
         "heavy_parts": min(max(_env_int("PGB_HSELL_HEAVY_PARTS", 32), 1), 32),
         "bank_order": _env_int("PGB_HSELL_BANK_ORDER", 1) != 0,
@@ -100,7 +100,12 @@ def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional
     if H < 4 * n_segments:
         raise Exception("hsell: block_cols too small")
     Hs = H // n_segments
-    K = max(min(cfg["max_blocks"], -(-seg_len // Hs)), 0)
+    max_blocks = cfg["max_blocks"]
+    if max_blocks <= 0:
+        # auto: hub blocks cover ~1/16 of the columns, between 64 and 256 blocks (measured: 64-96 best at
+        # 16.8 M columns, 256 best at 134 M, where the gather vector no longer fits L2)
+        max_blocks = max(64, min(256, (n_segments * seg_len) // (16 * H)))
+    K = max(min(max_blocks, -(-seg_len // Hs)), 0)
     if n_segments > 1 and K * Hs > seg_len:
         K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail
     return H, K
