@@ -301,6 +301,20 @@ def kernel_leg(args, g, pers0, dtype, _unused):
     return out
 
 
+def measured_traffic(scale, dtype, form):
+    """DRAM bytes per fused step from the committed ncu captures (profiles/traffic_r1.json: gather + update
+    kernels; the reduce kernel moves < 1 % of that), valid for the workload they were taken on."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r1.json")
+    if scale != 24 or dtype != "f32" or form is None or not os.path.exists(path):
+        return None
+    try:
+        per = json.load(open(path))["bytes_per_launch"]
+        parts = [v for k, v in per.items() if "hsell_gather_kernel" in k or "hsell_update_kernel" in k]
+        return sum(parts) if len(parts) == 2 else None
+    except (ValueError, KeyError):
+        return None
+
+
 def finish_line(args, v):
     n, nnz, w, scale = v["n"], v["nnz"], v["w"], v["scale"]
     value, dev_ms, conv_calls, build_s = v["value"], v["dev_ms"], v["conv_calls"], v["build_s"]
@@ -317,7 +331,7 @@ def finish_line(args, v):
                 "d2h_bytes_per_step": n * w + 64 * 2},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None,
+                     "traffic": measured_traffic(scale, args.dtype, form),
                      "kernel": ("one fused step = hsell_gather_kernel<%s> (dominant, ~2/3 of the step) + hsell_reduce_kernel"
                                 " + hsell_update_kernel<%s,AFFINE,SYMDEG=%s>"
                                 if form is not None else "item_stream_kernel<%s,unweighted,AFFINE,SYMDEG=%s>")

@@ -111,6 +111,46 @@ def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional
     return H, K
 
 
+def stream_layout(rounds: torch.Tensor, base: int, chunk: int = C.HSELL_CHUNK):
+    """Layout of one hsell stream (plain torch, device agnostic: covered by the CPU tests).
+
+    ``rounds`` int64 [B, S]: rounds of every unit in stream order (row b = one hub block, or the single
+    tail row); every row is padded to whole chunks.  A PIECE ends at the last round of a unit and at the
+    end of every chunk; pieces are numbered in stream order starting at ``base``.  Returns
+    (first round of every unit [B*S], number of the first piece of every unit [B*S], pieces per unit [B*S],
+    chunk descriptors int32 [n_chunks, 2] = (first piece of the chunk, mask of the rounds at which a unit
+    ends), n_chunks, number of pieces, first chunk of every row [B+1])."""
+    i64 = torch.int64
+    dev = rounds.device
+    CH = chunk
+    per_row = rounds.sum(1)
+    row_pad = (per_row + (CH - 1)) // CH * CH
+    row_base = torch.cumsum(row_pad, 0) - row_pad
+    g0 = (row_base[:, None] + torch.cumsum(rounds, 1) - rounds).reshape(-1)
+    r = rounds.reshape(-1)
+    g1 = g0 + r
+    ex = r > 0
+    n_chunks = int(row_pad.sum()) // CH
+    aligned = ex & (g1 % CH == 0)                       # unit end coincides with a chunk end: one piece end
+    unit_rank = torch.cumsum(ex.to(i64), 0) - ex.to(i64)
+    b_before = torch.cumsum(aligned.to(i64), 0) - aligned.to(i64)
+    p0 = base + unit_rank + g0 // CH - b_before         # piece ends before the unit's first round
+    pieces = torch.where(ex, (g1 - 1) // CH - g0 // CH + 1, torch.zeros_like(g0))
+    g1e = g1[ex]
+    starts = torch.arange(n_chunks, device=dev, dtype=i64) * CH
+    u = torch.searchsorted(g1e, starts, right=True)     # units that end before the chunk starts
+    bcum = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(aligned[ex].to(i64), 0)])
+    p_first = base + u + torch.arange(n_chunks, device=dev, dtype=i64) - bcum[u]
+    endmask = torch.zeros(max(n_chunks, 1), dtype=i64, device=dev)
+    if g1e.numel():
+        endmask.index_add_(0, (g1e - 1) // CH, torch.ones_like(g1e) << ((g1e - 1) % CH))
+    n_parts = int(ex.sum()) + n_chunks - int(aligned.sum())
+    desc = torch.stack([p_first, endmask[:n_chunks]], 1)
+    desc = torch.where(desc >= 2 ** 31, desc - 2 ** 32, desc).to(torch.int32).contiguous()
+    chunk_begin = torch.cat([row_base, row_pad.sum().reshape(1)]) // CH
+    return g0.contiguous(), p0.contiguous(), pieces, desc, n_chunks, n_parts, chunk_begin
+
+
 class HsellForm:
     """Device arrays of one pgb_hsell (kept alive here; the C struct holds raw pointers)."""
 
@@ -131,37 +171,6 @@ class HsellForm:
         tail_rounds = torch.zeros(max(S, 1), dtype=torch.int32, device=dev)
         C.check(lib.pgb_hsell_count(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, cfg["min_entries"],
                                     C.ptr(hub_rounds), C.ptr(tail_rounds), st))
-
-        def stream_layout(rounds, base):
-            """rounds: int64 [B, S] (units in stream order, every row padded to whole chunks).  Returns the
-            first round and first partial row of every unit, the chunk descriptors and the counts."""
-            Bn = rounds.shape[0]
-            per_row = rounds.sum(1)
-            row_pad = (per_row + (CH - 1)) // CH * CH
-            row_base = torch.cumsum(row_pad, 0) - row_pad
-            g0 = (row_base[:, None] + torch.cumsum(rounds, 1) - rounds).reshape(-1)
-            r = rounds.reshape(-1)
-            g1 = g0 + r
-            ex = r > 0
-            n_chunks = int(row_pad.sum()) // CH
-            aligned = ex & (g1 % CH == 0)
-            unit_rank = torch.cumsum(ex.to(i64), 0) - ex.to(i64)
-            b_before = torch.cumsum(aligned.to(i64), 0) - aligned.to(i64)
-            p0 = base + unit_rank + g0 // CH - b_before
-            pieces = torch.where(ex, (g1 - 1) // CH - g0 // CH + 1, torch.zeros_like(g0))
-            g1e = g1[ex]
-            starts = torch.arange(n_chunks, device=dev, dtype=i64) * CH
-            u = torch.searchsorted(g1e, starts, right=True)
-            bcum = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.cumsum(aligned[ex].to(i64), 0)])
-            p_first = base + u + torch.arange(n_chunks, device=dev, dtype=i64) - bcum[u]
-            endmask = torch.zeros(max(n_chunks, 1), dtype=i64, device=dev)
-            if g1e.numel():
-                endmask.index_add_(0, (g1e - 1) // CH, torch.ones_like(g1e) << ((g1e - 1) % CH))
-            n_parts = int(ex.sum()) + n_chunks - int(aligned.sum())
-            desc = torch.stack([p_first, endmask[:n_chunks]], 1)
-            desc = torch.where(desc >= 2 ** 31, desc - 2 ** 32, desc).to(torch.int32).contiguous()
-            chunk_begin = torch.cat([row_base, row_pad.sum().reshape(1)]) // CH
-            return g0.contiguous(), p0.contiguous(), pieces, desc, n_chunks, n_parts, chunk_begin
 
         hr = hub_rounds[:K * S].to(i64).view(K, S) if K > 0 else torch.zeros((0, S), dtype=i64, device=dev)
         tr = tail_rounds[:S].to(i64).view(1, S)

@@ -81,6 +81,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__cycles_elapsed.max"]
 
 
+TRAFFIC = {}
+
+
 def kernel_summary(rep, title, fname):
     path = os.path.join(ROOT, "gpurun_out", rep)
     if not os.path.exists(path):
@@ -96,6 +99,15 @@ def kernel_summary(rep, title, fname):
                 if w in hdr:
                     i = hdr.index(w)
                     f.write(f"| {w} | {r[i]} | {units[i]} |\n")
+            try:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                tot = 0.0
+                for w in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = hdr.index(w)
+                    tot += float(r[i].replace(",", "")) * scale[units[i]]
+                TRAFFIC[r[hdr.index("Kernel Name")].split("(")[0]] = tot
+            except (ValueError, KeyError):
+                pass
         src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"],
                              capture_output=True, text=True).stdout
         srows = list(csv.reader(io.StringIO(src)))
@@ -128,3 +140,10 @@ kernel_summary(f"prof_{tag}_gather.ncu-rep",
                f"Dominant kernel ({tag}): hsell_gather_kernel<float> — one PPR step on RMAT scale 24, fp32", f"kernel_{tag}_gather.md")
 kernel_summary(f"prof_{tag}_update.ncu-rep",
                f"Second kernel of the step ({tag}): hsell_update_kernel<float, AFFINE, SYMDEG>, same step", f"kernel_{tag}_update.md")
+
+if TRAFFIC:
+    import json
+    with open(os.path.join(out_dir, f"traffic_{tag}.json"), "w") as f:
+        json.dump({"source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                             "bench.py --kernel-only (RMAT scale 24, fp32)", "bytes_per_launch": TRAFFIC}, f, indent=1)
+    print("wrote traffic")
