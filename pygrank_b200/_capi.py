@@ -50,7 +50,7 @@ MAX_PEERS = 16
 class Peers(Structure):
     """pgb_peers (include/pgb200.h): peer-mapped buffers of the fused multi-GPU exchange."""
     _fields_ = [("n", c_int32), ("rank", c_int32), ("zbuf0", c_void_p * MAX_PEERS), ("zbuf1", c_void_p * MAX_PEERS),
-                ("mc_zbuf0", c_void_p), ("mc_zbuf1", c_void_p), ("acc", c_void_p * MAX_PEERS)]
+                ("mc_zbuf0", c_void_p), ("mc_zbuf1", c_void_p), ("acc", c_void_p * MAX_PEERS), ("row_mask", c_void_p)]
 
 
 class SpanWs(Structure):

@@ -959,6 +959,7 @@ int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *
         if (!P.peer_zout[r] || !P.peer_acc[r]) return fail("pgb_affine_step_peer: peer %d has no buffer", r);
     }
     P.mc_zout = (step & 1) ? peers->mc_zbuf1 : peers->mc_zbuf0;
+    P.peer_mask = peers->row_mask;
     return dispatch<MODE_AFFINE>(P, dtype, symdeg, as_stream(stream));
 }
 

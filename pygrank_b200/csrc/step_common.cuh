@@ -37,6 +37,7 @@ struct StepParams {
     void *peer_zout[PGB_MAX_PEERS];
     void *mc_zout;
     double *peer_acc[PGB_MAX_PEERS];
+    const uint32_t *peer_mask;   // [local rows] which ranks read the row's value (NULL: all)
 };
 
 // store to a multicast (multimem) address: NVSwitch replicates it into every peer's buffer
@@ -165,7 +166,9 @@ struct RowUpdate {
         } else if (P.mc_zout) {
             multimem_store((T *)P.mc_zout + own, v);
         } else {
-            for (int r = 0; r < P.n_peers; ++r) ((T *)P.peer_zout[r])[own] = v;
+            const uint32_t m = P.peer_mask ? P.peer_mask[own - P.out_offset] : 0xffffffffu;
+            for (int r = 0; r < P.n_peers; ++r)
+                if ((m >> r) & 1u) ((T *)P.peer_zout[r])[own] = v;
         }
     }
 

@@ -53,6 +53,7 @@ __global__ void reduce3_kernel(int64_t n, const T *__restrict__ x, const T *__re
 struct PeerOut {
     int n;
     void *z[PGB_MAX_PEERS];
+    const uint32_t *mask;
 };
 
 template <typename T>
@@ -74,7 +75,9 @@ __global__ void affine_init_kernel(int64_t n, const T *__restrict__ p, const T *
         if (peers.n == 0) {
             z0[out_offset + i] = zi;
         } else {   // row-partitioned multi-GPU: the start vector goes straight into every rank's buffer
-            for (int r = 0; r < peers.n; ++r) ((T *)peers.z[r])[out_offset + i] = zi;
+            const uint32_t m = peers.mask ? peers.mask[i] : 0xffffffffu;
+            for (int r = 0; r < peers.n; ++r)
+                if ((m >> r) & 1u) ((T *)peers.z[r])[out_offset + i] = zi;
         }
         if (q) q[i] = qi;
         if (c) tacc += (double)zi * (double)c[i];
@@ -158,6 +161,7 @@ static int affine_init_impl(int64_t n, int dtype, const void *p, const void *war
         if (peers->n < 1 || peers->n > PGB_MAX_PEERS) return fail("pgb_affine_init_peer: bad peer description");
         po.n = peers->n;
         for (int r = 0; r < peers->n; ++r) po.z[r] = peers->zbuf0[r];
+        po.mask = peers->row_mask;
     }
     const int grid = stride_grid(n, 256) < 592 ? stride_grid(n, 256) : 592;
     if (dtype == PGB_F32)

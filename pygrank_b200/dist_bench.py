@@ -129,7 +129,9 @@ def run(args):
     else:
         exchange = ("fused into the update kernel: z' and the convergence sums written into every rank's symmetric "
                     "memory (%s) + one barrier kernel per iteration; no NCCL in the loop"
-                    % ("NVSwitch multicast, multimem.st" if peer["multicast"] else "one NVLink store per peer"))
+                    % ("NVSwitch multicast, multimem.st" if peer["multicast"] else
+                       "one NVLink store per peer that reads the row" +
+                       ("" if peer.get("sent_fraction") is None else ": %.0f%% of (row, rank) pairs" % (100 * peer["sent_fraction"]))))
     if rank == 0:
         line = {
             "metric": "PPR GTEPS", "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
