@@ -52,7 +52,8 @@ enum {
     PGB_ERR_MABS = 0, /* sum|prev-cur| / n   (Mabs, supervised.py:101-106; default) */
     PGB_ERR_L1 = 1,   /* sum|prev-cur|       (L1,   supervised.py:125-130)          */
     PGB_ERR_MSQ = 2,  /* sum (prev-cur)^2/n  (MSQ,  supervised.py:117-122)          */
-    PGB_ERR_ITERS = 3 /* error_type == "iters": never converges early (convergence.py:97-98) */
+    PGB_ERR_ITERS = 3, /* error_type == "iters": never converges early (convergence.py:97-98) */
+    PGB_ERR_MAX = 4    /* max|prev-cur|       (MaxDifference, supervised.py:93-98)           */
 };
 
 /* stop reasons written to pgb_state_i32[PGB_SI_STOP] */

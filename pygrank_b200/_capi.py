@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 PGB_F32, PGB_F64 = 0, 1
 BUILD_SYMMETRIZE, BUILD_DROP_SELF_LOOPS, BUILD_BINARY = 1, 2, 4
 SCALE_ONE, SCALE_RECIP, SCALE_RSQRT = 0, 1, 2
-ERR_MABS, ERR_L1, ERR_MSQ, ERR_ITERS = 0, 1, 2, 3
+ERR_MABS, ERR_L1, ERR_MSQ, ERR_ITERS, ERR_MAX = 0, 1, 2, 3, 4
 RUNNING, CONVERGED, MAX_ITERS = 0, 1, 2
 # state_f64 / state_i32 slots
 SF_ALPHA, SF_BIAS, SF_INVS, SF_TACC, SF_EACC, SF_TOL, SF_MEAN, SF_LASTERR, SF_NORM, SF_PSUM = range(10)

@@ -61,6 +61,23 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
     return v;
 }
 
+// block-wide maximum of one non-negative double per thread; result valid in thread 0
+__device__ __forceinline__ double block_max(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    const int nwarps = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nwarps) ? scratch[threadIdx.x] : 0.0;
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    return v;
+}
+
 // streaming (evict-first) loads for data touched once per iteration: CSR indices / weights
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }

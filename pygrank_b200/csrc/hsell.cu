@@ -103,6 +103,12 @@ __device__ __forceinline__ int32_t hsell_real_col(int32_t v, int H, int K, int N
     return (int32_t)(rnk * seg_len + (int64_t)K * Hs + off);
 }
 
+constexpr int FILL_GROUP = 8;   // hub blocks per work item of the fill kernel
+
+// One warp per (slice, part): part j < NP-1 writes the hub units of blocks [j*FILL_GROUP, (j+1)*FILL_GROUP),
+// the last part the slice's tail (entries of the blocks without a unit, then the columns past the hub
+// blocks).  Splitting the slices matters for the hub rows: the top slice alone holds ~1 % of all entries
+// and used to be the critical path of the whole build.
 __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__restrict__ indptr,
                                   const int32_t *__restrict__ indices, int H, int K, int N, int64_t seg_len,
                                   const int32_t *__restrict__ hub_rounds, const int32_t *__restrict__ tail_rounds,
@@ -115,7 +121,10 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t s = warp; s < n_slices; s += nwarps) {
+    const int NP = (K + FILL_GROUP - 1) / FILL_GROUP + 1;
+    for (int64_t item = warp; item < n_slices * NP; item += nwarps) {
+        const int64_t s = item / NP;
+        const int part = (int)(item - s * NP);
         const int64_t row = s * 32 + lane;
         int b = 0, e = 0;
         if (row < n) {
@@ -123,16 +132,23 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
             e = indptr[row + 1];
         }
         const int64_t first_part = slice_ptr[s];
-        const int TR = tail_rounds[s];
-        const int64_t tg0 = tail_round_base[s];
-        const int64_t tw = tg0 * 32;
-        int pos = b, t = 0;
-        int64_t ord = 0;
-        for (int blk = 0; blk < K; ++blk) {
-            const int nxt = lower_bound_i32(indices, pos, e, (blk + 1) * H);
-            const int len = nxt - pos;
+        auto pieces_of = [&](int blk) -> int {
             const int R = hub_rounds[(int64_t)blk * n_slices + s];
-            if (R > 0) {
+            if (R <= 0) return 0;
+            const int64_t g0 = hub_round_base[(int64_t)blk * n_slices + s];
+            return (int)((g0 + R - 1) / CH - g0 / CH) + 1;
+        };
+        if (part < NP - 1) {
+            const int blk_lo = part * FILL_GROUP;
+            const int blk_hi = (blk_lo + FILL_GROUP < K) ? blk_lo + FILL_GROUP : K;
+            int64_t ord = 0;
+            for (int blk = 0; blk < blk_lo; ++blk) ord += pieces_of(blk);
+            int pos = lower_bound_i32(indices, b, e, blk_lo * H);
+            for (int blk = blk_lo; blk < blk_hi; ++blk) {
+                const int nxt = lower_bound_i32(indices, pos, e, (blk + 1) * H);
+                const int len = nxt - pos;
+                const int R = hub_rounds[(int64_t)blk * n_slices + s];
+                if (R > 0) {
                 const int64_t g0 = hub_round_base[(int64_t)blk * n_slices + s];
                 const int64_t wb = g0 * 32;
                 const int base = blk * H;
@@ -206,9 +222,24 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                 const int64_t p0 = hub_part_base[(int64_t)blk * n_slices + s];
                 for (int p = lane; p < pieces; p += 32) piece_row[p0 + p] = (int32_t)(first_part + ord + p);
                 ord += pieces;
-            } else {
-                for (int i = 0; i < len; ++i, ++t)
-                    tail_cols[tw + (int64_t)t * 32 + lane] = hsell_real_col(indices[pos + i], H, K, N, seg_len);
+                }
+                pos = nxt;
+            }
+            continue;
+        }
+        // ---- the tail of the slice --------------------------------------------------------------------
+        const int TR = tail_rounds[s];
+        const int64_t tg0 = tail_round_base[s];
+        const int64_t tw = tg0 * 32;
+        int pos = b, t = 0;
+        int64_t ord = 0;
+        for (int blk = 0; blk < K; ++blk) {
+            const int nxt = lower_bound_i32(indices, pos, e, (blk + 1) * H);
+            const int np = pieces_of(blk);
+            ord += np;
+            if (np == 0) {
+                for (int i = pos; i < nxt; ++i, ++t)
+                    tail_cols[tw + (int64_t)t * 32 + lane] = hsell_real_col(indices[i], H, K, N, seg_len);
             }
             pos = nxt;
         }
@@ -716,7 +747,7 @@ int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int
     if (scratch && block_cols >= 0xffff) return fail("pgb_hsell_fill: bank-aware ordering needs block_cols < 65535");
     if (n_segments < 1 || block_cols % n_segments) return fail("pgb_hsell_fill: block_cols must be a multiple of n_segments");
     const int64_t n_slices = ceil_div(n, 32);
-    const int grid = stride_grid(n_slices * 32, 256);
+    const int grid = stride_grid(n_slices * 32 * ((n_blocks + FILL_GROUP - 1) / FILL_GROUP + 1), 256);
     hsell_fill_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n_slices, indptr, indices, block_cols, n_blocks, n_segments,
                                                            seg_len, hub_rounds, tail_rounds, hub_round_base, hub_part_base,
                                                            tail_round_base, tail_part_base, slice_ptr, hub_words,

@@ -173,23 +173,7 @@ __global__ void __launch_bounds__(BLOCK, 4) tile_kernel(const StepParams P) {
         __syncthreads();  // shared memory is reused by the next tile
     }
 
-    if (MODE != MODE_CONV) {
-        const double err = block_sum(update.err, s_red);
-        const double tsum = block_sum(update.tsum, s_red);
-        if (tid == 0) {
-            atomicAdd(&P.sf[PGB_SF_EACC], err);
-            atomicAdd(&P.sf[PGB_SF_TACC], tsum);
-            __threadfence();
-            const int ticket = atomicAdd(&P.si[PGB_SI_TICKET], 1);
-            if (ticket == (int)gridDim.x - 1) {
-                __threadfence();
-                if (P.finalize)
-                    finalize_state(P.sf, P.si, P.err_hist);
-                else
-                    P.si[PGB_SI_TICKET] = 0;
-            }
-        }
-    }
+    if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -381,23 +365,7 @@ __global__ void __launch_bounds__(BLOCK, 4) warp_tile_kernel(const StepParams P)
         }
     }
 
-    if (MODE != MODE_CONV) {
-        const double err = block_sum(update.err, s_red);
-        const double tsum = block_sum(update.tsum, s_red);
-        if (threadIdx.x == 0) {
-            atomicAdd(&P.sf[PGB_SF_EACC], err);
-            atomicAdd(&P.sf[PGB_SF_TACC], tsum);
-            __threadfence();
-            const int ticket = atomicAdd(&P.si[PGB_SI_TICKET], 1);
-            if (ticket == (int)gridDim.x - 1) {
-                __threadfence();
-                if (P.finalize)
-                    finalize_state(P.sf, P.si, P.err_hist);
-                else
-                    P.si[PGB_SI_TICKET] = 0;
-            }
-        }
-    }
+    if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -624,23 +592,7 @@ __global__ void __launch_bounds__(BLOCK, PGB_V3_MINB) item_stream_kernel(const S
         }
     }
 
-    if (MODE != MODE_CONV) {
-        const double err = block_sum(update.err, s_red);
-        const double tsum = block_sum(update.tsum, s_red);
-        if (threadIdx.x == 0) {
-            atomicAdd(&P.sf[PGB_SF_EACC], err);
-            atomicAdd(&P.sf[PGB_SF_TACC], tsum);
-            __threadfence();
-            const int ticket = atomicAdd(&P.si[PGB_SI_TICKET], 1);
-            if (ticket == (int)gridDim.x - 1) {
-                __threadfence();
-                if (P.finalize)
-                    finalize_state(P.sf, P.si, P.err_hist);
-                else
-                    P.si[PGB_SI_TICKET] = 0;
-            }
-        }
-    }
+    if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
 }
 
 // Builds the item-space stream from CSR: warp per row.
@@ -966,9 +918,11 @@ int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *
 __global__ void state_finalize_peer_kernel(double *sf, int32_t *si, double *err_hist, const double *slots, int n) {
     if (si[PGB_SI_STOP] != PGB_RUNNING) return;
     double t = 0.0, e = 0.0;
+    const bool is_max = si[PGB_SI_ERR_MODE] == PGB_ERR_MAX;
     for (int r = 0; r < n; ++r) {   // rank order: the same sum on every rank
         t += ((const volatile double *)slots)[2 * r];
-        e += ((const volatile double *)slots)[2 * r + 1];
+        const double er = ((const volatile double *)slots)[2 * r + 1];
+        e = is_max ? fmax(e, er) : e + er;
     }
     sf[PGB_SF_TACC] = t;
     sf[PGB_SF_EACC] = e;

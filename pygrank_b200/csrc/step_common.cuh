@@ -99,8 +99,18 @@ struct RowUpdate {
     T berr, btsum;      // fp32 batch sums (see apply)
     bool batch_sums;
 
+    __device__ __forceinline__ void accumulate_error(double d) {
+        if (err_mode == PGB_ERR_MAX)
+            err = (err > d) ? err : d;
+        else
+            err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+    }
+
     __device__ __forceinline__ void flush_batch() {
-        err += (double)berr;
+        if (err_mode == PGB_ERR_MAX)
+            err = (err > (double)berr) ? err : (double)berr;
+        else
+            err += (double)berr;
         tsum += (double)btsum;
         berr = btsum = (T)0;
     }
@@ -187,11 +197,14 @@ struct RowUpdate {
                 // fp32 mode inside the hsell update pass: a few rows are summed in fp32 and flushed to the
                 // fp64 accumulators once per group (flush_batch) — one DADD pair per group instead of per row
                 const T d = L.sqi * fabsf((float)(znew - L.zi));
-                berr += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+                if (err_mode == PGB_ERR_MAX)
+                    berr = (berr > d) ? berr : d;
+                else
+                    berr += (err_mode == PGB_ERR_MSQ) ? d * d : d;
                 btsum += znew * L.b;
             } else {
                 double d = (double)L.sqi * fabs((double)znew - (double)L.zi);
-                err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+                accumulate_error(d);
                 tsum += (double)znew * (double)L.b;
             }
         } else {  // MODE_POLY
@@ -202,7 +215,7 @@ struct RowUpdate {
                 ((T *)P.ranks)[row] = cur;
                 // fp64: the literal |prev - cur| the reference's Mabs sees; fp32: the exact increment
                 double d = (sizeof(T) == 8) ? fabs((double)prev - (double)cur) : fabs((double)coef * (double)pw);
-                err += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+                accumulate_error(d);
             }
             store_z(own, L.wi * acc);
         }
@@ -218,10 +231,14 @@ struct RowUpdate {
 // the last CTA plays ConvergenceManager (or just resets the ticket in deferred multi-GPU mode).
 template <typename U>
 __device__ __forceinline__ void step_epilogue(const StepParams &P, U &update, double *s_red) {
-    const double err = block_sum(update.err, s_red);
+    const bool is_max = update.err_mode == PGB_ERR_MAX;
+    const double err = is_max ? block_max(update.err, s_red) : block_sum(update.err, s_red);
     const double tsum = block_sum(update.tsum, s_red);
     if (threadIdx.x == 0) {
-        atomicAdd(&P.sf[PGB_SF_EACC], err);
+        if (is_max)   // non-negative doubles order like their bit patterns
+            atomicMax((unsigned long long *)&P.sf[PGB_SF_EACC], (unsigned long long)__double_as_longlong(err));
+        else
+            atomicAdd(&P.sf[PGB_SF_EACC], err);
         atomicAdd(&P.sf[PGB_SF_TACC], tsum);
         __threadfence();
         const int ticket = atomicAdd(&P.si[PGB_SI_TICKET], 1);

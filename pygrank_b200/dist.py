@@ -369,11 +369,13 @@ class DistPageRank:
             return p
 
         err_code = _error_code(self.error_type)
+        if err_code == C.ERR_MAX and g.peer_buffers(dtype) is None:
+            raise Exception("MaxDifference on the row-partitioned path needs the symmetric-memory exchange")
         sf = [0.0] * C.STATE_LEN
         si = [0] * C.STATE_LEN
         sf[C.SF_ALPHA], sf[C.SF_INVS] = float(self.alpha), 1.0
         sf[C.SF_TOL] = 0.0 if self.tol is None else max(float(self.tol), float(np.finfo(float).eps))
-        sf[C.SF_MEAN] = 1.0 if err_code == C.ERR_L1 else float(g.n_nodes)   # Mabs divides by the node count
+        sf[C.SF_MEAN] = 1.0 if err_code in (C.ERR_L1, C.ERR_MAX) else float(g.n_nodes)   # Mabs divides by the node count
         sf[C.SF_NORM] = norm
         si[C.SI_MAX_ITERS], si[C.SI_END_MODULO] = self.max_iters, max(self.end_modulo, 1)
         si[C.SI_ERR_MODE], si[C.SI_QUOTIENT] = err_code, int(bool(self.use_quotient))
@@ -397,8 +399,8 @@ class DistPageRank:
             C.check(lib.pgb_affine_init(n_loc, code, C.ptr(p), None, C.ptr(sq), C.ptr(cvec), 1 - self.alpha, None, None,
                                         off, C.ptr(zfull[0]), C.ptr(q), C.ptr(state_f64), st))
             dist.all_gather_into_tensor(zfull[0], zfull[0][off:off + n_loc], group=g.group)
-        dist.all_reduce(state_f64[C.SF_BIAS:C.SF_BIAS + 1], group=g.group)
-        dist.all_reduce(state_f64[C.SF_TACC:C.SF_TACC + 1], group=g.group)
+        # BIAS (slot 1) and TACC (slot 3) in one call; INVS (slot 2) between them is rewritten by init_finish
+        dist.all_reduce(state_f64[C.SF_BIAS:C.SF_TACC + 1], group=g.group)
         C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
         C.count_launches(2)
         form = g.hsell(dtype)
@@ -409,7 +411,9 @@ class DistPageRank:
 
         budget, done = self.max_iters - 1, 0
         stop, steps, iteration = C.RUNNING, 0, 1
-        chunk = max(self.chunk, 1)
+        # run-ahead chunk: a previous solve on this graph is the best guess of how many steps this one needs,
+        # so repeated solves read the device state back once
+        chunk = max(self.chunk, min(getattr(self, "_steps_hint", 0) + 1, 64), 1)
         while done < budget:
             count = min(chunk, budget - done)
             for j in range(count):
@@ -443,6 +447,7 @@ class DistPageRank:
         if stop == C.RUNNING:
             iteration, stop = 1, C.MAX_ITERS
         self.iteration = iteration
+        self._steps_hint = steps
         self.errors = err_hist[1:steps + 1]
         if stop == C.MAX_ITERS and err_code != C.ERR_ITERS:
             raise Exception("Could not converge within " + str(self.max_iters) + " iterations")

@@ -28,14 +28,16 @@ import torch
 from . import _capi as C
 from .graph import DeviceGraph, as_device_graph, dtype_code, preprocessor as device_preprocessor, span_struct
 
-_ERROR_NAMES = {"mabs": C.ERR_MABS, "l1": C.ERR_L1, "msq": C.ERR_MSQ, "iters": C.ERR_ITERS}
+_ERROR_NAMES = {"mabs": C.ERR_MABS, "l1": C.ERR_L1, "msq": C.ERR_MSQ, "iters": C.ERR_ITERS,
+                "max": C.ERR_MAX, "maxdifference": C.ERR_MAX}
 
 
 def _error_code(error_type) -> int:
     name = error_type if isinstance(error_type, str) else getattr(error_type, "__name__", str(error_type))
     name = name.lower()
     if name not in _ERROR_NAMES:
-        raise Exception("the device engine fuses the Mabs, L1, MSQ and 'iters' criteria; got " + str(error_type))
+        raise Exception("the device engine fuses the Mabs, L1, MSQ, MaxDifference and 'iters' criteria; got "
+                        + str(error_type))
     return _ERROR_NAMES[name]
 
 
@@ -191,7 +193,7 @@ class GraphFilter:
         sf[C.SF_ALPHA] = float(alpha_s)
         sf[C.SF_INVS] = 1.0
         sf[C.SF_TOL] = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))  # convergence.py:101
-        sf[C.SF_MEAN] = 1.0 if code == C.ERR_L1 else float(g.n)
+        sf[C.SF_MEAN] = 1.0 if code in (C.ERR_L1, C.ERR_MAX) else float(g.n)
         sf[C.SF_NORM] = float(norm)
         si[C.SI_MAX_ITERS] = cm.max_iters
         si[C.SI_END_MODULO] = max(cm.end_modulo, 1)
@@ -207,7 +209,8 @@ class GraphFilter:
         cm = self.convergence
         budget = cm.max_iters - 1                             # convergence.py:85-90: at most max_iters-1 steps
         done = 0
-        chunk = max(self.chunk, 1)
+        # the previous solve of this filter is the best guess of how many steps the next one needs
+        chunk = max(self.chunk, min(getattr(self, "_steps_hint", 0) + 1, 64), 1)
         stop, steps, iteration = C.RUNNING, 0, 1
         while done < budget:
             k = min(chunk, budget - done)
@@ -221,6 +224,7 @@ class GraphFilter:
         if stop == C.RUNNING:                                 # max_iters <= 1: stopped before any step
             iteration, stop = 1, C.MAX_ITERS
         cm.iteration = iteration
+        self._steps_hint = steps
         cm.errors = err_hist[1:steps + 1]
         if stop == C.MAX_ITERS and _error_code(cm.error_type) != C.ERR_ITERS and cm.iter_exception is not None:
             raise cm.iter_exception("Could not converge within " + str(cm.max_iters) + " iterations")
@@ -255,6 +259,8 @@ class RecursiveGraphFilter(GraphFilter):
         # otherwise (PGB_PANEL=1 forces it: parity tests and A/B timing).
         if g.in_view.weighted or warm_start is not None or graph_dropout != 0 or g.pathological:
             return False
+        if _error_code(self.convergence.error_type) == C.ERR_MAX:
+            return False                                      # the panel kernel has no max reduction
         import os
         forced = os.environ.get("PGB_PANEL")
         if forced not in (None, ""):

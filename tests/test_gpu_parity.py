@@ -310,6 +310,46 @@ def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, monkeypatch, dt
         pgb.PageRank(0.99, tol=1e-14, max_iters=4, dtype=dtype).propagate(g, torch.from_numpy(P).cuda())
 
 
+@pytest.mark.parametrize("name", GOLDEN_GRAPHS)
+@pytest.mark.parametrize("variant", ["hsell_or_stream", "item_stream"])
+def test_max_difference_criterion_matches_oracle(pgb, torch_cuda, orc, name, variant):
+    """error_type=MaxDifference (measures/supervised.py:93-98): a max reduction instead of a sum, on both
+    per-iteration kernels; iteration counts and the error sequence must equal the oracle's."""
+    torch = torch_cuda
+    from pygrank_b200 import _capi as C
+    z, A, directed = load_golden(name)
+    M = orc.to_sparse_matrix(A, "auto", directed)
+    g = _graph(pgb, A, directed)
+
+    class MaxDifference:      # selected like the reference's class (its __name__ is what the engine maps)
+        pass
+
+    lib = C.lib()
+    try:
+        if variant == "item_stream":
+            C.check(lib.pgb_set_kernel_variant(3))
+        for c in range(2):
+            p = z["P"][:, c]
+            ref, iters, errs = orc.pagerank(M, p, 0.85, tol=1e-8, max_iters=1000, error_type="max")
+            for et in ("max", MaxDifference):
+                alg = pgb.PageRank(0.85, tol=1e-8, max_iters=1000, error_type=et)
+                r = alg(g, p)
+                assert alg.convergence.iteration == iters, (name, c)
+                assert rel_l1(r.numpy(), ref) <= FP64_TOL
+                # the maximum sits on the largest scores, whose fp64 rounding noise (1e-17 absolute) is ~1e-9 of
+                # an error near the tolerance: compare the sequences to 1e-6, the iteration counts exactly
+                assert np.allclose(alg.convergence.errors.cpu().numpy(), errs, rtol=1e-6, atol=1e-300)
+            ref, iters, _ = orc.heat_kernel(M, p, 3, tol=1e-8, error_type="max")
+            alg = pgb.HeatKernel(3, tol=1e-8, error_type="max")
+            assert rel_l1(alg(g, p).numpy(), ref) <= FP64_TOL and alg.convergence.iteration == iters
+            a32 = pgb.PageRank(0.85, tol=1e-6, max_iters=1000, error_type="max", dtype=torch.float32)
+            ref, iters, _ = orc.pagerank(M, p, 0.85, tol=1e-6, max_iters=1000, error_type="max")
+            r32 = a32(g, p)
+            assert abs(a32.convergence.iteration - iters) <= 1 and rel_l1(r32.numpy(), ref) <= FP32_TOL
+    finally:
+        C.check(lib.pgb_set_kernel_variant(4))
+
+
 def test_personalization_forms_and_edge_cases(pgb, torch_cuda):
     torch = torch_cuda
     z, A, directed = load_golden("ba2000")
