@@ -102,9 +102,9 @@ def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional
     Hs = H // n_segments
     max_blocks = cfg["max_blocks"]
     if max_blocks <= 0:
-        # auto: hub blocks cover ~1/16 of the columns, between 64 and 256 blocks (measured: 64-96 best at
-        # 16.8 M columns, 256 best at 134 M, where the gather vector no longer fits L2)
-        max_blocks = max(64, min(256, (n_segments * seg_len) // (16 * H)))
+        # auto: hub blocks cover ~1/16 of the columns, between 64 and 256 blocks (measured: 64-96 best at 16.8 M
+        # columns; at 134 M columns, where the gather vector no longer fits L2: 64 < 128 < 256 > 512)
+        max_blocks = max(64, min(_env_int("PGB_HSELL_BLOCKS_CAP", 256), (n_segments * seg_len) // (16 * H)))
     K = max(min(max_blocks, -(-seg_len // Hs)), 0)
     if n_segments > 1 and K * Hs > seg_len:
         K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail
@@ -670,15 +670,16 @@ class DeviceGraph:
         p = float(p)
         if p == 0:
             return self
-        if not self.symmetric_structure:
-            raise Exception("graph_dropout on directed device graphs is not implemented yet")
         g = object.__new__(DeviceGraph)
         g.__dict__.update(self.__dict__)
         g._cache = {}
         view = self.in_view
         base = view.values(torch.float64)
         keep = (torch.rand(view.nnz, device=view.indptr.device) >= p).to(torch.float64) / (1.0 - p)
-        g.in_view = g.out_view = view.with_values(keep if base is None else base * keep)
+        dropped = view.with_values(keep if base is None else base * keep)
+        g.in_view = dropped                       # conv (the only consumer of a dropped graph, abstract_filters.py:59-62)
+        if self.symmetric_structure:              # reads the pull structure; a directed graph keeps its push view
+            g.out_view = dropped
         g.array = g
         return g
 

@@ -80,6 +80,9 @@ def test_hsell_shape_and_config_defaults(monkeypatch):
     assert H == 16384 and K == 64
     H, K = graph.hsell_shape(torch.float32, 8, 1 << 24)         # 8 ranks x 16.8 M rows: 134 M columns
     assert H == 32768 and K == 256
+    monkeypatch.setenv("PGB_HSELL_BLOCKS_CAP", "128")
+    assert graph.hsell_shape(torch.float32, 8, 1 << 24)[1] == 128
+    monkeypatch.delenv("PGB_HSELL_BLOCKS_CAP")
     H, K = graph.hsell_shape(torch.float32, 1, 1000)            # tiny graph: one partial block
     assert K == 1
     H, K = graph.hsell_shape(torch.float32, 2, 5000)            # multi-segment blocks must be full

@@ -132,3 +132,21 @@ def test_graph_dropout_semantics(pg):
         # survivors rescaled by 1/(1-p): the expectation is preserved
         assert abs(float(dropped.sum()) / float(full.sum()) - 1.0) < 0.05
         assert float((dropped - full).abs().sum()) > 0
+
+
+def test_graph_dropout_on_a_directed_graph(pg):
+    """graph_dropout (torch backends' semantics, core/backend/pytorch.py:34-38) also on directed graphs: the
+    pull view conv reads is masked and rescaled; p = 0 is the identity; the expectation is preserved."""
+    import torch
+    import pygrank_b200
+    z, A, directed = load_golden("gnp600d")
+    assert directed
+    g = pygrank_b200.DeviceGraph.from_scipy(A, directed=True, normalization="col")
+    x = torch.ones(A.shape[0], dtype=torch.float64, device="cuda")
+    full = g.conv(x)
+    assert g.dropout(0) is g
+    torch.manual_seed(1)
+    dropped = g.dropout(0.3).conv(x)
+    assert abs(float(dropped.sum()) / float(full.sum()) - 1.0) < 0.05
+    assert float((dropped - full).abs().sum()) > 0
+    assert float((g.conv(x) - full).abs().sum()) == 0          # the original graph is untouched
