@@ -38,7 +38,7 @@ constexpr int HS_SMEM_LIMIT = 232448;   // 227 KB opt-in dynamic shared memory p
 constexpr int UPD_BLOCK = 256;
 constexpr int UPD_AHEAD = 5;   // partial rows per slice requested before the first add
 
-static int g_tail_warps = 8;
+static int g_tail_warps = 6;
 
 __device__ __forceinline__ unsigned ld_stream_u32(const uint32_t *p) { return __ldcs(p); }
 
@@ -422,8 +422,11 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
         }
         if (tid == 0) s_hub_next = cur;
         __syncthreads();
-        while (true) {
-            int kind = 0, u = 0;   // 0: nothing left in this segment, 1: hub chunk, 2: tail chunk
+        // the id of the NEXT chunk is requested (lane 0) before the current one is processed, so the atomic's
+        // round trip — ~1 us on the contended global tail counter — hides behind the chunk's own work
+        auto grab = [&](int &kind, int &u) {   // 0: nothing left in this segment, 1: hub chunk, 2: tail chunk
+            kind = 0;
+            u = 0;
             if (lane == 0) {
                 if (tail_pref && *(volatile int *)&s_hub_next < seg_end) {
                     u = (int)atomicAdd(G.tail_queue, (unsigned)TB);
@@ -434,27 +437,39 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
                     if (u < seg_end) kind = 1;
                 }
             }
-            kind = __shfl_sync(FULL, kind, 0);
-            u = __shfl_sync(FULL, u, 0);
-            if (kind == 0) break;
+        };
+        int kind, u;
+        grab(kind, u);
+        kind = __shfl_sync(FULL, kind, 0);
+        u = __shfl_sync(FULL, u, 0);
+        while (kind != 0) {
+            int nkind, nu;
+            grab(nkind, nu);
             if (kind == 1) {
-                if (G.debug_skip & 1) continue;
-                const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.hub_chunks) + u);
-                hub_chunk<T>(h.hub_words, u, d.x, d.y, h.piece_row, s_z, partials, lane);
+                if (!(G.debug_skip & 1)) {
+                    const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.hub_chunks) + u);
+                    hub_chunk<T>(h.hub_words, u, d.x, d.y, h.piece_row, s_z, partials, lane);
+                }
             } else {
                 run_tail(u);
             }
+            kind = __shfl_sync(FULL, nkind, 0);
+            u = __shfl_sync(FULL, nu, 0);
         }
         cur = seg_end;
     }
     __syncthreads();
     // ---- drain the tail queue ---------------------------------------------------------------------
-    while (true) {
+    {
         int u = 0;
         if (lane == 0) u = (int)atomicAdd(G.tail_queue, (unsigned)TB);
         u = __shfl_sync(FULL, u, 0);
-        if (u >= tail_hi) break;
-        run_tail(u);
+        while (u < tail_hi) {
+            int nu = 0;
+            if (lane == 0) nu = (int)atomicAdd(G.tail_queue, (unsigned)TB);
+            run_tail(u);
+            u = __shfl_sync(FULL, nu, 0);
+        }
     }
 }
 
