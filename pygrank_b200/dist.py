@@ -103,6 +103,20 @@ def real_columns(vcols: torch.Tensor, n_local: int, world: int, block_cols: int,
     return torch.where(v < span, hub_col, tail_col)
 
 
+def reader_mask_from_need(need: torch.Tensor, rank: int, world: int, n_local: int, group=None) -> torch.Tensor:
+    """``need`` uint8[world*n_local]: 1 where THIS rank reads the entry of the gather vector (its rows reference
+    the column, it lies in one of its hub blocks, or it owns it).  One all-gather of these byte maps gives
+    every rank, for each of its own rows, the set of ranks that read the row's value: bit r of the returned
+    int32[n_local].  Collective; device agnostic (covered by the gloo CPU test)."""
+    gathered = torch.empty(world * need.numel(), dtype=torch.uint8, device=need.device)
+    dist.all_gather_into_tensor(gathered, need.contiguous(), group=group)
+    mine = gathered.view(world, need.numel())[:, rank * n_local:(rank + 1) * n_local]
+    mask = torch.zeros(n_local, dtype=torch.int32, device=need.device)
+    for r in range(world):
+        mask |= mine[r].to(torch.int32) << r
+    return mask
+
+
 # ------------------------------------------------------------------------------------------------
 class DistGraph:
     """This rank's rows of a symmetric-normalised, unweighted, undirected graph."""
@@ -225,14 +239,8 @@ class DistGraph:
             hs = form.block_cols // self.world
             need.view(self.world, self.n_local)[:, : min(form.n_blocks * hs, self.n_local)] = 1
         need[self.offset:self.offset + self.n_local] = 1              # the owner reads its own rows
-        gathered = torch.empty(self.world * self.n_global, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(gathered, need, group=self.group)
+        mask = reader_mask_from_need(need, self.rank, self.world, self.n_local, self.group)
         del need
-        mine = gathered.view(self.world, self.n_global)[:, self.offset:self.offset + self.n_local]
-        mask = torch.zeros(self.n_local, dtype=torch.int32, device=dev)
-        for r in range(self.world):
-            mask |= mine[r].to(torch.int32) << r
-        del gathered, mine
         self._cache[key] = mask
         return mask
 

@@ -61,15 +61,34 @@ def _worker(rank, world, port, scale, out):
     dist.all_reduce(acc)
     invS = 1.0 / (alpha * acc[0].item() + acc[1].item())
     bias = acc[1].item()
-    zfull = torch.empty(n_global, dtype=torch.float64)
-    dist.all_gather_into_tensor(zfull, torch.from_numpy(z))
+    # masked exchange (pgb_peers.row_mask): a rank's buffer receives a new value only where the rank reads it;
+    # everything else stays NaN here, so a missing reader bit would poison the result
+    from pygrank_b200.dist import reader_mask_from_need
+    need = torch.zeros(n_global, dtype=torch.uint8)
+    need[torch.from_numpy(A_loc.indices.astype(np.int64))] = 1
+    need[off:off + n_local] = 1
+    mask = reader_mask_from_need(need, rank, world, n_local)
+    assert bool(((mask >> rank) & 1).all())
+    all_masks = torch.empty(n_global, dtype=torch.int32)
+    dist.all_gather_into_tensor(all_masks, mask)
+    reads_me = ((all_masks >> rank) & 1).bool().numpy()           # entries of the full vector this rank receives
+    assert np.array_equal(reads_me, need.numpy().astype(bool))
+
+    def exchange(local):
+        full = torch.empty(n_global, dtype=torch.float64)
+        dist.all_gather_into_tensor(full, torch.from_numpy(np.ascontiguousarray(local)))
+        out = np.full(n_global, np.nan)
+        out[reads_me] = full.numpy()[reads_me]
+        return torch.from_numpy(out)
+
+    zfull = exchange(z)
     iteration, steps = 1, 0
     w = np.where(d_loc > 0, 1.0 / np.maximum(d_loc, 1), 0.0)
     while True:
         znew = (alpha * w * (A_loc @ zfull.numpy()) + q) * invS
         zold = zfull.numpy()[off:off + n_local]
         acc = torch.tensor([float((znew * c).sum()), float((sq * np.abs(znew - zold)).sum())], dtype=torch.float64)
-        dist.all_gather_into_tensor(zfull, torch.from_numpy(znew))
+        zfull = exchange(znew)
         dist.all_reduce(acc)
         steps += 1
         iteration = steps + 1
@@ -79,7 +98,10 @@ def _worker(rank, world, port, scale, out):
     scores_int = zfull.numpy() * np.concatenate([np.empty(0)] + [None] * 0) if False else None
     sq_full = torch.empty(n_global, dtype=torch.float64)
     dist.all_gather_into_tensor(sq_full, torch.from_numpy(sq))
-    scores_user = (zfull.numpy() * sq_full.numpy() * 10.0)[new_id.numpy()][:n]
+    zall = torch.empty(n_global, dtype=torch.float64)             # results: every rank's own (always valid) slice
+    dist.all_gather_into_tensor(zall, zfull[off:off + n_local].clone())
+    assert not np.isnan(zall.numpy()).any()
+    scores_user = (zall.numpy() * sq_full.numpy() * 10.0)[new_id.numpy()][:n]
     gathered = [None] * world
     dist.all_gather_object(gathered, (A_loc.indptr, A_loc.indices, A_loc.nnz))
     if rank == 0:
