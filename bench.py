@@ -195,19 +195,35 @@ def run_single(args):
     value = nnz * conv_calls / (dev_ms * 1e-3) / 1e9
 
     # ---- end-to-end leg: host seed lists in, full score vector out to pinned host memory -----
-    host_out = torch.empty(n, dtype=dtype).pin_memory()
+    # Every solve's scores go to pinned host memory inside the timed region; the copy of solve k runs on a
+    # side stream while solve k+1 computes (two host buffers), as a serving loop would do it.
+    host_out = [torch.empty(n, dtype=dtype).pin_memory(), torch.empty(n, dtype=dtype).pin_memory()]
+    copy_stream = torch.cuda.Stream()
     seed_lists = [[int(v) for v in s] for s in seeds]
+
+    def solve_to_host(i, keep):
+        r = alg(g, seed_lists[i])
+        ready = torch.cuda.Event()
+        ready.record()
+        copy_stream.wait_event(ready)
+        with torch.cuda.stream(copy_stream):
+            host_out[i & 1].copy_(r.np, non_blocking=True)
+        r.np.record_stream(copy_stream)
+        keep.append(r)
+        del keep[:-2]
+        return alg.convergence.iteration - 1
+
+    keep = []
     for i in range(args.warmup):
-        host_out.copy_(alg(g, seed_lists[i]).np, non_blocking=False)
+        solve_to_host(i, keep)
     torch.cuda.synchronize()
     e2e_calls = 0
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
     t1 = time.perf_counter()
     for i in range(args.warmup, total):
-        r = alg(g, seed_lists[i])
-        host_out.copy_(r.np, non_blocking=False)
-        e2e_calls += alg.convergence.iteration - 1
+        e2e_calls += solve_to_host(i, keep)
+    copy_stream.synchronize()
     ev3.record()
     torch.cuda.synchronize()
     e2e_s = max(ev2.elapsed_time(ev3) * 1e-3, time.perf_counter() - t1)
