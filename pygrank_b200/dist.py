@@ -473,3 +473,38 @@ class DistPageRank:
         full = torch.empty(g.n_global, dtype=local_scores.dtype, device=local_scores.device)
         dist.all_gather_into_tensor(full, local_scores.contiguous(), group=g.group)
         return full[g.new_id.long()][: g.n_nodes]
+
+
+# ------------------------------------------------------------------------------------------------
+# independent-unit sharding: seed sets / alpha values / tuner candidates are independent,
+# so with the graph replicated on every GPU the columns of a propagate() call are dealt to the ranks and
+# no collective touches the data path; only the results are gathered, if asked for.
+def column_shard(n_columns: int, rank: int, world: int) -> range:
+    """Columns owned by ``rank``: contiguous, sizes differing by at most one."""
+    base, extra = divmod(n_columns, world)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+def propagate_sharded(alg, graph, features: torch.Tensor, gather: bool = True, group=None):
+    """``NodeRanking.propagate`` (core/signals.py:225-226) over the GPUs of one box: every rank runs
+    ``alg.propagate`` (a pygrank_b200 filter) on its own columns of ``features`` against its own replica of
+    ``graph``.  Returns ``(scores, iterations)``: with ``gather`` the full ``[n, B]`` matrix and the
+    per-column iteration counts on every rank, else this rank's ``[n, len(shard)]`` block.  Collective."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    B = int(features.shape[1])
+    mine = column_shard(B, rank, world)
+    local = alg.propagate(graph, features[:, mine.start:mine.stop].contiguous()) if len(mine) else \
+        features.new_zeros((features.shape[0], 0))
+    its = list(getattr(alg.convergence, "iterations", [])) if len(mine) else []
+    if not gather:
+        return local, its
+    width = -(-B // world)                                           # pad every block to the widest shard
+    block = local.new_zeros((local.shape[0], width))
+    block[:, :local.shape[1]] = local
+    blocks = [torch.empty_like(block) for _ in range(world)]
+    dist.all_gather(blocks, block, group=group)
+    all_its = [None] * world
+    dist.all_gather_object(all_its, its, group=group)
+    out = torch.cat([blocks[r][:, :len(column_shard(B, r, world))] for r in range(world)], dim=1)
+    return out, [i for part in all_its for i in part]

@@ -167,3 +167,55 @@ def test_virtual_columns_are_a_bijection_with_contiguous_hub_blocks():
             assert torch.equal(v[inside] - b * H, rnk * hs + (pos - b * hs))
         tail = v >= K * H
         assert int(tail.sum()) == world * (n_local - K * hs)
+
+
+def test_column_shards_partition_the_columns():
+    from pygrank_b200.dist import column_shard
+    for B in (0, 1, 7, 8, 256, 257):
+        for world in (1, 2, 3, 8):
+            shards = [column_shard(B, r, world) for r in range(world)]
+            assert [c for sh in shards for c in sh] == list(range(B))
+            assert max(len(sh) for sh in shards) - min(len(sh) for sh in shards) <= 1
+
+
+class _FakeFilter:
+    """Stands in for a pygrank_b200 filter on CPU: propagate() doubles the features, one "iteration" per column index."""
+
+    class _CM:
+        iterations = []
+
+    def __init__(self):
+        self.convergence = self._CM()
+
+    def propagate(self, graph, features):
+        self.convergence.iterations = [graph + c for c in range(features.shape[1])]
+        return features * 2.0
+
+
+def _shard_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pygrank_b200.dist import column_shard, propagate_sharded
+    feats = torch.arange(5 * 7, dtype=torch.float64).reshape(5, 7)
+    full, its = propagate_sharded(_FakeFilter(), 100, feats, gather=True)
+    local, lits = propagate_sharded(_FakeFilter(), 100, feats, gather=False)
+    mine = column_shard(7, rank, world)
+    ok = torch.equal(full, feats * 2.0) and torch.equal(local, feats[:, mine.start:mine.stop] * 2.0)
+    ok = ok and its == [100 + c for r in range(world) for c in range(len(column_shard(7, r, world)))]
+    ok = ok and lits == [100 + c for c in range(len(mine))]
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok))
+    if rank == 0:
+        np.save(out, np.array(flags))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_propagate_sharded_two_ranks(tmp_path):
+    world = 2
+    out = str(tmp_path / "shard.npy")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_shard_worker, args=(world, port, out), nprocs=world, join=True)
+    assert np.load(out).all()
