@@ -102,9 +102,10 @@ def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional
     Hs = H // n_segments
     max_blocks = cfg["max_blocks"]
     if max_blocks <= 0:
-        # auto: hub blocks cover ~1/16 of the columns, between 64 and 256 blocks (measured: 64-96 best at 16.8 M
-        # columns; at 134 M columns, where the gather vector no longer fits L2: 64 < 128 < 256 > 512)
-        max_blocks = max(64, min(_env_int("PGB_HSELL_BLOCKS_CAP", 256), (n_segments * seg_len) // (16 * H)))
+        # auto: hub blocks cover ~1/8 of the columns, between 64 and 256 blocks.  Measured (ms per step): fp32,
+        # 16.8 M columns: 64 -> .685, 96 -> .670, 128 -> .70; fp64 (blocks half as wide): 64 -> 1.00, 128 -> .965;
+        # fp32, 134 M columns on 8 ranks: 64 -> 1.40, 128 -> 1.28, 256 -> 1.19, 512 -> 1.36
+        max_blocks = max(64, min(_env_int("PGB_HSELL_BLOCKS_CAP", 256), (n_segments * seg_len) // (8 * H)))
     K = max(min(max_blocks, -(-seg_len // Hs)), 0)
     if n_segments > 1 and K * Hs > seg_len:
         K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail

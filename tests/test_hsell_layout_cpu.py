@@ -77,7 +77,7 @@ def test_hsell_shape_and_config_defaults(monkeypatch):
     H, K = graph.hsell_shape(torch.float32, 1, 1 << 24)
     assert H == 32768 and K == 64
     H, K = graph.hsell_shape(torch.float64, 1, 1 << 24)
-    assert H == 16384 and K == 64
+    assert H == 16384 and K == 128
     H, K = graph.hsell_shape(torch.float32, 8, 1 << 24)         # 8 ranks x 16.8 M rows: 134 M columns
     assert H == 32768 and K == 256
     monkeypatch.setenv("PGB_HSELL_BLOCKS_CAP", "128")
