@@ -1,0 +1,38 @@
+"""Tiny end-to-end pass over every per-iteration kernel, meant to run under compute-sanitizer:
+    compute-sanitizer --tool memcheck python scripts/sanitize_small.py
+(hsell with small blocks so that many blocks, a tail, heavy slices and the second-level reduction appear)."""
+import os
+import sys
+
+os.environ.setdefault("PGB_HSELL_BLOCK_COLS", "256")
+os.environ.setdefault("PGB_HSELL_BLOCKS", "6")
+os.environ.setdefault("PGB_HSELL_MIN_ENTRIES", "8")
+os.environ.setdefault("PGB_HSELL_HEAVY_PARTS", "4")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import pygrank_b200 as pgb  # noqa: E402
+from pygrank_b200 import _capi as C  # noqa: E402
+from pygrank_b200 import device_synthetic  # noqa: E402
+
+scale = 12
+n = 1 << scale
+g = device_synthetic.rmat_graph_device(scale, 16, seed=1)
+p = torch.zeros(n, dtype=torch.float64, device="cuda")
+p[torch.arange(0, n, n // 10, device="cuda")] = 1.0
+for dtype in (torch.float32, torch.float64):
+    a = pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=dtype)
+    r = a(g, p.to(dtype))
+    h = pgb.HeatKernel(3, dtype=dtype)(g, p.to(dtype))
+    w = pgb.AbsorbingWalks(0.85, tol=1e-9, max_iters=200, dtype=dtype)(g, p.to(dtype))
+    m = pgb.PageRank(0.85, tol=1e-8, max_iters=200, dtype=dtype, error_type="max")(g, p.to(dtype))
+    y = g.conv(p.to(dtype))
+    print(dtype, a.convergence.iteration, float(r.np.sum()), float(h.np.sum()), float(w.np.sum()), float(y.sum()))
+os.environ["PGB_PANEL"] = "1"
+out = pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=torch.float32).propagate(g, torch.stack([p, p * 2, p * 0], 1).float())
+print("panel", tuple(out.shape), float(out.sum()))
+C.check(C.lib().pgb_set_kernel_variant(3))
+a = pgb.PageRank(0.85, tol=1e-9, max_iters=200)
+print("item stream", a(g, p).np.sum().item(), a.convergence.iteration)
+torch.cuda.synchronize()
+print("sanitize_small done")
