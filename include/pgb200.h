@@ -172,8 +172,8 @@ int pgb_build_item_stream(int64_t n, int64_t nnz, const int32_t *indptr, const i
  * kernel's phase 2, and nothing else — the measured ceiling of any row-gather formulation for this
  * graph (bench.py reports the fused kernel against it).  scratch: >= 8 bytes. */
 int pgb_gather_probe(const pgb_csr *g, int dtype, const void *z, void *scratch, void *stream);
-/* 4 (default): hsell when the graph carries that form, else 3; 3: warp tiles over the item stream;
- * 2: warp tiles over CSR; 1: CTA-wide tiles (A/B timing). */
+/* 4 (default): hsell when the graph carries that form, else the item-stream kernel; 3: always the
+ * item-stream kernel (A/B timing and parity between the two per-iteration kernels). */
 int pgb_set_kernel_variant(int variant);
 
 /* ---- synthetic graphs (bench/tests; no reference counterpart, graphs are downloaded in

@@ -151,7 +151,7 @@ def lib() -> ctypes.CDLL:
         if handle.pgb_abi_version() != 2:
             raise Exception("libpgb200.so ABI version mismatch")
         variant = os.environ.get("PGB_KERNEL_VARIANT")
-        if variant:   # A/B timing aid: 1 = CTA-wide tiles, 2 = warp tiles, 3 = item stream, 4 = hsell (default)
+        if variant:   # A/B timing aid: 3 = item-stream kernel, 4 = hsell when available (default)
             if handle.pgb_set_kernel_variant(int(variant)) != 0:
                 raise Exception("pgb200: " + handle.pgb_last_error().decode())
         tail_warps = os.environ.get("PGB_HSELL_TAIL_WARPS")

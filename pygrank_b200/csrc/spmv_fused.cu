@@ -1,5 +1,5 @@
-// K2 / K4 / K5 — the per-iteration kernel of the hot path: one merge-path CSR row-gather
-// fused with the filter's elementwise update and the convergence reduction.
+// K2 / K4 / K5 — the merge-path per-iteration kernel (weighted graphs; A/B twin of csrc/hsell.cu on
+// unweighted ones) and the C-ABI entry points of the fused steps, which dispatch to either kernel family.
 //
 // Reference op sequence replaced per iteration (paths under /root/reference/pygrank):
 //   conv(ranks, M)                      core/backend/numpy.py:64-65 (scipy csc_matvec)
@@ -8,17 +8,13 @@
 //   Mabs(prev)(cur) <= tol              algorithms/convergence.py:96-101, measures/supervised.py:101-106
 //
 // Work decomposition.  The CSR is cut by merge path: the sequence "entries of row 0, end-marker of
-// row 0, entries of row 1, end-marker of row 1, ..." (n + nnz items) is split into tiles of
-// TILE_ITEMS consecutive items, so every tile costs the same no matter how skewed the degrees
-// are (power-law hubs, 38 % empty rows on RMAT).  A persistent grid (CTAs-per-SM x 148 SMs) walks
-// the tiles.  Per tile: (A) the column indices are streamed with coalesced evict-first loads and
-// the gather vector z is read through the read-only path into shared memory; (B) every thread
-// consumes IPT consecutive merge items from shared memory (IPT odd -> conflict-free strides) and
-// deposits per-row sums; (C) one thread per finished row applies the fused update with coalesced
-// reads/writes of the row-aligned vectors.  Rows cut by a tile boundary are completed by the LAST
-// tile that reaches them (fp64 atomic partial + ticket per completing tile; no spinning, no
-// ordering assumption).  Grid-level sums (error numerator, next normaliser) are one fp64 atomic
-// per CTA; the last CTA to finish plays ConvergenceManager on the device.
+// row 0, entries of row 1, end-marker of row 1, ..." (n + nnz items, stored as the item stream) is split
+// into tiles of TILE_ITEMS consecutive items, so every tile costs the same no matter how skewed the
+// degrees are (power-law hubs, 38 % empty rows on RMAT).  A persistent grid (CTAs-per-SM x 148 SMs) of
+// warp-autonomous tiles walks them (item_stream_kernel below).  Rows cut by a tile boundary are completed
+// by the LAST tile that reaches them (fp64 atomic partial + ticket per completing tile; no spinning, no
+// ordering assumption).  Grid-level sums (error numerator, next normaliser) are one fp64 atomic per CTA;
+// the last CTA to finish plays ConvergenceManager on the device (step_common.cuh).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -32,9 +28,9 @@ constexpr int BLOCK = 256;
 #endif
 constexpr int IPT = PGB_IPT;  // odd: thread-blocked reads of shared memory hit distinct banks
 static_assert(IPT % 2 == 1 && IPT <= 31, "items per thread must be odd");
-constexpr int TILE_ITEMS = BLOCK * IPT;   // merge items per tile (v1: one CTA; v2: one warp, 8 sub-tiles)
+constexpr int TILE_ITEMS = BLOCK * IPT;   // merge items per tile (one warp walks a tile in 8 passes)
 constexpr int WARPS = BLOCK / 32;
-constexpr int SUB_ITEMS = 32 * IPT;       // v2: items one warp consumes per pass
+constexpr int SUB_ITEMS = 32 * IPT;       // items one warp consumes per pass
 static_assert(TILE_ITEMS % SUB_ITEMS == 0, "a tile is a whole number of warp passes");
 
 __global__ void state_finalize_kernel(double *sf, int32_t *si, double *err_hist) {
@@ -61,315 +57,8 @@ __device__ __forceinline__ bool span_arrive(double *acc, uint32_t *cnt, double p
     return true;
 }
 
-template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
-__global__ void __launch_bounds__(BLOCK, 4) tile_kernel(const StepParams P) {
-    __shared__ T s_val[TILE_ITEMS];
-    __shared__ T s_rowsum[TILE_ITEMS + 1];
-    __shared__ int32_t s_end[TILE_ITEMS];
-    __shared__ double s_red[32];
-
-    if (MODE != MODE_CONV) {
-        if (P.si[PGB_SI_STOP] != PGB_RUNNING) return;  // run-ahead launches after convergence are no-ops
-    }
-    const int tid = threadIdx.x;
-    const T *__restrict__ zin = (const T *)P.zin;
-    const int32_t *__restrict__ indices = P.indices;
-    const int32_t *__restrict__ indptr = P.indptr;
-    const T *__restrict__ values = (const T *)P.values;
-    RowUpdate<T, MODE, SYMDEG> update(P);
-    const int64_t total_items = P.n + P.nnz;
-
-    for (int32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const int64_t item_lo = (int64_t)tile * TILE_ITEMS;
-        const int64_t item_hi = (item_lo + TILE_ITEMS < total_items) ? item_lo + TILE_ITEMS : total_items;
-        const int32_t r_lo = P.tile_row[tile], r_hi = P.tile_row[tile + 1];
-        const int64_t e_lo = item_lo - r_lo, e_hi = item_hi - r_hi;
-        const int nrows = r_hi - r_lo;           // rows whose end marker lies in this tile
-        const int nedges = (int)(e_hi - e_lo);   // entries in this tile
-        const int64_t row0_begin = indptr[r_lo];
-        const int start0 = (int)((row0_begin > e_lo ? row0_begin : e_lo) - e_lo);
-
-        // ---- phase A: stream indices, gather z, stage in shared memory ----------------------
-        for (int k = tid; k < nrows; k += BLOCK) s_end[k] = (int32_t)((int64_t)indptr[r_lo + 1 + k] - e_lo);
-        for (int k = tid; k <= nrows; k += BLOCK) s_rowsum[k] = (T)0;
-        {
-            int32_t cols[IPT];
-            T vals[IPT];
-#pragma unroll
-            for (int s = 0; s < IPT; ++s) {
-                const int i = s * BLOCK + tid;
-                cols[s] = (i < nedges) ? ld_stream(indices + e_lo + i) : -1;
-            }
-#pragma unroll
-            for (int s = 0; s < IPT; ++s) vals[s] = (cols[s] >= 0) ? __ldg(zin + cols[s]) : (T)0;
-            if (WEIGHTED) {
-#pragma unroll
-                for (int s = 0; s < IPT; ++s) {
-                    const int i = s * BLOCK + tid;
-                    if (i < nedges) vals[s] *= ld_stream(values + e_lo + i);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < IPT; ++s) {
-                const int i = s * BLOCK + tid;
-                if (i < nedges) s_val[i] = vals[s];
-            }
-        }
-        __syncthreads();
-
-        // ---- phase B: each thread consumes IPT consecutive merge items -----------------------
-        const int nitems = nrows + nedges;
-        const int d = tid * IPT;
-        if (d < nitems) {
-            int lo = 0, hi = nrows;  // rows whose marker precedes item d
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (s_end[mid] + mid < d)
-                    lo = mid + 1;
-                else
-                    hi = mid;
-            }
-            int k = lo, ec = d - lo;
-            T run = (T)0;
-            bool first = true;
-            const int stop = (d + IPT < nitems) ? IPT : nitems - d;
-            for (int s = 0; s < stop; ++s) {
-                if (k < nrows && ec == s_end[k]) {
-                    if (first)
-                        atomicAdd(&s_rowsum[k], run);  // row may have started in an earlier thread
-                    else
-                        s_rowsum[k] = run;             // row lies entirely inside this thread
-                    first = false;
-                    run = (T)0;
-                    ++k;
-                } else {
-                    run += s_val[ec];
-                    ++ec;
-                }
-            }
-            atomicAdd(&s_rowsum[k], run);  // open row continues in the next thread / tile
-        }
-        __syncthreads();
-
-        // ---- phase C: fused row update ---------------------------------------------------------
-        const bool lead_span = (nrows > 0) && (row0_begin < e_lo);  // first finished row began earlier
-        for (int k = tid; k < nrows; k += BLOCK) {
-            if (k == 0 && lead_span) continue;
-            const int deg = s_end[k] - (k ? s_end[k - 1] : start0);
-            update((int64_t)r_lo + k, s_rowsum[k], deg);
-        }
-        // rows cut by a tile boundary: partial -> slot of the completing tile; last arrival finishes the row
-        const bool has_trail = (r_hi < P.n) && (nrows > 0 ? (int)(s_end[nrows - 1]) < nedges : nedges > 0);
-        if ((tid == 0 && lead_span) || (tid == 32 && has_trail)) {
-            const int64_t r = (tid == 0) ? r_lo : r_hi;
-            const double partial = (double)((tid == 0) ? s_rowsum[0] : s_rowsum[nrows]);
-            const int64_t b = indptr[r], e = indptr[r + 1];
-            const int64_t t_a = (b + r) / TILE_ITEMS, t_b = (e + r) / TILE_ITEMS;
-            const uint32_t expected = (uint32_t)(t_b - t_a + 1);
-            double total;
-            if (span_arrive(&P.span_acc[t_b], &P.span_cnt[t_b], partial, expected, &total))
-                update(r, (T)total, (int)(e - b));
-        }
-        __syncthreads();  // shared memory is reused by the next tile
-    }
-
-    if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
-}
-
 // ---------------------------------------------------------------------------------------------
-// v2: warp-autonomous merge tiles.  Each WARP owns a tile (TILE_ITEMS consecutive merge items) and
-// walks it in passes of SUB_ITEMS = 32 x IPT items with __syncwarp only — no block barrier on the
-// hot loop, so the 32 resident warps of an SM are always spread over all phases and the L1 wavefront
-// pipe (the measured limit for scattered 4-byte gathers, ~1 line/clk/SM) stays busy.
-//   1. the row-end markers of the pass become a bitmask over its items (REDUX.OR across lanes);
-//   2. lanes take items STRIPED (item = s*32+lane): non-marker items are consecutive CSR entries ->
-//      coalesced evict-first index loads, IPT independent gathers in flight per lane, values parked
-//      in shared memory in ITEM space (markers hold 0);
-//   3. lanes re-read their IPT consecutive items BLOCKED (conflict-free, IPT odd) and run the merge
-//      from registers: a marker bit closes a row; the open head/tail pieces are stitched with one
-//      5-step segmented warp scan; the piece still open at the end is carried to the next pass;
-//   4. finished rows are updated 32 at a time by consecutive lanes (coalesced row-aligned streams).
-// Shared memory is 2 x SUB_ITEMS values per warp (18 KB per CTA in fp32), leaving most of the 228 KB
-// for L1, which holds the hub end of the degree-ranked gather vector.
-template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
-__global__ void __launch_bounds__(BLOCK, 4) warp_tile_kernel(const StepParams P) {
-    // one buffer per warp: item values (phase 2 -> 3), then reused for the finished-row sums (3 -> 4)
-    __shared__ T s_item[WARPS][SUB_ITEMS + 1];
-    __shared__ unsigned s_mask[WARPS][IPT + 1];  // marker words of the pass (+ a zero guard word)
-    __shared__ int s_pre[WARPS][IPT + 1];        // markers before each word
-    __shared__ double s_red[32];
-
-    if (MODE != MODE_CONV) {
-        if (P.si[PGB_SI_STOP] != PGB_RUNNING) return;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) s_mask[warp][IPT] = 0u;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const T *__restrict__ zin = (const T *)P.zin;
-    const int32_t *__restrict__ indices = P.indices;
-    const int32_t *__restrict__ indptr = P.indptr;
-    const T *__restrict__ values = (const T *)P.values;
-    T *item = s_item[warp];
-    T *rowsum = s_item[warp];
-    RowUpdate<T, MODE, SYMDEG> update(P);
-    const int64_t total_items = P.n + P.nnz;
-
-    for (int32_t tile = blockIdx.x * WARPS + warp; tile < P.n_tiles; tile += gridDim.x * WARPS) {
-        const int64_t item_lo = (int64_t)tile * TILE_ITEMS;
-        const int64_t item_hi = (item_lo + TILE_ITEMS < total_items) ? item_lo + TILE_ITEMS : total_items;
-        const int32_t r_lo = P.tile_row[tile], r_hi = P.tile_row[tile + 1];
-        const int64_t e_lo = item_lo - r_lo, e_hi = item_hi - r_hi;
-        const bool lead_span = (r_hi > r_lo) && ((int64_t)indptr[r_lo] < e_lo);  // first finished row began earlier
-        int64_t r_cur = r_lo;
-        T carry = (T)0;  // sum of the row still open at the end of the previous pass
-
-        for (int64_t I0 = item_lo; I0 < item_hi; I0 += SUB_ITEMS) {
-            const int nitems = (int)((item_hi - I0 < SUB_ITEMS) ? item_hi - I0 : SUB_ITEMS);
-            const int64_t e_cur = I0 - r_cur;  // CSR entry of the first non-marker item
-
-            // ---- 1. marker bitmask of this pass -------------------------------------------------
-            unsigned m[IPT];
-#pragma unroll
-            for (int s = 0; s < IPT; ++s) m[s] = 0u;
-            int nrows = 0;
-            for (int b = 0;; ++b) {
-                const int64_t row = r_cur + b * 32 + lane;
-                int64_t pos = nitems;
-                if (row < P.n) pos = (int64_t)indptr[row + 1] + row - I0;
-                const bool valid = pos < nitems;
-                const int w = valid ? (int)(pos >> 5) : -1;
-                const unsigned bit = valid ? (1u << (pos & 31)) : 0u;
-#pragma unroll
-                for (int s = 0; s < IPT; ++s) m[s] |= __reduce_or_sync(FULL, (w == s) ? bit : 0u);
-                const int cnt = __popc(__ballot_sync(FULL, valid));
-                nrows += cnt;
-                if (cnt < 32) break;
-            }
-
-            // ---- 2. striped: stream indices, gather, park values in item space ------------------
-            {
-                int32_t cols[IPT];
-                int64_t eidx[WEIGHTED ? IPT : 1];
-                int pre = 0;
-#pragma unroll
-                for (int s = 0; s < IPT; ++s) {
-                    const int p = s * 32 + lane;
-                    const bool is_marker = (m[s] >> lane) & 1u;
-                    const int rank = pre + __popc(m[s] & lt_mask);
-                    const int64_t e = e_cur + p - rank;
-                    const bool active = (p < nitems) && !is_marker;
-                    cols[s] = active ? ld_stream(indices + e) : -1;
-                    if (WEIGHTED) eidx[s] = e;
-                    if (lane == s) {  // publish the mask for the blocked phase (dynamic word index there)
-                        s_mask[warp][s] = m[s];
-                        s_pre[warp][s] = pre;
-                    }
-                    pre += __popc(m[s]);
-                }
-                T x[IPT];
-#pragma unroll
-                for (int s = 0; s < IPT; ++s) x[s] = (cols[s] >= 0) ? __ldg(zin + cols[s]) : (T)0;
-                if (WEIGHTED) {
-#pragma unroll
-                    for (int s = 0; s < IPT; ++s)
-                        if (cols[s] >= 0) x[s] *= ld_stream(values + eidx[WEIGHTED ? s : 0]);
-                }
-#pragma unroll
-                for (int s = 0; s < IPT; ++s) item[s * 32 + lane] = x[s];
-            }
-            __syncwarp();
-
-            // ---- 3. blocked: IPT consecutive items per lane, merge from registers ---------------
-            {
-                const int p0 = lane * IPT;
-                const int w0 = p0 >> 5, sh = p0 & 31;
-                const unsigned lo = s_mask[warp][w0], hi = s_mask[warp][w0 + 1];
-                int k = s_pre[warp][w0] + __popc(lo & ((1u << sh) - 1u));  // rows finished before item p0
-                const unsigned bits = __funnelshift_r(lo, hi, sh) & ((1u << IPT) - 1u);
-                T it[IPT];
-#pragma unroll
-                for (int j = 0; j < IPT; ++j) it[j] = item[p0 + j];
-                __syncwarp();  // every lane holds its items in registers: the buffer becomes the row sums
-                T run = (T)0, head = (T)0;
-                int first_k = -1;
-#pragma unroll
-                for (int j = 0; j < IPT; ++j) {
-                    if ((bits >> j) & 1u) {
-                        if (first_k < 0) {
-                            head = run;
-                            first_k = k;
-                        } else {
-                            rowsum[k] = run;  // row lies entirely inside this lane
-                        }
-                        run = (T)0;
-                        ++k;
-                    } else {
-                        run += it[j];
-                    }
-                }
-                // stitch pieces across lanes: segments restart at every lane that closed a row
-                const bool closed = first_k >= 0;
-                const unsigned closed_mask = __ballot_sync(FULL, closed);
-                T seg = run;  // inclusive segmented scan of the open tails
-                bool f = closed;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const T t = __shfl_up_sync(FULL, seg, d);
-                    const bool tf = __shfl_up_sync(FULL, (int)f, d);
-                    if (lane >= d && !f) {
-                        seg += t;
-                        f = tf;
-                    }
-                }
-                T carry_in = __shfl_up_sync(FULL, seg, 1);
-                if (lane == 0) carry_in = (T)0;
-                if ((closed_mask & lt_mask) == 0u) carry_in += carry;  // nothing closed before this lane
-                if (closed) rowsum[first_k] = head + carry_in;
-                const T last = __shfl_sync(FULL, seg, 31);
-                carry = (closed_mask == 0u) ? carry + last : last;
-            }
-            __syncwarp();
-
-            // ---- 4. fused update of the rows finished in this pass ------------------------------
-            for (int k = lane; k < nrows; k += 32) {
-                const int64_t row = r_cur + k;
-                const T acc = rowsum[k];
-                const int64_t b = indptr[row], e = indptr[row + 1];
-                if (lead_span && row == r_lo) {
-                    // began in an earlier tile: this tile is its completing slot
-                    const int64_t t_a = (b + row) / TILE_ITEMS;
-                    const uint32_t expected = (uint32_t)(tile - t_a + 1);
-                    double total;
-                    if (span_arrive(&P.span_acc[tile], &P.span_cnt[tile], (double)acc, expected, &total))
-                        update(row, (T)total, (int)(e - b));
-                } else {
-                    update(row, acc, (int)(e - b));
-                }
-            }
-            __syncwarp();
-            r_cur += nrows;
-        }
-
-        // row still open at the end of the tile: hand the partial to the tile that completes it
-        if (lane == 0 && r_hi < P.n) {
-            const int64_t b = indptr[r_hi], e = indptr[r_hi + 1];
-            const int64_t first_here = b > e_lo ? b : e_lo;
-            if (e_hi > first_here) {
-                const int64_t t_a = (b + r_hi) / TILE_ITEMS, t_b = (e + r_hi) / TILE_ITEMS;
-                const uint32_t expected = (uint32_t)(t_b - t_a + 1);
-                double total;
-                if (span_arrive(&P.span_acc[t_b], &P.span_cnt[t_b], (double)carry, expected, &total))
-                    update(r_hi, (T)total, (int)(e - b));
-            }
-        }
-    }
-
-    if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
-}
-
-// ---------------------------------------------------------------------------------------------
-// v3: warp-autonomous tiles over the ITEM-SPACE stream.  The graph is additionally stored as
+// Warp-autonomous tiles over the ITEM-SPACE stream.  The graph is additionally stored as
 // istream[n + nnz]: for every row its ascending column indices followed by one terminator
 // -1-deg (same bytes as indices + row pointers).  A merge tile is then a plain slice of that array:
 // no row-pointer loads, no rank arithmetic — a lane's item is an entry (col >= 0) or a row end
@@ -638,30 +327,25 @@ __global__ void __launch_bounds__(BLOCK, 4) gather_probe_kernel(const int32_t *_
     if (acc == (T)-123456789) out[0] = acc;  // keeps the loads alive
 }
 
-static int g_kernel_variant = 4;  // 1 = CTA tiles, 2 = warp tiles over CSR, 3 = warp tiles over the item stream,
-                                   // 4 = hsell when the graph carries that form, else 3
+static int g_kernel_variant = 4;  // 3 = warp tiles over the item stream, 4 = hsell when the graph carries that form, else 3
 
 template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
 static int launch_tiles(const StepParams &P, cudaStream_t st) {
-    static int ctas_per_sm[4] = {0, 0, 0, 0};
-    int variant = g_kernel_variant > 3 ? 3 : g_kernel_variant;
-    if (variant == 3 && (!P.istream || (WEIGHTED && !P.vstream)))
+    static int ctas_per_sm = 0;
+    if (!P.istream || (WEIGHTED && !P.vstream))
         return fail("the item-stream kernel needs pgb_csr.istream%s (pgb_build_item_stream)", WEIGHTED ? "/vstream" : "");
-    if (ctas_per_sm[variant] == 0) {
+    if (ctas_per_sm == 0) {
         int v = 0;
-        cudaError_t e = (variant == 1)
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, tile_kernel<T, WEIGHTED, MODE, SYMDEG>, BLOCK, 0)
-            : (variant == 2)
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, warp_tile_kernel<T, WEIGHTED, MODE, SYMDEG>, BLOCK, 0)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, item_stream_kernel<T, WEIGHTED, MODE, SYMDEG>, BLOCK, 0);
-        if (e != cudaSuccess || v < 1) v = 2;
-        ctas_per_sm[variant] = v;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, item_stream_kernel<T, WEIGHTED, MODE, SYMDEG>, BLOCK, 0) !=
+                cudaSuccess || v < 1)
+            v = 2;
+        ctas_per_sm = v;
         // Give shared memory only what the resident CTAs need: the rest of the 228 KB stays L1, which
         // holds the hot end of the gather vector (measured 1.92 -> 1.81 ms on RMAT-24 fp32).
         int pct = -1;
         if (const char *c = getenv("PGB_SMEM_CARVEOUT")) {
             pct = atoi(c);  // experiment knob
-        } else if (variant == 3) {
+        } else {
             cudaFuncAttributes fa;
             if (cudaFuncGetAttributes(&fa, item_stream_kernel<T, WEIGHTED, MODE, SYMDEG>) == cudaSuccess) {
                 const size_t need = (fa.sharedSizeBytes + 1024) * (size_t)v;
@@ -669,36 +353,16 @@ static int launch_tiles(const StepParams &P, cudaStream_t st) {
                 if (pct > 100) pct = 100;
             }
         }
-        if (pct >= 0) {
-            if (variant == 1)
-                cudaFuncSetAttribute(tile_kernel<T, WEIGHTED, MODE, SYMDEG>,
-                                     cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            else if (variant == 2)
-                cudaFuncSetAttribute(warp_tile_kernel<T, WEIGHTED, MODE, SYMDEG>,
-                                     cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            else
-                cudaFuncSetAttribute(item_stream_kernel<T, WEIGHTED, MODE, SYMDEG>,
-                                     cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        }
+        if (pct >= 0)
+            cudaFuncSetAttribute(item_stream_kernel<T, WEIGHTED, MODE, SYMDEG>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
-    int grid = sm_count() * ctas_per_sm[variant];
-    if (variant == 1) {
-        if (grid > P.n_tiles) grid = P.n_tiles;
-        if (grid < 1) return 0;
-        tile_kernel<T, WEIGHTED, MODE, SYMDEG><<<grid, BLOCK, 0, st>>>(P);
-        PGB_LAUNCH_OK("tile_kernel");
-    } else {
-        const int need = (int)ceil_div(P.n_tiles, WARPS);
-        if (grid > need) grid = need;
-        if (grid < 1) return 0;
-        if (variant == 2) {
-            warp_tile_kernel<T, WEIGHTED, MODE, SYMDEG><<<grid, BLOCK, 0, st>>>(P);
-            PGB_LAUNCH_OK("warp_tile_kernel");
-        } else {
-            item_stream_kernel<T, WEIGHTED, MODE, SYMDEG><<<grid, BLOCK, 0, st>>>(P);
-            PGB_LAUNCH_OK("item_stream_kernel");
-        }
-    }
+    int grid = sm_count() * ctas_per_sm;
+    const int need = (int)ceil_div(P.n_tiles, WARPS);
+    if (grid > need) grid = need;
+    if (grid < 1) return 0;
+    item_stream_kernel<T, WEIGHTED, MODE, SYMDEG><<<grid, BLOCK, 0, st>>>(P);
+    PGB_LAUNCH_OK("item_stream_kernel");
     return 0;
 }
 
@@ -783,7 +447,7 @@ int pgb_gather_probe(const pgb_csr *g, int dtype, const void *z, void *scratch, 
 }
 
 int pgb_set_kernel_variant(int variant) {
-    if (variant < 1 || variant > 4) return fail("pgb_set_kernel_variant: %d is not 1, 2, 3 or 4", variant);
+    if (variant < 3 || variant > 4) return fail("pgb_set_kernel_variant: %d is not 3 or 4", variant);
     g_kernel_variant = variant;
     return 0;
 }
