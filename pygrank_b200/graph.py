@@ -152,6 +152,61 @@ def stream_layout(rounds: torch.Tensor, base: int, chunk: int = C.HSELL_CHUNK):
     return g0.contiguous(), p0.contiguous(), pieces, desc, n_chunks, n_parts, chunk_begin
 
 
+def hsell_layout(hr: torch.Tensor, tr: torch.Tensor, heavy_parts: int) -> dict:
+    """Everything of a pgb_hsell that follows from the unit sizes alone (plain torch, device agnostic; the CPU
+    tests run it against a numpy model of the kernels): ``hr`` int64 [K, S] rounds of every hub unit (0 = no
+    unit), ``tr`` int64 [S] tail rounds of every slice.  Streams and pieces as in :func:`stream_layout` (hub
+    stream first); first-level partial rows slice-major (a slice's pieces in block order, then its tail pieces);
+    slices with more than ``heavy_parts`` pieces reduced in groups of 32 consecutive rows into second-level
+    rows stored after the first level; one dump row at the very end for the padding pieces."""
+    i64 = torch.int64
+    dev = tr.device
+    K, S = int(hr.shape[0]), int(tr.shape[0])
+    if K > 0:
+        hub_g0, hub_p0, hub_pieces, hub_chunks, n_hub_chunks, n_hub_parts, bcb = stream_layout(hr, 0)
+    else:
+        hub_g0 = hub_p0 = torch.zeros(1, dtype=i64, device=dev)
+        hub_pieces = torch.zeros(0, dtype=i64, device=dev)
+        hub_chunks = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        n_hub_chunks = n_hub_parts = 0
+        bcb = torch.zeros(1, dtype=i64, device=dev)
+    tail_g0, tail_p0, tail_pieces, tail_chunks, n_tail_chunks, n_tail_parts, _ = stream_layout(tr.view(1, S), n_hub_parts)
+    n_pieces = n_hub_parts + n_tail_parts                       # pieces in stream order (hub stream, then tail)
+    per_slice = tail_pieces + (hub_pieces.view(K, S).sum(0) if K > 0 else 0)
+    slice_ptr64 = torch.zeros(S + 1, dtype=i64, device=dev)
+    torch.cumsum(per_slice, 0, out=slice_ptr64[1:])
+    n_rows1 = int(slice_ptr64[-1])                              # first-level partial rows, slice-major
+    # slices with many pieces (hub rows) are reduced in two levels: groups of 32 consecutive
+    # first-level rows -> one second-level row each (kernel B1); the slice then reads those
+    big = torch.nonzero(per_slice > heavy_parts).reshape(-1)
+    upd_begin = slice_ptr64[:-1].clone()
+    upd_count = per_slice.clone()
+    n_reduce = 0
+    reduce_items = torch.zeros(3, dtype=torch.int32, device=dev)
+    if big.numel():
+        cnt1 = per_slice[big]
+        groups = (cnt1 + 31) // 32
+        n_reduce = int(groups.sum())
+        owner = torch.repeat_interleave(torch.arange(big.numel(), device=dev), groups)       # item -> big slice
+        first_item = torch.cumsum(groups, 0) - groups
+        k = torch.arange(n_reduce, device=dev, dtype=i64) - first_item[owner]                # group index in slice
+        start = slice_ptr64[big][owner] + 32 * k
+        count = torch.clamp(cnt1[owner] - 32 * k, max=32)
+        out_row = n_rows1 + torch.arange(n_reduce, device=dev, dtype=i64)
+        reduce_items = torch.stack([start, count, out_row], 1).to(torch.int32).contiguous()
+        upd_begin[big] = n_rows1 + first_item
+        upd_count[big] = groups
+    dump_row = n_rows1 + n_reduce                               # written by the padding pieces of the streams
+    return {
+        "hub_g0": hub_g0, "hub_p0": hub_p0, "tail_g0": tail_g0, "tail_p0": tail_p0,
+        "hub_chunks": hub_chunks, "tail_chunks": tail_chunks, "n_hub_chunks": n_hub_chunks,
+        "n_tail_chunks": n_tail_chunks, "block_chunk_begin": bcb, "n_pieces": n_pieces, "n_rows1": n_rows1,
+        "n_reduce": n_reduce, "dump_row": dump_row, "n_partials": dump_row + 1,
+        "slice_ptr": slice_ptr64.to(torch.int32), "reduce_items": reduce_items, "upd_count": upd_count,
+        "upd_rows": torch.stack([upd_begin, upd_count], 1).to(torch.int32).contiguous(),
+    }
+
+
 class HsellForm:
     """Device arrays of one pgb_hsell (kept alive here; the C struct holds raw pointers)."""
 
@@ -174,56 +229,23 @@ class HsellForm:
                                     C.ptr(hub_rounds), C.ptr(tail_rounds), st))
 
         hr = hub_rounds[:K * S].to(i64).view(K, S) if K > 0 else torch.zeros((0, S), dtype=i64, device=dev)
-        tr = tail_rounds[:S].to(i64).view(1, S)
-        if K > 0:
-            hub_g0, hub_p0, hub_pieces, self.hub_chunks, n_hub_chunks, n_hub_parts, bcb = stream_layout(hr, 0)
-        else:
-            hub_g0 = hub_p0 = torch.zeros(1, dtype=i64, device=dev)
-            hub_pieces = torch.zeros(0, dtype=i64, device=dev)
-            self.hub_chunks = torch.zeros((1, 2), dtype=torch.int32, device=dev)
-            n_hub_chunks = n_hub_parts = 0
-            bcb = torch.zeros(1, dtype=i64, device=dev)
-        tail_g0, tail_p0, tail_pieces, self.tail_chunks, n_tail_chunks, n_tail_parts, _ = stream_layout(tr, n_hub_parts)
-        n_pieces = n_hub_parts + n_tail_parts                       # pieces in stream order (hub stream, then tail)
-        per_slice = tail_pieces + (hub_pieces.view(K, S).sum(0) if K > 0 else 0)
-        slice_ptr64 = torch.zeros(S + 1, dtype=i64, device=dev)
-        torch.cumsum(per_slice, 0, out=slice_ptr64[1:])
-        n_rows1 = int(slice_ptr64[-1])                              # first-level partial rows, slice-major
+        lay = hsell_layout(hr, tail_rounds[:S].to(i64), cfg["heavy_parts"])
+        hub_g0, hub_p0, tail_g0, tail_p0 = lay["hub_g0"], lay["hub_p0"], lay["tail_g0"], lay["tail_p0"]
+        self.hub_chunks, self.tail_chunks = lay["hub_chunks"], lay["tail_chunks"]
+        n_hub_chunks, n_tail_chunks, bcb = lay["n_hub_chunks"], lay["n_tail_chunks"], lay["block_chunk_begin"]
+        n_pieces, n_rows1, n_reduce, n_partials = lay["n_pieces"], lay["n_rows1"], lay["n_reduce"], lay["n_partials"]
+        heavy_parts, upd_count = cfg["heavy_parts"], lay["upd_count"]
         n_hub_words, n_tail_words = n_hub_chunks * CH * 32, n_tail_chunks * CH * 32
         if max(n_hub_words, n_tail_words) >= 2 ** 31 or max(n_pieces, n_rows1) >= 2 ** 31 - 2 ** 20:
             raise Exception("hsell: graph exceeds the 32-bit offsets of one device; row-partition it")
-        self.slice_ptr = slice_ptr64.to(torch.int32)
+        if n_partials >= 2 ** 27:
+            raise Exception("hsell: more than 2^27 partial rows; row-partition the graph")
+        self.slice_ptr, self.reduce_items, self.upd_rows = lay["slice_ptr"], lay["reduce_items"], lay["upd_rows"]
         pad_word = (H | (H << 16))
         pad_word = pad_word - 2 ** 32 if pad_word >= 2 ** 31 else pad_word
         self.hub_words = torch.full((max(n_hub_words, 1),), pad_word, dtype=torch.int32, device=dev)
         self.tail_cols = torch.full((max(n_tail_words, 1),), -1, dtype=torch.int32, device=dev)
-        # slices with many pieces (hub rows) are reduced in two levels: groups of 32 consecutive
-        # first-level rows -> one second-level row each (kernel B1); the slice then reads those
-        heavy_parts = cfg["heavy_parts"]
-        big = torch.nonzero(per_slice > heavy_parts).reshape(-1)
-        upd_begin = slice_ptr64[:-1].clone()
-        upd_count = per_slice.clone()
-        n_reduce = 0
-        self.reduce_items = torch.zeros(3, dtype=torch.int32, device=dev)
-        if big.numel():
-            cnt1 = per_slice[big]
-            groups = (cnt1 + 31) // 32
-            n_reduce = int(groups.sum())
-            owner = torch.repeat_interleave(torch.arange(big.numel(), device=dev), groups)       # item -> big slice
-            first_item = torch.cumsum(groups, 0) - groups
-            k = torch.arange(n_reduce, device=dev, dtype=i64) - first_item[owner]                # group index in slice
-            start = slice_ptr64[big][owner] + 32 * k
-            count = torch.clamp(cnt1[owner] - 32 * k, max=32)
-            out_row = n_rows1 + torch.arange(n_reduce, device=dev, dtype=i64)
-            self.reduce_items = torch.stack([start, count, out_row], 1).to(torch.int32).contiguous()
-            upd_begin[big] = n_rows1 + first_item
-            upd_count[big] = groups
-        dump_row = n_rows1 + n_reduce                               # written by the padding pieces of the streams
-        n_partials = dump_row + 1
-        if n_partials >= 2 ** 27:
-            raise Exception("hsell: more than 2^27 partial rows; row-partition the graph")
-        self.upd_rows = torch.stack([upd_begin, upd_count], 1).to(torch.int32).contiguous()
-        self.piece_row = torch.full((max(n_pieces, 1),), dump_row, dtype=torch.int32, device=dev)
+        self.piece_row = torch.full((max(n_pieces, 1),), lay["dump_row"], dtype=torch.int32, device=dev)
         scratch = torch.empty(max(view.nnz, 1), dtype=torch.int32, device=dev) if cfg["bank_order"] else None
         C.check(lib.pgb_hsell_fill(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, n_segments, seg_len,
                                    C.ptr(hub_rounds), C.ptr(tail_rounds), C.ptr(hub_g0), C.ptr(hub_p0),
