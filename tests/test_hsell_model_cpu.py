@@ -41,8 +41,9 @@ def count_np(indptr, indices, n, H, K, min_entries):
     return hub, tail
 
 
-def fill_np(indptr, indices, n, H, K, hub, tail, lay):
-    """hsell_fill_kernel without the bank-aware order: round data [round][lane] and piece_row."""
+def fill_np(indptr, indices, n, H, K, hub, tail, lay, real_col=lambda v: v):
+    """hsell_fill_kernel without the bank-aware order: round data [round][lane] and piece_row.  ``real_col``
+    maps the (virtual) columns of the tail to positions in the gather vector (hsell_real_col)."""
     S = (n + 31) // 32
     hub_words = np.full((lay["n_hub_chunks"] * CH * 32, 2), H, dtype=np.int64)      # (lo, hi) per word
     tail_cols = np.full(lay["n_tail_chunks"] * CH * 32, -1, dtype=np.int64)
@@ -69,7 +70,7 @@ def fill_np(indptr, indices, n, H, K, hub, tail, lay):
                 else:
                     tg0 = tail_g0[s]
                     for c in mine:
-                        tail_cols[(tg0 + t[lane]) * 32 + lane] = c
+                        tail_cols[(tg0 + t[lane]) * 32 + lane] = real_col(c)
                         t[lane] += 1
             if R > 0:
                 g0 = hub_g0[b, s]
@@ -82,7 +83,7 @@ def fill_np(indptr, indices, n, H, K, hub, tail, lay):
                 continue
             cols = indices[indptr[r]:indptr[r + 1]]
             for c in cols[cols // H >= K]:
-                tail_cols[(tail_g0[s] + t[lane]) * 32 + lane] = c
+                tail_cols[(tail_g0[s] + t[lane]) * 32 + lane] = real_col(c)
                 t[lane] += 1
         TR = tail[s]
         if TR > 0:
@@ -92,8 +93,10 @@ def fill_np(indptr, indices, n, H, K, hub, tail, lay):
     return hub_words, tail_cols, piece_row
 
 
-def execute_np(n, H, K, lay, hub_words, tail_cols, piece_row, z):
-    """hsell_gather_kernel + hsell_reduce_kernel + the summation part of hsell_update_kernel."""
+def execute_np(n, H, K, lay, hub_words, tail_cols, piece_row, z, n_segments=1, seg_len=None):
+    """hsell_gather_kernel + hsell_reduce_kernel + the summation part of hsell_update_kernel.  With
+    ``n_segments`` > 1 the gather vector is that many ranges of ``seg_len`` entries and hub block b is loaded as
+    the pieces [b*Hs, (b+1)*Hs) of every range, one after the other (Hs = H / n_segments)."""
     partials = np.full((lay["n_partials"], 32), np.nan)
     bcb = lay["block_chunk_begin"].numpy()
     for desc, n_chunks, is_hub in ((lay["hub_chunks"], lay["n_hub_chunks"], True),
@@ -103,9 +106,15 @@ def execute_np(n, H, K, lay, hub_words, tail_cols, piece_row, z):
             p, mask = d[c, 0], d[c, 1] | (1 << (CH - 1))
             if is_hub:
                 blk = int(np.searchsorted(bcb, c, side="right") - 1)
-                sz = np.zeros(H + 1)
-                seg = z[blk * H:(blk + 1) * H]
-                sz[:len(seg)] = seg                               # one hub block of z in "shared memory", + the zero slot
+                sz = np.zeros(H + 1)                             # one hub block of z in "shared memory", + the zero slot
+                if n_segments == 1:
+                    seg = z[blk * H:(blk + 1) * H]
+                    sz[:len(seg)] = seg
+                else:
+                    hs = H // n_segments
+                    for sg in range(n_segments):
+                        piece = z[sg * seg_len + blk * hs: sg * seg_len + min((blk + 1) * hs, seg_len)]
+                        sz[sg * hs: sg * hs + len(piece)] = piece
             acc = np.zeros(32)
             for r in range(CH):
                 base = (c * CH + r) * 32
@@ -157,3 +166,42 @@ def test_model_reproduces_the_matvec(scale, H, K, min_entries, heavy):
     assert np.allclose(y, ref, rtol=1e-12, atol=0)
     if heavy <= 2:
         assert lay["n_reduce"] > 0                               # the two-level reduction really ran
+
+
+@pytest.mark.parametrize("world,H,K", [(2, 64, 5), (4, 128, 3), (2, 256, 0)])
+def test_model_row_partitioned_form(world, H, K):
+    """The multi-GPU form: one rank's rows against the all-gathered vector (``world`` ranges of ``n_local``
+    entries).  The builders see virtual columns (pygrank_b200.dist.virtual_columns), hub block b gathers
+    the same positions of every range, tail columns are mapped back (real_columns / hsell_real_col)."""
+    from pygrank_b200.dist import real_columns, virtual_columns
+    rng = np.random.default_rng(world * 100 + H)
+    n_local = 640
+    n_global = world * n_local
+    hs = H // world
+    K = min(K, n_local // hs)
+    # a power-law-ish local block: columns near the start of every range are hubs
+    rows, cols = [], []
+    for r in range(n_local):
+        d = int(rng.integers(0, 40)) if r > 32 else int(rng.integers(200, 600))
+        pos = np.minimum((rng.pareto(0.7, d) * 8).astype(np.int64), n_local - 1)
+        c = np.unique(rng.integers(0, world, d) * n_local + pos)
+        rows += [r] * len(c)
+        cols += c.tolist()
+    A = sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(n_local, n_global)).tocsr()
+    A.sort_indices()
+    v = virtual_columns(torch.from_numpy(A.indices.astype(np.int64)), n_local, world, H, K).numpy()
+    Av = sp.coo_matrix((np.ones(len(rows)), (np.repeat(np.arange(n_local), np.diff(A.indptr)), v)),
+                       shape=(n_local, max(int(v.max()) + 1, n_global))).tocsr()
+    Av.sort_indices()
+    indptr, vidx = Av.indptr.astype(np.int64), Av.indices.astype(np.int64)
+    hub, tail = count_np(indptr, vidx, n_local, H, K, 8)
+    lay = hsell_layout(torch.from_numpy(hub), torch.from_numpy(tail), 4)
+
+    def real_col(vc):
+        return int(real_columns(torch.tensor([vc]), n_local, world, H, K)[0])
+
+    hub_words, tail_cols, piece_row = fill_np(indptr, vidx, n_local, H, K, hub, tail, lay, real_col)
+    assert (hub_words != H).sum() + (tail_cols >= 0).sum() == A.nnz
+    z = rng.uniform(0.5, 1.5, n_global)
+    y = execute_np(n_local, H, K, lay, hub_words, tail_cols, piece_row, z, n_segments=world, seg_len=n_local)
+    assert np.allclose(y, A @ z, rtol=1e-12, atol=0)
