@@ -635,8 +635,9 @@ class DeviceGraph:
         if out is None:
             out = torch.empty(self.n, dtype=dtype, device=z.device)
         cs = view.cstruct(dtype, hsell=hsell)
+        # (the partial-row buffer — and with it the hsell form — is only asked for when that form is used)
         C.check(lib.pgb_spmv(ctypes.byref(cs), dtype_code(dtype), C.ptr(z), C.ptr(rscale), None, C.ptr(out_perm),
-                             C.ptr(out), span_struct(view.span_ws(dtype)), C.stream_ptr()))
+                             C.ptr(out), span_struct(view.span_ws(dtype if hsell else None)), C.stream_ptr()))
         C.count_launches(view.kernels_per_step(dtype, hsell))
         return out
 
