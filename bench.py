@@ -375,7 +375,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=int, default=None, help="RMAT scale (default 24 + log2(gpus))")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--relabel", default="degree", choices=["degree", "none"])
+    ap.add_argument("--relabel", default="hub", choices=["hub", "degree", "none"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel-only", action="store_true",
                     help="experiments: time only the fused step (no solves, no e2e, no CPU leg) and print a short line")

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PGB_ABI_VERSION 2
+#define PGB_ABI_VERSION 3
 
 enum { PGB_F32 = 0, PGB_F64 = 1 };
 
@@ -124,6 +124,7 @@ typedef struct pgb_hsell {
     const int32_t *block_chunk_begin; /* [n_blocks+1] first hub chunk of each block                 */
     const int32_t *cta_hub_begin;     /* [n_ctas+1]                                                 */
     const int32_t *cta_tail_begin;    /* [n_ctas+1]                                                 */
+    const int32_t *piece_slice;       /* [pieces] slice of each piece (n_slices for padding pieces): accumulate mode */
 } pgb_hsell;
 
 /* Cross-tile workspace of one running filter: rows that straddle merge-path tiles are
@@ -132,6 +133,12 @@ typedef struct pgb_span_ws {
     double *acc;        /* [n_tiles * ncols]  */
     uint32_t *cnt;      /* [n_tiles]          */
     void *partials;     /* [hsell.n_partials][32] of the vector dtype when the graph has an hsell form, else NULL */
+    void *yacc;         /* accumulate mode of the hsell step: [hsell.n_slices + 1][32] of the vector dtype, zeroed by
+                         * the caller once (the update pass re-zeroes what it reads).  Non-NULL selects the mode: every
+                         * piece is added to its slice's row with one coalesced RED.ADD instead of being stored as a
+                         * partial row, and the update pass streams y — faster (no partial-row round trip through HBM,
+                         * no reduce kernel) but the order of the floating-point additions is not fixed; NULL keeps
+                         * the deterministic partial-row path. */
 } pgb_span_ws;
 
 /* Device-resident iteration state (mirror of ConvergenceManager, convergence.py:24-101). */
@@ -199,6 +206,18 @@ size_t pgb_degree_order_workspace_bytes(int64_t n);
 int pgb_degree_order(int64_t n, const int32_t *indptr, void *workspace, size_t workspace_bytes,
                      int32_t *perm, int32_t *iperm, void *stream);
 int pgb_relabel_coo(int64_t nnz, const int32_t *iperm, int32_t *row, int32_t *col, void *stream);
+/* Hub-signature order (refines pgb_degree_order; the internal node order is the engine's own choice — the
+ * reference keeps the user's order, preprocessing.py:151).  Degree ranks are cut into regions of G nodes up to
+ * rank `span` (the hub blocks of pgb_hsell) plus one tail region; INSIDE every region nodes are re-sorted by the
+ * set of hub regions their row touches (presence bits, region 0 most significant, rows touching it first; ties
+ * keep the degree order).  Column block membership is unchanged, but the 32 rows of a slice now share their
+ * blocks, so (slice, block) units that were too sparse for the shared-memory path become dense: on RMAT graphs
+ * the low-degree rows' entries move from the L2-gather tail into hub units.  In: perm/iperm from
+ * pgb_degree_order and the CSR in ORIGINAL labels; out: perm/iperm of the refined order. */
+#define PGB_SIGNATURE_WORDS 8
+size_t pgb_hub_order_workspace_bytes(int64_t n, int32_t words);
+int pgb_hub_order(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t G, int64_t span,
+                  void *workspace, size_t workspace_bytes, int32_t *perm, int32_t *iperm, void *stream);
 int pgb_mergepath_partition(int64_t n, int64_t nnz, const int32_t *indptr, int32_t n_tiles,
                             int32_t *tile_row, void *stream);
 
@@ -207,10 +226,11 @@ int pgb_mergepath_partition(int64_t n, int64_t nnz, const int32_t *indptr, int32
 /* Largest block_cols the gather kernel can keep in shared memory for this dtype (0: unknown dtype). */
 int pgb_hsell_max_block_cols(int dtype);
 /* Pass 1 — one warp per slice: hub_rounds[b*n_slices+s] = rounds (2 entries each) of the unit of
- * slice s in block b, or 0 when the slice has fewer than min_entries entries there (they stay in the
- * tail); tail_rounds[s] = longest tail row of the slice. */
+ * slice s in block b, or 0 when the slice has fewer than min_entries + round_cost * rounds entries there
+ * (a unit costs about round_cost L1 wavefronts per round plus a partial row, a tail entry one wavefront:
+ * sparse units stay in the tail); tail_rounds[s] = longest tail row of the slice. */
 int pgb_hsell_count(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
-                    int32_t min_entries, int32_t *hub_rounds, int32_t *tail_rounds, void *stream);
+                    int32_t min_entries, double round_cost, int32_t *hub_rounds, int32_t *tail_rounds, void *stream);
 /* Pass 2 — writes the round data and piece_row.  The caller supplies, per (block, slice) in
  * block-major order and per slice for the tail: the first round of the unit in its stream and the
  * number of its first piece (exclusive scans), and slice_ptr (first partial row of every slice: the

@@ -36,7 +36,8 @@ _lib = None
 def build_c(force: bool = False) -> str:
     """Compile ``csc_matvec.c`` with the Makefile next to it (gcc only)."""
     if force or not os.path.exists(_LIB_PATH) or (
-            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "csc_matvec.c"))):
+            os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f))
+                                              for f in ("csc_matvec.c", "rmat_gen.c"))):
         subprocess.run(["make", "-s", "-C", _HERE] + (["-B"] if force else []), check=True)
     return _LIB_PATH
 
@@ -52,6 +53,9 @@ def _c():
             getattr(lib, name).restype = None
         lib.oracle_csr_row_sums_f64.argtypes = [i64, vp, vp, vp]
         lib.oracle_csr_row_sums_f64.restype = None
+        lib.oracle_rmat_edges.argtypes = [ctypes.c_int, i64, i64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
+                                          ctypes.c_uint32, vp, vp]
+        lib.oracle_rmat_edges.restype = None
         _lib = lib
     return _lib
 

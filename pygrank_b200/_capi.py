@@ -23,6 +23,8 @@ RUNNING, CONVERGED, MAX_ITERS = 0, 1, 2
 SF_ALPHA, SF_BIAS, SF_INVS, SF_TACC, SF_EACC, SF_TOL, SF_MEAN, SF_LASTERR, SF_NORM, SF_PSUM = range(10)
 SI_TICKET, SI_STEPS, SI_STOP, SI_ITERATION, SI_MAX_ITERS, SI_END_MODULO, SI_ERR_MODE, SI_QUOTIENT = range(8)
 STATE_LEN = 16
+ABI_VERSION = 3
+SIGNATURE_WORDS = 8
 HSELL_CHUNK = 32   # PGB_HSELL_CHUNK: rounds per chunk of the hsell streams
 
 
@@ -41,7 +43,8 @@ class Hsell(Structure):
                 ("hub_chunks", c_void_p), ("tail_chunks", c_void_p), ("hub_words", c_void_p), ("tail_cols", c_void_p),
                 ("piece_row", c_void_p), ("upd_rows", c_void_p), ("heavy_slices", c_void_p),
                 ("reduce_items", c_void_p),
-                ("block_chunk_begin", c_void_p), ("cta_hub_begin", c_void_p), ("cta_tail_begin", c_void_p)]
+                ("block_chunk_begin", c_void_p), ("cta_hub_begin", c_void_p), ("cta_tail_begin", c_void_p),
+                ("piece_slice", c_void_p)]
 
 
 MAX_PEERS = 16
@@ -54,7 +57,7 @@ class Peers(Structure):
 
 
 class SpanWs(Structure):
-    _fields_ = [("acc", c_void_p), ("cnt", c_void_p), ("partials", c_void_p)]
+    _fields_ = [("acc", c_void_p), ("cnt", c_void_p), ("partials", c_void_p), ("yacc", c_void_p)]
 
 
 _SIGNATURES = {
@@ -65,7 +68,8 @@ _SIGNATURES = {
     "pgb_set_kernel_variant": (c_int, [c_int]),
     "pgb_hsell_max_block_cols": (c_int, [c_int]),
     "pgb_hsell_set_tail_warps": (c_int, [c_int]),
-    "pgb_hsell_count": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "pgb_hsell_count": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_void_p, c_void_p,
+                                c_void_p]),
     "pgb_hsell_fill": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_int32, c_void_p]),
@@ -82,6 +86,9 @@ _SIGNATURES = {
     "pgb_degree_order_workspace_bytes": (c_size_t, [c_int64]),
     "pgb_degree_order": (c_int, [c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "pgb_relabel_coo": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgb_hub_order_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "pgb_hub_order": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_size_t, c_void_p, c_void_p,
+                              c_void_p]),
     "pgb_mergepath_partition": (c_int, [c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "pgb_csr_row_sums": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgb_make_scales": (c_int, [c_int64, c_void_p, c_int, c_void_p, c_void_p]),
@@ -148,7 +155,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.pgb_abi_version() != 2:
+        if handle.pgb_abi_version() != ABI_VERSION:
             raise Exception("libpgb200.so ABI version mismatch")
         variant = os.environ.get("PGB_KERNEL_VARIANT")
         if variant:   # A/B timing aid: 3 = item-stream kernel, 4 = hsell when available (default)

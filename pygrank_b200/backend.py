@@ -21,7 +21,7 @@ import torch
 from . import _capi as C
 from .graph import DeviceGraph, _dev
 
-_config = {"dtype": torch.float64, "relabel": "degree"}
+_config = {"dtype": torch.float64, "relabel": "hub"}
 
 
 def configure(dtype=None, relabel=None):
@@ -31,8 +31,9 @@ def configure(dtype=None, relabel=None):
             raise Exception("dtype must be torch.float32 or torch.float64")
         _config["dtype"] = dtype
     if relabel is not None:
-        if relabel not in ("degree", "none"):
-            raise Exception("relabel must be 'degree' or 'none'")
+        from .graph import RELABELS
+        if relabel not in RELABELS:
+            raise Exception("relabel must be one of " + ", ".join(RELABELS))
         _config["relabel"] = relabel
 
 

@@ -39,7 +39,15 @@ inline int stride_grid(int64_t n, int block) {
     return (int)(want < cap ? want : cap);
 }
 
-int sm_count();
+int sm_count();          // SMs of the CURRENT device
+int current_device();    // cudaGetDevice, clamped to [0, PGB_MAX_DEVICES)
+constexpr int PGB_MAX_DEVICES = 64;
+// Function attributes (opt-in shared memory, carveout) and occupancy are per device: launchers keep one cache
+// slot per device instead of a process-wide static, so a process that drives several GPUs configures each.
+struct PerDeviceInt {
+    int v[PGB_MAX_DEVICES] = {};
+    int &here() { return v[current_device()]; }
+};
 
 // ---- device helpers ------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

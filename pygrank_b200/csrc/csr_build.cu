@@ -111,6 +111,55 @@ __global__ void invert_perm_kernel(int64_t n, const int32_t *__restrict__ perm, 
         iperm[perm[i]] = (int32_t)i;
 }
 
+// Hub-block signature of every row (original labels): bit b (b = 0 most significant of word 0) is set when the
+// row has an entry whose degree RANK (iperm[col]) lies in [b*G, (b+1)*G); ranks >= span set nothing.  One warp
+// per row.  sig is [words][n].
+__global__ void block_signature_kernel(int64_t n, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                       const int32_t *__restrict__ iperm, int32_t G, int64_t span, int words,
+                                       uint64_t *__restrict__ sig) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        uint64_t acc[PGB_SIGNATURE_WORDS];
+#pragma unroll
+        for (int w = 0; w < PGB_SIGNATURE_WORDS; ++w) acc[w] = 0ull;
+        for (int32_t k = indptr[r] + lane; k < indptr[r + 1]; k += 32) {
+            const int32_t c = iperm ? iperm[indices[k]] : indices[k];
+            if (c < span) {
+                const int b = c / G;
+#pragma unroll
+                for (int w = 0; w < PGB_SIGNATURE_WORDS; ++w)
+                    if ((b >> 6) == w) acc[w] |= 1ull << (63 - (b & 63));
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < PGB_SIGNATURE_WORDS; ++w) {
+            if (w < words) {
+                const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)acc[w]);
+                const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(acc[w] >> 32));
+                if (lane == 0) sig[(int64_t)w * n + r] = ((uint64_t)hi << 32) | lo;
+            }
+        }
+    }
+}
+
+// keys of one pass of the signature sort for the current order `ids`: the complemented signature word (rows
+// that touch a block sort first), or (sig == NULL) the region of the node's degree rank
+__global__ void signature_keys_kernel(int64_t n, const int32_t *__restrict__ ids, const uint64_t *__restrict__ sig,
+                                      const int32_t *__restrict__ iperm, int32_t G, int64_t span,
+                                      uint64_t *__restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = ids[i];
+        if (sig) {
+            keys[i] = ~sig[v];
+        } else {
+            const int64_t rank = iperm[v];
+            keys[i] = (uint64_t)((rank < span ? rank : span) / G);
+        }
+    }
+}
+
 __global__ void relabel_kernel(int64_t nnz, const int32_t *__restrict__ iperm, int32_t *__restrict__ row,
                                int32_t *__restrict__ col) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
@@ -362,6 +411,52 @@ int pgb_degree_order(int64_t n, const int32_t *indptr, void *workspace, size_t w
     PGB_LAUNCH_OK("degree_keys_kernel");
     cub::DoubleBuffer<int32_t> dk(deg_a, deg_b), dv(id_a, id_b);
     PGB_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(cub_temp, cub_bytes, dk, dv, n, 0, 32, st));
+    PGB_CUDA_OK(cudaMemcpyAsync(perm, dv.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    invert_perm_kernel<<<stride_grid(n, 256), 256, 0, st>>>(n, perm, iperm);
+    PGB_LAUNCH_OK("invert_perm_kernel");
+    return 0;
+}
+
+size_t pgb_hub_order_workspace_bytes(int64_t n, int32_t words) {
+    size_t t = 0;
+    cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
+    cub::DoubleBuffer<int32_t> dv(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, dk, dv, n);
+    return align256(t + 256) + (size_t)(words + 2) * align256((size_t)n * 8) + 2 * align256((size_t)n * 4);
+}
+
+int pgb_hub_order(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t G, int64_t span, void *workspace,
+                  size_t workspace_bytes, int32_t *perm, int32_t *iperm, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    if (n <= 0) return 0;
+    if (G < 1 || span < 0) return fail("pgb_hub_order: bad block size / span");
+    const int64_t bits = ceil_div(span, G);
+    const int words = (int)ceil_div(bits, 64);
+    if (words > PGB_SIGNATURE_WORDS)
+        return fail("pgb_hub_order: %lld signature bits exceed the %d supported", (long long)bits, 64 * PGB_SIGNATURE_WORDS);
+    if (workspace_bytes < pgb_hub_order_workspace_bytes(n, words)) return fail("pgb_hub_order: workspace too small");
+    char *ws = (char *)workspace;
+    const size_t seg8 = align256((size_t)n * 8), seg4 = align256((size_t)n * 4);
+    uint64_t *sig = (uint64_t *)ws;
+    uint64_t *key_a = (uint64_t *)(ws + (size_t)words * seg8), *key_b = (uint64_t *)(ws + (size_t)(words + 1) * seg8);
+    int32_t *id_a = (int32_t *)(ws + (size_t)(words + 2) * seg8), *id_b = (int32_t *)(ws + (size_t)(words + 2) * seg8 + seg4);
+    void *cub_temp = ws + (size_t)(words + 2) * seg8 + 2 * seg4;
+    size_t cub_bytes = workspace_bytes - ((size_t)(words + 2) * seg8 + 2 * seg4);
+    if (words > 0) {
+        block_signature_kernel<<<stride_grid(n * 32, 256), 256, 0, st>>>(n, indptr, indices, iperm, G, span, words, sig);
+        PGB_LAUNCH_OK("block_signature_kernel");
+    }
+    // LSD passes of a stable sort: degree rank (the incoming perm) < signature words (last word first) < region
+    PGB_CUDA_OK(cudaMemcpyAsync(id_a, perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    cub::DoubleBuffer<int32_t> dv(id_a, id_b);
+    for (int pass = words - 1; pass >= -1; --pass) {
+        cub::DoubleBuffer<uint64_t> dk(key_a, key_b);
+        signature_keys_kernel<<<stride_grid(n, 256), 256, 0, st>>>(n, dv.Current(), pass >= 0 ? sig + (int64_t)pass * n : nullptr,
+                                                                  iperm, G, span, dk.Current());
+        PGB_LAUNCH_OK("signature_keys_kernel");
+        size_t tb = cub_bytes;
+        PGB_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_temp, tb, dk, dv, n, 0, pass >= 0 ? 64 : 32, st));
+    }
     PGB_CUDA_OK(cudaMemcpyAsync(perm, dv.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     invert_perm_kernel<<<stride_grid(n, 256), 256, 0, st>>>(n, perm, iperm);
     PGB_LAUNCH_OK("invert_perm_kernel");

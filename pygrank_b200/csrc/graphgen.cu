@@ -18,17 +18,23 @@ int fail(const char *fmt, ...) {
     return 1;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PGB_MAX_DEVICES) dev = 0;
+    return dev;
+}
+
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-            cached = sms;
+    static PerDeviceInt cached;
+    int &c = cached.here();
+    if (c == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device()) == cudaSuccess && sms > 0)
+            c = sms;
         else
-            cached = 148;
+            c = 148;
     }
-    return cached;
+    return c;
 }
 
 __global__ void rmat_kernel(int scale, int64_t first_edge, int64_t num_edges, uint64_t seed_hash, uint32_t t1,

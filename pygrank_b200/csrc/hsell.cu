@@ -28,6 +28,8 @@
 // check (algorithms/convergence.py:77-101).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "step_common.cuh"
 
 namespace pgb {
@@ -38,7 +40,7 @@ constexpr int HS_SMEM_LIMIT = 232448;   // 227 KB opt-in dynamic shared memory p
 constexpr int UPD_BLOCK = 256;
 constexpr int UPD_AHEAD = 5;   // partial rows per slice requested before the first add
 
-static int g_tail_warps = 6;
+static int g_tail_warps = 5;   // measured with TEX-path tail gathers: 4 -> .586, 5 -> .572, 6 -> .563, 8 -> .585 ms (RMAT-24 fp32, box-to-box +-3 %)
 
 __device__ __forceinline__ unsigned ld_stream_u32(const uint32_t *p) { return __ldcs(p); }
 
@@ -58,7 +60,8 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t *__restrict__ a, in
 
 __global__ void hsell_count_kernel(int64_t n, int64_t n_slices, const int32_t *__restrict__ indptr,
                                    const int32_t *__restrict__ indices, int H, int K, int min_entries,
-                                   int32_t *__restrict__ hub_rounds, int32_t *__restrict__ tail_rounds) {
+                                   float round_cost, int32_t *__restrict__ hub_rounds,
+                                   int32_t *__restrict__ tail_rounds) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -77,8 +80,9 @@ __global__ void hsell_count_kernel(int64_t n, int64_t n_slices, const int32_t *_
             pos = nxt;
             const int ent = __reduce_add_sync(FULL, len);
             const int mx = __reduce_max_sync(FULL, len);
-            const bool use = ent >= min_entries && ent > 0;
-            if (lane == 0) hub_rounds[(int64_t)blk * n_slices + s] = use ? (mx + 1) / 2 : 0;
+            const int rounds = (mx + 1) / 2;
+            const bool use = ent > 0 && (float)ent >= (float)min_entries + round_cost * (float)rounds;
+            if (lane == 0) hub_rounds[(int64_t)blk * n_slices + s] = use ? rounds : 0;
             if (!use) tail_len += len;
         }
         tail_len += e - pos;
@@ -265,14 +269,28 @@ struct GatherParams {
     int tail_warps;
     int tail_batch;        // tail chunks taken per grab of the global queue
     int debug_skip;        // timing experiments only (PGB_HSELL_DEBUG_SKIP): 1 = skip hub chunks, 2 = skip tail chunks
+    cudaTextureObject_t ztex;   // linear texture over z (TEX kernels): tail gathers go through the TEX pipe
 };
+
+// A piece's 32 lane sums leave the gather kernel either as one 128-byte partial row (deterministic path: the
+// update pass adds the rows of a slice in a fixed order) or — ACCUM — as one coalesced 128-byte RED.ADD into the
+// slice's row of an accumulator y kept in L2.  Measured on B200 (scripts/red_rate.cu): a coalesced fp32 RED costs
+// what the store costs (2.1 M rows in 0.059 ms either way, hot rows included), fp64 1.5x; and the update pass then
+// streams y once instead of chasing 4 partial rows per slice through upd_rows, with no reduce kernel in between.
+template <bool ACCUM, typename T>
+__device__ __forceinline__ void flush_piece(T *__restrict__ dst, int row, int lane, T v) {
+    if (ACCUM)
+        atomicAdd(dst + (int64_t)row * 32 + lane, v);
+    else
+        dst[(int64_t)row * 32 + lane] = v;
+}
 
 constexpr int CH = PGB_HSELL_CHUNK;   // rounds per chunk
 constexpr int BATCH = 8;              // rounds loaded ahead per lane
 static_assert(CH == 32 && CH % BATCH == 0, "the end mask of a chunk is one 32-bit word");
 
 // One chunk of the hub stream: 32 rounds, two shared-memory gathers per lane and round.
-template <typename T>
+template <typename T, bool ACCUM>
 __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, int64_t chunk, uint32_t p_first,
                                           uint32_t endmask, const int32_t *__restrict__ piece_row, const T *s_z,
                                           T *__restrict__ partials, int lane) {
@@ -304,7 +322,7 @@ __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, in
                 a0 += s_z[w[u] & 0xffffu];
                 a1 += s_z[w[u] >> 16];
                 if ((m8 >> u) & 1u) {
-                    partials[(int64_t)__shfl_sync(0xffffffffu, my_row, p) * 32 + lane] = a0 + a1;
+                    flush_piece<ACCUM>(partials, __shfl_sync(0xffffffffu, my_row, p), lane, a0 + a1);
                     ++p;
                     a0 = a1 = (T)0;
                 }
@@ -315,11 +333,22 @@ __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, in
     }
 }
 
+// z[c] through the texture unit.  Measured on B200 (scripts/gather_paths.cu): a scattered 4-byte gather costs
+// about one L1TEX cycle per lane on either input pipe, but the TEX pipe and the LSU pipe (which also carries
+// every shared-memory gather and the index streams) run side by side — so the tail's L2 gathers stop competing
+// with the hub path for LSU wavefronts.
+__device__ __forceinline__ float tex_fetch(cudaTextureObject_t t, int c, float) { return tex1Dfetch<float>(t, c); }
+__device__ __forceinline__ double tex_fetch(cudaTextureObject_t t, int c, double) {
+    const int2 v = tex1Dfetch<int2>(t, c);
+    return __hiloint2double(v.y, v.x);
+}
+
 // One chunk of the tail stream: 32 rounds, one L2 gather per lane and round (padding lanes are off).
-template <typename T>
+template <typename T, bool TEX, bool ACCUM>
 __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int64_t chunk, uint32_t p_first,
                                            uint32_t endmask, const int32_t *__restrict__ piece_row,
-                                           const T *__restrict__ z, T *__restrict__ partials, int lane) {
+                                           const T *__restrict__ z, cudaTextureObject_t ztex,
+                                           T *__restrict__ partials, int lane) {
     const int32_t *d = cols + chunk * (CH * 32) + lane;
     endmask |= 0x80000000u;
     const int my_row = (lane < __popc(endmask)) ? __ldg(piece_row + p_first + lane) : 0;
@@ -332,7 +361,12 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
     for (int bt = 0; bt < CH / BATCH; ++bt) {
         T x[BATCH];
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) x[u] = (c[u] >= 0) ? __ldg(z + c[u]) : (T)0;
+        for (int u = 0; u < BATCH; ++u) {
+            if (TEX)
+                x[u] = (c[u] >= 0) ? tex_fetch(ztex, c[u], (T)0) : (T)0;
+            else
+                x[u] = (c[u] >= 0) ? __ldg(z + c[u]) : (T)0;
+        }
         if (bt + 1 < CH / BATCH) {
 #pragma unroll
             for (int u = 0; u < BATCH; ++u) nx[u] = ld_stream(d + ((bt + 1) * BATCH + u) * 32);
@@ -349,7 +383,7 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
             for (int u = 0; u < BATCH; ++u) {
                 a0 += x[u];
                 if ((m8 >> u) & 1u) {
-                    partials[(int64_t)__shfl_sync(0xffffffffu, my_row, p) * 32 + lane] = a0 + a1;
+                    flush_piece<ACCUM>(partials, __shfl_sync(0xffffffffu, my_row, p), lane, a0 + a1);
                     ++p;
                     a0 = a1 = (T)0;
                 }
@@ -360,7 +394,7 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
     }
 }
 
-template <typename T>
+template <typename T, bool TEX, bool ACCUM>
 __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const GatherParams G) {
     extern __shared__ __align__(16) unsigned char hs_smem[];
     T *s_z = reinterpret_cast<T *>(hs_smem);   // [block_cols + 1]; the last entry is the padding target (0)
@@ -371,7 +405,8 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const T *__restrict__ z = (const T *)G.z;
-    T *__restrict__ partials = (T *)G.partials;
+    T *__restrict__ partials = (T *)G.partials;   // partial rows, or (ACCUM) the accumulator y [n_slices + 1][32]
+    const int32_t *__restrict__ piece_dst = ACCUM ? h.piece_slice : h.piece_row;
     const int cta = blockIdx.x;
     const int hub_lo = h.cta_hub_begin[cta], hub_hi = h.cta_hub_begin[cta + 1];
     // hub chunks need this CTA's shared-memory block, so they are dealt statically (block-major ranges);
@@ -389,7 +424,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
         const int u1 = (u0 + TB < tail_hi) ? u0 + TB : tail_hi;
         for (int u = u0; u < u1; ++u) {
             const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.tail_chunks) + u);
-            tail_chunk<T>(h.tail_cols, u, d.x, d.y, h.piece_row, z, partials, lane);
+            tail_chunk<T, TEX, ACCUM>(h.tail_cols, u, d.x, d.y, piece_dst, z, G.ztex, partials, lane);
         }
     };
 
@@ -448,7 +483,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
             if (kind == 1) {
                 if (!(G.debug_skip & 1)) {
                     const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.hub_chunks) + u);
-                    hub_chunk<T>(h.hub_words, u, d.x, d.y, h.piece_row, s_z, partials, lane);
+                    hub_chunk<T, ACCUM>(h.hub_words, u, d.x, d.y, piece_dst, s_z, partials, lane);
                 }
             } else {
                 run_tail(u);
@@ -616,16 +651,129 @@ __global__ void __launch_bounds__(UPD_BLOCK, (sizeof(T) == 8 ? 2 : 3) * (UPD_GRO
     if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
 }
 
+// Kernel B, accumulate mode: the gathered sums sit complete in y (one value per row), so the update pass is a pure
+// stream — y (read, then zeroed for the next step), the row pointers, z, q, c in, z' out — four rows per thread with
+// all their loads requested together, then the fused filter update and the convergence reduction as above.
+constexpr int UPA_BLOCK = 256;
+constexpr int UPA_ROWS = 4;
+template <typename T, int MODE, bool SYMDEG>
+__global__ void __launch_bounds__(UPA_BLOCK) hsell_update_accum_kernel(const StepParams P, T *__restrict__ y) {
+    __shared__ double s_red[32];
+    if (MODE != MODE_CONV) {
+        if (P.si[PGB_SI_STOP] != PGB_RUNNING) return;
+    }
+    RowUpdate<T, MODE, SYMDEG> update(P);
+    using Loaded = typename RowUpdate<T, MODE, SYMDEG>::Loaded;
+    update.batch_sums = true;
+    const int64_t n = P.n;
+    const int64_t stride = (int64_t)gridDim.x * UPA_BLOCK;
+    for (int64_t base = blockIdx.x * (int64_t)UPA_BLOCK + threadIdx.x; base < n; base += stride * UPA_ROWS) {
+        T acc[UPA_ROWS];
+        Loaded L[UPA_ROWS];
+        int ip0[UPA_ROWS], ip1[UPA_ROWS];
+#pragma unroll
+        for (int k = 0; k < UPA_ROWS; ++k) {
+            const int64_t row = base + k * stride;
+            acc[k] = (T)0;
+            ip0[k] = ip1[k] = 0;
+            if (row < n) {
+                acc[k] = ld_stream(y + row);
+                if (SYMDEG && MODE != MODE_CONV) {
+                    ip0[k] = P.indptr[row];
+                    ip1[k] = P.indptr[row + 1];
+                }
+                L[k] = update.load(row, 0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UPA_ROWS; ++k) {
+            const int64_t row = base + k * stride;
+            if (row < n) {
+                y[row] = (T)0;
+                update.set_degree(L[k], ip1[k] - ip0[k]);
+                update.apply(row, acc[k], L[k]);
+            }
+        }
+        update.flush_batch();
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0 && P.span_cnt) P.span_cnt[0] = 0u;   // tail queue of the next gather
+    if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
+}
+
+// Linear texture objects over gather vectors, keyed by (device, address, bytes): the filters alternate two z
+// buffers per solve and torch's allocator hands the same blocks out again, so a small LRU table suffices.
+// Returns 0 when the vector cannot be a linear texture (alignment, size): the caller then gathers with LDG.
+struct TexEntry {
+    const void *p;
+    size_t bytes;
+    int dev, dtype;
+    cudaTextureObject_t tex;
+    uint64_t stamp;
+};
+static TexEntry g_tex[64];
+static uint64_t g_tex_stamp = 0;
+static std::mutex g_tex_mutex;
+
+static cudaTextureObject_t texture_for(const void *z, size_t elems, int dtype) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *e = getenv("PGB_HSELL_TEX");
+        enabled = e ? atoi(e) : 1;
+    }
+    if (!enabled || !z || elems == 0) return 0;
+    const size_t bytes = elems * (dtype == PGB_F32 ? 4 : 8);
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(g_tex_mutex);
+    int victim = 0;
+    for (int i = 0; i < 64; ++i) {
+        TexEntry &e = g_tex[i];
+        if (e.tex && e.p == z && e.bytes == bytes && e.dev == dev && e.dtype == dtype) {
+            e.stamp = ++g_tex_stamp;
+            return e.tex;
+        }
+        if (g_tex[i].stamp < g_tex[victim].stamp) victim = i;
+    }
+    static PerDeviceInt max_linear;
+    int &lim = max_linear.here();
+    if (lim == 0 && cudaDeviceGetAttribute(&lim, cudaDevAttrMaxTexture1DLinearWidth, dev) != cudaSuccess) lim = 1 << 27;
+    if (elems > (size_t)lim || ((uintptr_t)z & 511u)) return 0;
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = const_cast<void *>(z);
+    rd.res.linear.desc = dtype == PGB_F32 ? cudaCreateChannelDesc<float>() : cudaCreateChannelDesc<int2>();
+    rd.res.linear.sizeInBytes = bytes;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t t = 0;
+    if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    TexEntry &v = g_tex[victim];
+    if (v.tex) cudaDestroyTextureObject(v.tex);
+    v = TexEntry{z, bytes, dev, dtype, t, ++g_tex_stamp};
+    return t;
+}
+
 template <typename T>
-static int launch_gather(const pgb_hsell *h, const void *z, void *partials, const int32_t *stop, uint32_t *tail_queue,
-                         cudaStream_t st) {
-    static bool configured = false;
+static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool accum, const int32_t *stop,
+                         uint32_t *tail_queue, cudaStream_t st) {
+    static PerDeviceInt configured_on;
     const size_t smem = ((size_t)h->block_cols + 1) * sizeof(T);
     if (smem > (size_t)HS_SMEM_LIMIT - 64) return fail("hsell: block_cols=%d does not fit in shared memory", h->block_cols);
+    int &configured = configured_on.here();
     if (!configured) {
-        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HS_SMEM_LIMIT - 64));
-        configured = true;
+        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HS_SMEM_LIMIT - 64));
+        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HS_SMEM_LIMIT - 64));
+        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HS_SMEM_LIMIT - 64));
+        configured = 1;
     }
     GatherParams G;
     G.h = *h;
@@ -647,7 +795,16 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, cons
         if (tail_batch < 1) tail_batch = 1;
     }
     G.tail_batch = tail_batch;
-    hsell_gather_kernel<T><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
+    G.ztex = h->n_tail_chunks > 0 ? texture_for(z, (size_t)h->seg_len * (size_t)h->n_segments, sizeof(T) == 4 ? PGB_F32 : PGB_F64) : 0;
+    if (accum && !h->piece_slice) return fail("hsell: accumulate mode needs pgb_hsell.piece_slice");
+    if (G.ztex && accum)
+        hsell_gather_kernel<T, true, true><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
+    else if (G.ztex)
+        hsell_gather_kernel<T, true, false><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
+    else if (accum)
+        hsell_gather_kernel<T, false, true><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
+    else
+        hsell_gather_kernel<T, false, false><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
     PGB_LAUNCH_OK("hsell_gather_kernel");
     return 0;
 }
@@ -667,7 +824,8 @@ template <typename T, int MODE, bool SYMDEG, int GROUP>
 static int launch_update_g(const StepParams &P, const pgb_hsell *h, const void *partials, cudaStream_t st) {
     int64_t want = ceil_div(h->n_slices, UPD_WARPS * GROUP);
     if (want < h->n_heavy) want = h->n_heavy;
-    static int ctas = 0;
+    static PerDeviceInt ctas_on;
+    int &ctas = ctas_on.here();
     if (ctas == 0) {
         int v = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_kernel<T, MODE, SYMDEG, GROUP>, UPD_BLOCK, 0) != cudaSuccess || v < 1)
@@ -694,20 +852,53 @@ static int launch_update(const StepParams &P, const pgb_hsell *h, const void *pa
                       : launch_update_g<T, MODE, SYMDEG, 4>(P, h, partials, st);
 }
 
+template <typename T, int MODE, bool SYMDEG>
+static int launch_update_accum(const StepParams &P, void *yacc, cudaStream_t st) {
+    static PerDeviceInt ctas_on;
+    int &ctas = ctas_on.here();
+    if (ctas == 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_accum_kernel<T, MODE, SYMDEG>, UPA_BLOCK, 0) != cudaSuccess || v < 1)
+            v = 4;
+        ctas = v;
+    }
+    int64_t want = ceil_div(P.n, (int64_t)UPA_BLOCK * UPA_ROWS);
+    const int64_t cap = (int64_t)sm_count() * ctas;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    hsell_update_accum_kernel<T, MODE, SYMDEG><<<(int)want, UPA_BLOCK, 0, st>>>(P, (T *)yacc);
+    PGB_LAUNCH_OK("hsell_update_accum_kernel");
+    return 0;
+}
+
+template <typename T, int MODE>
+static int hsell_step_accum(const StepParams &P, const pgb_hsell *h, bool symdeg, const int32_t *stop, cudaStream_t st) {
+    if (launch_gather<T>(h, P.zin, P.yacc, true, stop, P.span_cnt, st)) return 1;
+    return symdeg ? launch_update_accum<T, MODE, true>(P, P.yacc, st) : launch_update_accum<T, MODE, false>(P, P.yacc, st);
+}
+
 // One fused step on the hsell form: gather (kernel A) + update (kernel B).  Called from spmv_fused.cu.
 template <int MODE>
 int hsell_step(const StepParams &P, const pgb_hsell *h, void *partials, int dtype, bool symdeg, cudaStream_t st) {
+    if (P.yacc) {   // accumulate mode: pieces are RED.ADDed into y, the update pass streams y (two launches per step)
+        if (!P.span_cnt) return fail("hsell: the workspace has no counter array");
+        if (h->n_rows != P.n) return fail("hsell: form built for %lld rows, graph has %lld", (long long)h->n_rows, (long long)P.n);
+        const int32_t *stop_a = (MODE == MODE_CONV) ? nullptr : P.si + PGB_SI_STOP;
+        if (dtype == PGB_F32) return hsell_step_accum<float, MODE>(P, h, symdeg, stop_a, st);
+        if (dtype == PGB_F64) return hsell_step_accum<double, MODE>(P, h, symdeg, stop_a, st);
+        return fail("unknown dtype %d", dtype);
+    }
     if (!partials) return fail("hsell: the workspace has no partials buffer");
     if (!P.span_cnt) return fail("hsell: the workspace has no counter array");
     if (h->n_rows != P.n) return fail("hsell: form built for %lld rows, graph has %lld", (long long)h->n_rows, (long long)P.n);
     const int32_t *stop = (MODE == MODE_CONV) ? nullptr : P.si + PGB_SI_STOP;
     if (dtype == PGB_F32) {
-        if (launch_gather<float>(h, P.zin, partials, stop, P.span_cnt, st)) return 1;
+        if (launch_gather<float>(h, P.zin, partials, false, stop, P.span_cnt, st)) return 1;
         if (launch_reduce<float>(h, partials, stop, st)) return 1;
         return symdeg ? launch_update<float, MODE, true>(P, h, partials, st)
                       : launch_update<float, MODE, false>(P, h, partials, st);
     } else if (dtype == PGB_F64) {
-        if (launch_gather<double>(h, P.zin, partials, stop, P.span_cnt, st)) return 1;
+        if (launch_gather<double>(h, P.zin, partials, false, stop, P.span_cnt, st)) return 1;
         if (launch_reduce<double>(h, partials, stop, st)) return 1;
         return symdeg ? launch_update<double, MODE, true>(P, h, partials, st)
                       : launch_update<double, MODE, false>(P, h, partials, st);
@@ -740,14 +931,14 @@ int pgb_hsell_set_tail_warps(int warps) {
 }
 
 int pgb_hsell_count(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
-                    int32_t min_entries, int32_t *hub_rounds, int32_t *tail_rounds, void *stream) {
+                    int32_t min_entries, double round_cost, int32_t *hub_rounds, int32_t *tail_rounds, void *stream) {
     if (n <= 0) return 0;
     if (block_cols < 1 || block_cols > 65535) return fail("pgb_hsell_count: block_cols must be in 1..65535");
     if (n_blocks < 0 || (int64_t)n_blocks * block_cols >= (1ll << 31)) return fail("pgb_hsell_count: bad n_blocks");
     const int64_t n_slices = ceil_div(n, 32);
     const int grid = stride_grid(n_slices * 32, 256);
     hsell_count_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n_slices, indptr, indices, block_cols, n_blocks,
-                                                            min_entries, hub_rounds, tail_rounds);
+                                                            min_entries, (float)round_cost, hub_rounds, tail_rounds);
     PGB_LAUNCH_OK("hsell_count_kernel");
     return 0;
 }

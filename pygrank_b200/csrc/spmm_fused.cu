@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(BBLOCK, 3) panel_kernel(const BatchParams P) {
 
 template <typename T, int PB, bool SYMDEG>
 static int launch_panel(const BatchParams &P, cudaStream_t st) {
-    static int ctas = 0;
+    static PerDeviceInt ctas_on;
+    int &ctas = ctas_on.here();
     if (ctas == 0) {
         int v = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, panel_kernel<T, PB, SYMDEG>, BBLOCK, 0) != cudaSuccess ||

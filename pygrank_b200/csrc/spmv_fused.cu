@@ -331,7 +331,8 @@ static int g_kernel_variant = 4;  // 3 = warp tiles over the item stream, 4 = hs
 
 template <typename T, bool WEIGHTED, int MODE, bool SYMDEG>
 static int launch_tiles(const StepParams &P, cudaStream_t st) {
-    static int ctas_per_sm = 0;
+    static PerDeviceInt ctas_on;
+    int &ctas_per_sm = ctas_on.here();
     if (!P.istream || (WEIGHTED && !P.vstream))
         return fail("the item-stream kernel needs pgb_csr.istream%s (pgb_build_item_stream)", WEIGHTED ? "/vstream" : "");
     if (ctas_per_sm == 0) {
@@ -466,6 +467,7 @@ int pgb_spmv(const pgb_csr *g, int dtype, const void *z, const void *rscale, con
     P.span_acc = ws.acc;
     P.span_cnt = ws.cnt;
     P.partials = ws.partials;
+    P.yacc = ws.yacc;
     return dispatch<MODE_CONV>(P, dtype, false, as_stream(stream));
 }
 
@@ -493,6 +495,7 @@ int pgb_affine_steps(const pgb_csr *g, int dtype, double alpha, const void *w, c
     P.span_acc = ws.acc;
     P.span_cnt = ws.cnt;
     P.partials = ws.partials;
+    P.yacc = ws.yacc;
     P.finalize = finalize;
     void *buf[2] = {zbuf0, zbuf1};
     for (int j = 0; j < num_launches; ++j) {
@@ -526,6 +529,7 @@ int pgb_poly_steps(const pgb_csr *g, int dtype, const void *w, const void *sq, c
     P.span_acc = ws.acc;
     P.span_cnt = ws.cnt;
     P.partials = ws.partials;
+    P.yacc = ws.yacc;
     P.finalize = finalize;
     void *buf[2] = {zbuf0, zbuf1};
     for (int j = 0; j < num_launches; ++j) {
@@ -563,6 +567,7 @@ int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *
     P.span_acc = ws.acc;
     P.span_cnt = ws.cnt;
     P.partials = ws.partials;
+    P.yacc = ws.yacc;
     P.finalize = 0;
     void *buf[2] = {zbuf0, zbuf1};
     P.zin = buf[(step - 1) & 1];

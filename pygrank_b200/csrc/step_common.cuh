@@ -32,6 +32,7 @@ struct StepParams {
     int finalize;
     const pgb_hsell *hsell;  // host pointer: hub-blocked sliced-ELL form of the same graph (or NULL)
     void *partials;          // its per-filter workspace
+    void *yacc;              // accumulate mode: y [n_slices + 1][32], zero between steps (or NULL: partial rows)
     // row-partitioned multi-GPU with the exchange fused into the step (pgb_affine_step_peer)
     int n_peers, peer_rank;
     void *peer_zout[PGB_MAX_PEERS];

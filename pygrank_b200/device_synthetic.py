@@ -32,14 +32,14 @@ def ba_edges_device(n: int, m: int, seed: int = 1, device=None):
 
 
 def rmat_graph_device(scale: int, edge_factor: int = 16, seed: int = 1, normalization: str = "symmetric",
-                      relabel: str = "degree", device=None) -> DeviceGraph:
+                      relabel: str = "hub", device=None) -> DeviceGraph:
     """Undirected RMAT graph (symmetrised, self loops dropped, duplicates collapsed to weight 1)."""
     src, dst = rmat_edges_device(scale, edge_factor, seed, device=device)
     return DeviceGraph.from_edges(1 << scale, src, dst, directed=False, drop_self_loops=True, binary=True,
                                   normalization=normalization, relabel=relabel)
 
 
-def ba_graph_device(n: int, m: int, seed: int = 1, normalization: str = "symmetric", relabel: str = "degree",
+def ba_graph_device(n: int, m: int, seed: int = 1, normalization: str = "symmetric", relabel: str = "hub",
                     device=None) -> DeviceGraph:
     src, dst = ba_edges_device(n, m, seed, device=device)
     return DeviceGraph.from_edges(n, src, dst, directed=False, drop_self_loops=True, binary=True,

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import time
 from typing import Optional
 
@@ -272,7 +273,10 @@ class DistGraph:
                 mask = None
                 # measured: at 8 ranks the masks cut the stores to a fraction and lift 2131 -> 2470 GTEPS; at 2 ranks
                 # almost every row is read by the other rank and the mask only costs (1231 -> 1158)
-                if not mc and self.world >= 4 and os.environ.get("PGB_PEER_MASK", "1") != "0":
+                # PGB_PEER_MASK: unset = masks from 4 ranks up, 1 = always (parity tests exercise the mask path
+                # on 2 GPUs), 0 = never
+                want_mask = os.environ.get("PGB_PEER_MASK", "")
+                if not mc and (want_mask == "1" or (want_mask != "0" and self.world >= 4)):
                     mask = self.reader_mask(dtype)
                 peers = []
                 for parity in (0, 1):
@@ -340,6 +344,7 @@ class DistPageRank:
                  chunk: int = 4):
         self.alpha, self.tol, self.max_iters, self.end_modulo = alpha, tol, int(max_iters), int(end_modulo)
         self.error_type, self.use_quotient, self.dtype, self.chunk = error_type, use_quotient, dtype, int(chunk)
+        self.poison = os.environ.get("PGB_PEER_POISON", "0") == "1"   # NaN-fill the exchanged buffers before a solve
         self.iteration = 0
         self.elapsed_time = None
 
@@ -398,6 +403,10 @@ class DistPageRank:
         else:
             zfull = [torch.empty(g.n_global, dtype=dtype, device=dev), torch.empty(g.n_global, dtype=dtype, device=dev)]
         q = torch.empty(n_loc, dtype=dtype, device=dev)
+        if peer is not None and self.poison:
+            # parity runs: every entry a peer fails to deliver (reader masks leave unread entries alone) is a NaN
+            peer["z"].fill_(float("nan"))
+            peer["hz"].barrier(channel=1)
         if peer is not None:
             # start vector straight into every rank's buffer 0 (no all-gather); the barrier orders it before step 1
             C.check(lib.pgb_affine_init_peer(n_loc, code, C.ptr(p), None, C.ptr(sq), C.ptr(cvec), 1 - self.alpha, None,
@@ -494,8 +503,12 @@ def propagate_sharded(alg, graph, features: torch.Tensor, gather: bool = True, g
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     B = int(features.shape[1])
     mine = column_shard(B, rank, world)
-    local = alg.propagate(graph, features[:, mine.start:mine.stop].contiguous()) if len(mine) else \
-        features.new_zeros((features.shape[0], 0))
+    if len(mine):
+        local = alg.propagate(graph, features[:, mine.start:mine.stop].contiguous())
+    else:   # an empty shard still takes part in the gather: same dtype and device as every other rank's block
+        view = getattr(graph, "out_view", None)
+        local = torch.zeros((features.shape[0], 0), dtype=getattr(alg, "dtype", features.dtype),
+                            device=view.indptr.device if view is not None else features.device)
     its = list(getattr(alg.convergence, "iterations", [])) if len(mine) else []
     if not gather:
         return local, its

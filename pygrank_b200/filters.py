@@ -114,7 +114,7 @@ class GraphFilter:
     def __init__(self, preprocessor=None, convergence=None, preserve_norm: bool = True,
                  normalization: str = "auto", renormalize=False, assume_immutability: bool = False,
                  tol: Optional[float] = 1.E-6, error_type="mabs", max_iters: int = 100, end_modulo: int = 1,
-                 dtype: torch.dtype = torch.float64, relabel: str = "degree", chunk: int = 8):
+                 dtype: torch.dtype = torch.float64, relabel: str = "hub", chunk: int = 8):
         self.preprocessor = preprocessor if preprocessor is not None else device_preprocessor(
             normalization=normalization, renormalize=renormalize, assume_immutability=assume_immutability,
             relabel=relabel)
@@ -122,6 +122,7 @@ class GraphFilter:
             tol=tol, error_type=error_type, max_iters=max_iters, end_modulo=end_modulo)
         self.preserve_norm = preserve_norm
         self.dtype = dtype
+        self.relabel = relabel
         self.chunk = int(chunk)
 
     # -- public API -------------------------------------------------------------------------
@@ -140,9 +141,7 @@ class GraphFilter:
     def rank(self, graph=None, personalization=None, warm_start=None, graph_dropout: float = 0, **kwargs) -> RankResult:
         if graph is None and isinstance(personalization, RankResult):
             graph = personalization.graph
-        g = self.preprocessor(graph)
-        if not isinstance(g, DeviceGraph):
-            g = as_device_graph(g)
+        g = self._device_graph(graph)
         if graph_dropout != 0:
             raise Exception("graph_dropout with the fused filters is not supported; use the backend plugin path")
         p, norm = _personalization(g, personalization, self.dtype)
@@ -165,9 +164,7 @@ class GraphFilter:
         """``NodeRanking.propagate`` (signals.py:225-226): one rank per feature column.  Filters
         with a batched kernel (``_run_batched``) advance a panel of columns per pass over the CSR;
         the others run column by column like the reference."""
-        g = self.preprocessor(graph)
-        if not isinstance(g, DeviceGraph):
-            g = as_device_graph(g)
+        g = self._device_graph(graph)
         cols = features if isinstance(features, torch.Tensor) else torch.as_tensor(np.asarray(features))
         if cols.dim() != 2 or cols.shape[0] != g.n:
             raise Exception("propagate expects a features matrix with one row per node")
@@ -182,6 +179,31 @@ class GraphFilter:
 
     def _can_batch(self, g, *args, **kwargs) -> bool:
         return False
+
+    def _device_graph(self, graph) -> DeviceGraph:
+        """The preprocessor's output as a DeviceGraph.  A custom preprocessor that returns a host matrix (the
+        reference's ``pg.preprocessor`` under numpy, a callable normalisation, an ``Adjacency`` around a scipy
+        matrix) has ALREADY normalised it (preprocessing.py:104-145): it is uploaded as is, like
+        ``scipy_sparse_to_backend`` does, never normalised a second time."""
+        g = self.preprocessor(graph)
+        if isinstance(g, DeviceGraph):
+            pass
+        elif isinstance(getattr(g, "array", None), DeviceGraph):
+            g = g.array
+        else:
+            import scipy.sparse as sp
+            M = getattr(g, "array", g)
+            if not sp.issparse(M):
+                raise Exception("the preprocessor returned " + str(type(g)) + ": the fused filters need a DeviceGraph "
+                                "(pygrank_b200.preprocessor) or an already normalised scipy matrix")
+            g = DeviceGraph.from_scipy(M, directed=True, normalization="none", relabel=self.relabel,
+                                       node2id=getattr(g, "_pygrank_node2id", None))
+        if g.normalization == "laplacian":
+            # the fused steps iterate on D^-1/2 A D^-1/2; the I - M of preprocessing.py:122 is only applied by
+            # DeviceGraph.conv, i.e. on the backend plugin route
+            raise Exception("normalization='laplacian' is not fused; run the filter through the b200 backend plugin "
+                            "(pg.PageRank under pg.Backend('b200')), whose conv applies I - M")
+        return g
 
     # -- machinery shared by the subclasses ---------------------------------------------------
     def _new_state(self, g: DeviceGraph, norm: float, alpha_s: float, quotient: bool):

@@ -74,6 +74,11 @@ def _env_int(name: str, default: int) -> int:
     return int(v) if v not in (None, "") else default
 
 
+def _env_float(name: str, default: float) -> float:
+    v = os.environ.get(name)
+    return float(v) if v not in (None, "") else default
+
+
 def hsell_config() -> dict:
     """Knobs of the hub-blocked sliced-ELL builder (environment overrides are for tests/experiments).
     block_cols 0 = 128 KB of the gather vector per block: measured best on B200 — the rest of the SM's
@@ -84,8 +89,12 @@ def hsell_config() -> dict:
         "block_cols": _env_int("PGB_HSELL_BLOCK_COLS", 0),
         "max_blocks": _env_int("PGB_HSELL_BLOCKS", 0),
         "min_entries": _env_int("PGB_HSELL_MIN_ENTRIES", 32),
+        "round_cost": _env_float("PGB_HSELL_ROUND_COST", 0.0),
         "heavy_parts": min(max(_env_int("PGB_HSELL_HEAVY_PARTS", 32), 1), 32),
         "bank_order": _env_int("PGB_HSELL_BANK_ORDER", 1) != 0,
+        # 1: pieces are RED.ADDed into one accumulator row per slice and the update pass streams it (fast path);
+        # 0: partial rows added in a fixed order (bit-reproducible runs; PGB_DETERMINISTIC=1 selects it too)
+        "accumulate": _env_int("PGB_HSELL_ACCUM", 1) != 0 and _env_int("PGB_DETERMINISTIC", 0) == 0,
     }
 
 
@@ -110,6 +119,19 @@ def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional
     if n_segments > 1 and K * Hs > seg_len:
         K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail
     return H, K
+
+
+RELABELS = ("hub", "degree", "none")
+
+
+def hub_signature_shape(n: int):
+    """(G, span) of the hub-signature order: regions of G degree ranks (the narrower of the two dtypes' hub
+    blocks, so the membership of BOTH forms' blocks survives the reordering) up to the wider hub span."""
+    H32, K32 = hsell_shape(torch.float32, 1, n)
+    H64, K64 = hsell_shape(torch.float64, 1, n)
+    G = min(H32, H64)
+    span = min(max(H32 * K32, H64 * K64), -(-n // G) * G)
+    return G, span
 
 
 def stream_layout(rounds: torch.Tensor, base: int, chunk: int = C.HSELL_CHUNK):
@@ -226,7 +248,7 @@ class HsellForm:
         hub_rounds = torch.zeros(max(K * S, 1), dtype=torch.int32, device=dev)
         tail_rounds = torch.zeros(max(S, 1), dtype=torch.int32, device=dev)
         C.check(lib.pgb_hsell_count(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, cfg["min_entries"],
-                                    C.ptr(hub_rounds), C.ptr(tail_rounds), st))
+                                    float(cfg["round_cost"]), C.ptr(hub_rounds), C.ptr(tail_rounds), st))
 
         hr = hub_rounds[:K * S].to(i64).view(K, S) if K > 0 else torch.zeros((0, S), dtype=i64, device=dev)
         lay = hsell_layout(hr, tail_rounds[:S].to(i64), cfg["heavy_parts"])
@@ -253,6 +275,10 @@ class HsellForm:
                                    C.ptr(self.tail_cols), C.ptr(self.piece_row), C.ptr(scratch),
                                    32 if dtype == torch.float32 else 16, st))
         del scratch
+        # slice of every piece (accumulate mode): first-level rows are slice-major, padding pieces -> row n_slices
+        ps = torch.searchsorted(lay["slice_ptr"].to(i64), self.piece_row.to(i64), right=True) - 1
+        self.piece_slice = torch.where(self.piece_row.to(i64) >= n_rows1, torch.full_like(ps, S), ps).to(torch.int32)
+        del ps
         self.heavy_slices = torch.nonzero(upd_count > heavy_parts).reshape(-1).to(torch.int32)
         n_heavy = int(self.heavy_slices.numel())
         if n_heavy == 0:
@@ -279,7 +305,7 @@ class HsellForm:
                               C.ptr(self.hub_words), C.ptr(self.tail_cols), C.ptr(self.piece_row),
                               C.ptr(self.upd_rows), C.ptr(self.heavy_slices), C.ptr(self.reduce_items),
                               C.ptr(self.block_chunk_begin),
-                              C.ptr(self.cta_hub_begin), C.ptr(self.cta_tail_begin))
+                              C.ptr(self.cta_hub_begin), C.ptr(self.cta_tail_begin), C.ptr(self.piece_slice))
 
     def nbytes(self) -> int:
         return sum(int(t.numel()) * t.element_size() for t in (self.hub_chunks, self.tail_chunks, self.hub_words,
@@ -362,6 +388,8 @@ class CsrView:
         """Kernels one fused step launches (bench.py counts its own launches): gather + update on the hsell
         form, plus the second-level reduction when some slice needs it; one on the item stream."""
         form = self._hsell.get(dtype) if hsell else None
+        if form is not None and hsell_config()["accumulate"]:
+            return 2
         return 1 if form is None else (3 if form.n_reduce else 2)
 
     def new_span_ws(self, dtype: Optional[torch.dtype] = None):
@@ -371,8 +399,12 @@ class CsrView:
         acc = torch.zeros(max(self.n_tiles, 1), dtype=torch.float64, device=dev)
         cnt = torch.zeros(max(self.n_tiles, 1), dtype=torch.int32, device=dev)
         form = self.hsell(dtype) if dtype is not None else None
-        partials = torch.empty(max(form.n_partials, 1) * 32, dtype=dtype, device=dev) if form is not None else None
-        return (acc, cnt, partials)
+        partials = yacc = None
+        if form is not None and hsell_config()["accumulate"]:
+            yacc = torch.zeros((form.n_slices + 1) * 32, dtype=dtype, device=dev)
+        elif form is not None:
+            partials = torch.empty(max(form.n_partials, 1) * 32, dtype=dtype, device=dev)
+        return (acc, cnt, partials, yacc)
 
     def span_ws(self, dtype: Optional[torch.dtype] = None):
         if self._ws is None:
@@ -393,7 +425,8 @@ class CsrView:
 
 
 def span_struct(ws) -> C.SpanWs:
-    return C.SpanWs(C.ptr(ws[0]), C.ptr(ws[1]), C.ptr(ws[2]) if len(ws) > 2 else None)
+    return C.SpanWs(C.ptr(ws[0]), C.ptr(ws[1]), C.ptr(ws[2]) if len(ws) > 2 else None,
+                    C.ptr(ws[3]) if len(ws) > 3 else None)
 
 
 class IdentityNodeMap:
@@ -470,7 +503,7 @@ class DeviceGraph:
     def from_edges(n: int, src: torch.Tensor, dst: torch.Tensor, weights: Optional[torch.Tensor] = None,
                    directed: bool = False, symmetrize: Optional[bool] = None, drop_self_loops: bool = False,
                    binary: bool = False, normalization: str = "auto", renormalize=False,
-                   relabel: str = "degree", node2id=None) -> "DeviceGraph":
+                   relabel: str = "hub", node2id=None) -> "DeviceGraph":
         """Edge list (device int32 tensors) -> normalised operator.  ``symmetrize`` defaults to
         ``not directed`` (an undirected edge list names every edge once)."""
         lib = C.lib()
@@ -504,7 +537,7 @@ class DeviceGraph:
 
     @staticmethod
     def from_scipy(A, directed: bool = False, normalization: str = "auto", renormalize=False,
-                   relabel: str = "degree", device=None, node2id=None) -> "DeviceGraph":
+                   relabel: str = "hub", device=None, node2id=None) -> "DeviceGraph":
         """A host scipy adjacency (what ``pg.AdjacencyWrapper`` carries, wrapgraph.py:4-22)."""
         import scipy.sparse as sp
         lib = C.lib()
@@ -536,16 +569,27 @@ class DeviceGraph:
         if normalization not in _SCALE_KINDS:
             raise Exception("Supported normalizations: none, col, symmetric, both, laplacian, auto")
         self.normalization = normalization
-        if relabel not in ("degree", "none"):
-            raise Exception("relabel must be 'degree' or 'none'")
+        if relabel not in RELABELS:
+            raise Exception("relabel must be one of " + ", ".join(RELABELS))
         rows = None
-        if relabel == "degree" and n > 1 and nnz > 0:
+        if relabel != "none" and n > 1 and nnz > 0:
             wsb = lib.pgb_degree_order_workspace_bytes(n)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             self.perm = torch.empty(n, dtype=torch.int32, device=dev)
             self.iperm = torch.empty(n, dtype=torch.int32, device=dev)
             C.check(lib.pgb_degree_order(n, C.ptr(indptr), C.ptr(ws), wsb, C.ptr(self.perm), C.ptr(self.iperm), st))
             del ws
+            if relabel == "hub" and values is None:
+                # refine the degree order inside every hub block / the tail by the blocks each row touches
+                # (pgb_hub_order): only the hub-blocked form (unweighted graphs) gains from it
+                G, span = hub_signature_shape(n)
+                words = -(-(-(-span // G)) // 64)
+                if 0 < words <= C.SIGNATURE_WORDS:
+                    wsb = lib.pgb_hub_order_workspace_bytes(n, words)
+                    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                    C.check(lib.pgb_hub_order(n, C.ptr(indptr), C.ptr(indices), G, span, C.ptr(ws), wsb,
+                                              C.ptr(self.perm), C.ptr(self.iperm), st))
+                    del ws
             rows = torch.empty(nnz, dtype=torch.int32, device=dev)
             C.check(lib.pgb_csr_expand_rows(n, nnz, C.ptr(indptr), C.ptr(rows), st))
             cols = indices.clone()
@@ -743,7 +787,7 @@ class DeviceGraph:
         return self.directed
 
 
-def as_device_graph(graph, normalization="auto", renormalize=False, relabel="degree", weight="weight",
+def as_device_graph(graph, normalization="auto", renormalize=False, relabel="hub", weight="weight",
                     device=None) -> DeviceGraph:
     """Anything the reference's preprocessor accepts -> DeviceGraph (preprocessing.py:88-103)."""
     if isinstance(graph, DeviceGraph):
@@ -777,7 +821,7 @@ def _is_range_nodes(graph) -> bool:
 
 
 def preprocessor(normalization: str = "auto", assume_immutability: bool = False, weight: str = "weight",
-                 renormalize=False, relabel: str = "degree", device=None):
+                 renormalize=False, relabel: str = "hub", device=None):
     """Device twin of ``pg.preprocessor`` (preprocessing.py:233-287): returns a callable named
     ``preprocess`` (so ``filter + preprocess`` works, abstract_filters.py:91-92) mapping a graph
     to a :class:`DeviceGraph`; ``assume_immutability`` memoises per input object like MethodHasher."""

@@ -126,7 +126,7 @@ def test_laplacian_identity(pgb, torch_cuda, name):
 
 # ---------------------------------------------------------------------------- conv
 @pytest.mark.parametrize("name", GOLDEN_GRAPHS)
-@pytest.mark.parametrize("relabel", ["none", "degree"])
+@pytest.mark.parametrize("relabel", ["none", "degree", "hub"])
 def test_conv_matches_reference(pgb, torch_cuda, name, relabel):
     torch = torch_cuda
     z, A, directed = load_golden(name)
@@ -191,7 +191,7 @@ RUN_NAMES = ["ppr85", "ppr90_noq", "ppr85_sym", "ppr85_col", "ppr85_tol6_mod3", 
 
 @pytest.mark.parametrize("name", GOLDEN_GRAPHS)
 @pytest.mark.parametrize("run", RUN_NAMES)
-@pytest.mark.parametrize("relabel", ["degree", "none"])
+@pytest.mark.parametrize("relabel", ["hub", "degree", "none"])
 def test_filters_fp64_match_golden(pgb, torch_cuda, name, run, relabel):
     torch = torch_cuda
     z, A, directed = load_golden(name)
@@ -250,7 +250,7 @@ def test_custom_absorption_and_propagate(pgb, torch_cuda, name):
 @pytest.mark.parametrize("name", GOLDEN_GRAPHS)
 @pytest.mark.parametrize("run", ["ppr85", "ppr90_noq", "ppr85_col", "ppr85_l1", "ppr85_msq", "ppr85_tol6_mod3",
                                  "absorb85", "absorb85_col"])
-@pytest.mark.parametrize("relabel", ["degree", "none"])
+@pytest.mark.parametrize("relabel", ["hub", "degree", "none"])
 def test_batched_propagate_matches_golden(pgb, torch_cuda, monkeypatch, name, run, relabel):
     """propagate() through the panel kernel (pgb_affine_steps_batched): every column must stop at the
     reference's own iteration count and match its scores (signals.py:225-226 runs them one by one)."""

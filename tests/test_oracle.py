@@ -90,3 +90,17 @@ def test_max_iters_raises_and_zero_personalization():
         orc.pagerank(M, p, 0.99, tol=1e-14, max_iters=5)
     r, iters, _ = orc.pagerank(M, np.zeros(A.shape[0]))
     assert iters == 0 and not r.any()
+
+
+def test_fast_c_generator_equals_numpy_recipe():
+    """oracle/rmat_gen.c (bench CPU legs) == pygrank_b200.synthetic (the documented recipe), bit for bit."""
+    from oracle import fastgen
+    from pygrank_b200 import synthetic
+    for scale, seed in ((9, 1), (12, 7), (13, 1)):
+        s0, d0 = synthetic.rmat_edges_host(scale, 16, seed)
+        s1, d1 = fastgen.rmat_edges(scale, 16, seed)
+        assert np.array_equal(s0, s1) and np.array_equal(d0, d1)
+        A0 = synthetic.rmat_graph_host(scale, 16, seed)
+        A1 = fastgen.rmat_graph(scale, 16, seed)
+        assert np.array_equal(A0.indptr, A1.indptr) and np.array_equal(A0.indices, A1.indices)
+        assert np.array_equal(A0.data, A1.data)
