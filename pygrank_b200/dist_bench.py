@@ -1,4 +1,13 @@
-"""bench.py's N>1 leg: weak-scaling PPR on a row-partitioned RMAT graph (scale 24 + log2 N)."""
+"""bench.py's N>1 leg: weak-scaling PageRank on a row-partitioned RMAT graph (scale 24 + log2 N, BASELINE config 4).
+
+Before anything is timed the run checks itself (`parity` in the JSON line, non-zero exit on failure):
+* the SAME code path (same world size, same exchange, reader masks as selected, NaN-poisoned symmetric buffers) on a
+  small RMAT graph against the single-GPU engine on rank 0: fp64 iteration counts equal, fp64 <= 1e-10 / fp32 <= 1e-5
+  relative L1;
+* on the timed graph itself a size-independent property of the converged vector, evaluated WITHOUT the engine's
+  kernels (plain torch gathers over this rank's CSR rows): r = (alpha*M r + (1-alpha)*p)/s means v_i/r_i is one
+  constant s on every row; sampled rows of every rank must agree on it.
+"""
 from __future__ import annotations
 
 import ctypes
@@ -32,7 +41,11 @@ def run(args):
     g = DistGraph.rmat(scale, 16, seed=1)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
-    alg = DistPageRank(B.ALPHA, tol=B.TOL, max_iters=B.MAX_ITERS, dtype=dtype)
+    alpha = B.alpha_for(world)
+    parity = None
+    if not args.no_parity:
+        parity = small_scale_parity(alpha, rank, world, dev)
+    alg = DistPageRank(alpha, tol=B.TOL, max_iters=B.MAX_ITERS, dtype=dtype)
     total = args.warmup + args.steps
     seeds = synthetic.seed_sets(g.n_nodes, total, 10, seed=0)
     pers = [alg.local_personalization(g, s) for s in seeds]
@@ -52,7 +65,10 @@ def run(args):
         return float(worst.item()), calls
 
     for i in range(args.warmup):
-        alg.rank(g, p_local=pers[i][0], norm=pers[i][1])
+        last = alg.rank(g, p_local=pers[i][0], norm=pers[i][1])
+    if parity is not None and args.warmup > 0:
+        parity["fixed_point"] = fixed_point_check(g, alg, last, pers[args.warmup - 1][0], alpha, dtype)
+        parity["ok"] = bool(parity["ok"] and parity["fixed_point"]["ok"])
     sampler = B.ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -101,7 +117,7 @@ def run(args):
     n_loc, off = g.n_local, g.offset
     sf = [0.0] * C.STATE_LEN
     si = [0] * C.STATE_LEN
-    sf[C.SF_ALPHA], sf[C.SF_INVS], sf[C.SF_MEAN], sf[C.SF_NORM] = B.ALPHA, 1.0, float(g.n_nodes), 10.0
+    sf[C.SF_ALPHA], sf[C.SF_INVS], sf[C.SF_MEAN], sf[C.SF_NORM] = alpha, 1.0, float(g.n_nodes), 10.0
     si[C.SI_MAX_ITERS], si[C.SI_END_MODULO], si[C.SI_ERR_MODE], si[C.SI_QUOTIENT] = 10 ** 6, 1, C.ERR_ITERS, 0
     state_f64 = torch.tensor(sf, dtype=torch.float64, device=dev)
     state_i32 = torch.tensor(si, dtype=torch.int32, device=dev)
@@ -115,7 +131,7 @@ def run(args):
     reps = 20
 
     def steps(first, count):
-        C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, B.ALPHA, None, None, C.ptr(cvec), C.ptr(q),
+        C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, alpha, None, None, C.ptr(cvec), C.ptr(q),
                                      C.ptr(zfull[0]), C.ptr(zfull[1]), off, C.ptr(state_f64), C.ptr(state_i32),
                                      C.ptr(err_hist), span_struct(ws), first, count, 1, st))
 
@@ -148,7 +164,7 @@ def run(args):
             "metric": "PPR GTEPS", "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": dict(B.workload_config(world, scale), n=g.n_nodes, nnz=g.nnz_global,
+            "config": dict(B.workload_config(world, scale, alpha), n=g.n_nodes, nnz=g.nnz_global,
                            nnz_per_rank=[int(x) for x in nnz_all], conv_calls_per_solve=conv_calls / args.steps,
                            exchange=exchange,
                            graph_build_s=round(build_s, 2)),
@@ -157,12 +173,98 @@ def run(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None,
-                         "kernel": ("hsell gather+reduce+update<%s> (one step, per rank, max over ranks)" if form is not None
+                         "kernel": ("hsell gather+update<%s> (one step, per rank, max over ranks)" if form is not None
                                     else "item_stream_kernel<%s,unweighted,AFFINE,SYMDEG> (per rank, max over ranks)") % args.dtype,
                          "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
             "cpu_baseline": None,
+            "parity": parity,
             "clocks": clocks,
         }
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(3)
+
+
+PARITY_SCALE = 20
+
+
+def small_scale_parity(alpha, rank, world, dev):
+    """The N-rank path (this world size, this exchange configuration, NaN-poisoned buffers) against the single-GPU
+    engine on RMAT-20; rank 0 compares, every rank learns the verdict."""
+    import pygrank_b200 as pgb
+    from . import device_synthetic, synthetic
+    from .dist import DistGraph, DistPageRank
+    g = DistGraph.rmat(PARITY_SCALE, 16, seed=1)
+    peer = g.peer_buffers(torch.float32)
+    exchange = "nccl all-gather" if peer is None else ("multicast" if peer["multicast"] else
+                                                       "unicast stores" + (" + reader mask" if peer["mask"] is not None else ""))
+    seeds = synthetic.seed_sets(1 << PARITY_SCALE, 2, 10, seed=0)
+    single = device_synthetic.rmat_graph_device(PARITY_SCALE, 16, seed=1) if rank == 0 else None
+    out = {"ranks": world, "rmat_scale": PARITY_SCALE, "against": "single-GPU engine (fp64), same graph and seeds",
+           "exchange": exchange, "poisoned_buffers": True, "ok": True}
+    for name, dtype, tol in (("f64", torch.float64, 1e-10), ("f32", torch.float32, 1e-5)):
+        worst, its_d, its_s = 0.0, [], []
+        for s in seeds:
+            alg = DistPageRank(alpha, tol=1e-9, max_iters=1000, dtype=dtype)
+            alg.poison = True
+            full = alg.gather_user_order(g, alg.rank(g, s))
+            if rank == 0:
+                ref_alg = pgb.PageRank(alpha, tol=1e-9, max_iters=1000, dtype=torch.float64)
+                ref = ref_alg(single, [int(v) for v in s]).np
+                worst = max(worst, float((full.double() - ref).abs().sum() / ref.abs().sum()))
+                its_d.append(int(alg.iteration))
+                its_s.append(int(ref_alg.convergence.iteration))
+        if rank == 0:
+            same = its_d == its_s
+            ok = bool(np.isfinite(worst)) and worst <= tol and (same if name == "f64" else
+                                                                 all(abs(a - b) <= 1 for a, b in zip(its_d, its_s)))
+            out[name] = {"rel_l1": worst, "tolerance": tol, "iterations": its_d, "iterations_single_gpu": its_s,
+                         "iterations_equal": same, "ok": ok}
+            out["ok"] = out["ok"] and ok
+    flag = torch.tensor([1 if out["ok"] else 0], device=dev)
+    dist.broadcast(flag, 0)
+    out["ok"] = bool(int(flag.item()))
+    del g, single
+    torch.cuda.empty_cache()
+    return out
+
+
+def fixed_point_check(g, alg, local_scores, p_local, alpha, dtype, samples: int = 512):
+    """Size-independent check on the timed graph: with r the returned scores (sum = |p|), v = alpha*M r + (1-alpha)*p
+    satisfies v_i = s*r_i with ONE s for all rows.  Evaluated on sampled rows of every rank with plain torch index
+    arithmetic over the rank's CSR rows (no engine kernel): M_ij = 1/sqrt(d_i d_j).  p_local is the rank's slice of the
+    UNnormalised personalization (|p| = the norm the scores were rescaled by)."""
+    dev = local_scores.device
+    f64 = torch.float64
+    r_full = torch.empty(g.n_global, dtype=dtype, device=dev)
+    dist.all_gather_into_tensor(r_full, local_scores.contiguous(), group=g.group)
+    deg_local = (g.view.indptr[1:] - g.view.indptr[:-1]).to(torch.int32)
+    deg_full = torch.empty(g.n_global, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(deg_full, deg_local.contiguous(), group=g.group)
+    # the highest-scored rows of this rank: tol 1e-9 bounds the mean ABSOLUTE change per node, so only rows whose
+    # score is orders of magnitude above it pin the ratio tightly
+    rows = torch.topk(local_scores, min(samples, g.n_local)).indices
+    rows = rows[deg_local[rows] > 0][:256]
+    ratios = []
+    ip = g.view.indptr
+    for i in rows.tolist():
+        cols = g.view.indices[int(ip[i]):int(ip[i + 1])].long()
+        y = (r_full[cols].to(f64) / torch.sqrt(deg_full[cols].to(f64))).sum() / np.sqrt(float(deg_local[i]))
+        v = alpha * y + (1 - alpha) * p_local[i].to(f64)
+        ratios.append(v / local_scores[i].to(f64))
+    if ratios:
+        rt = torch.stack(ratios)
+        lo, hi, cnt = rt.min(), rt.max(), torch.tensor(float(len(ratios)), device=dev, dtype=f64)
+    else:
+        lo, hi = torch.tensor(float("inf"), device=dev, dtype=f64), torch.tensor(float("-inf"), device=dev, dtype=f64)
+        cnt = torch.tensor(0.0, device=dev, dtype=f64)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=g.group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=g.group)
+    dist.all_reduce(cnt, group=g.group)
+    spread = float((hi - lo) / ((hi + lo) / 2)) if float(cnt) > 0 else float("nan")
+    ok = float(cnt) > 0 and np.isfinite(spread) and spread <= 5e-3
+    return {"property": "v_i / r_i constant over rows, v = alpha*M r + (1-alpha)*p (torch gathers, no engine kernel)",
+            "rows_checked": int(cnt), "ratio_min": float(lo), "ratio_max": float(hi), "relative_spread": spread,
+            "tolerance": 5e-3, "ok": bool(ok)}
