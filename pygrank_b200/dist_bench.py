@@ -4,9 +4,10 @@ Before anything is timed the run checks itself (`parity` in the JSON line, non-z
 * the SAME code path (same world size, same exchange, reader masks as selected, NaN-poisoned symmetric buffers) on a
   small RMAT graph against the single-GPU engine on rank 0: fp64 iteration counts equal, fp64 <= 1e-10 / fp32 <= 1e-5
   relative L1;
-* on the timed graph itself a size-independent property of the converged vector, evaluated WITHOUT the engine's
-  kernels (plain torch gathers over this rank's CSR rows): r = (alpha*M r + (1-alpha)*p)/s means v_i/r_i is one
-  constant s on every row; sampled rows of every rank must agree on it.
+* on the timed graph itself a size-independent property, evaluated WITHOUT the engine's kernels (plain torch gathers
+  over this rank's CSR rows): the iterates after m and m+1 steps obey r_{m+1} = (alpha*M r_m + (1-alpha)*p)/s with one
+  s on every row; the highest-scored rows of every rank must agree on it to rounding.  (The converged vector itself is
+  no fixed point to that accuracy: Mabs divides by n, so at 10^8 nodes the loop stops while the top rows still move.)
 """
 from __future__ import annotations
 
@@ -65,10 +66,10 @@ def run(args):
         return float(worst.item()), calls
 
     for i in range(args.warmup):
-        last = alg.rank(g, p_local=pers[i][0], norm=pers[i][1])
-    if parity is not None and args.warmup > 0:
-        parity["fixed_point"] = fixed_point_check(g, alg, last, pers[args.warmup - 1][0], alpha, dtype)
-        parity["ok"] = bool(parity["ok"] and parity["fixed_point"]["ok"])
+        alg.rank(g, p_local=pers[i][0], norm=pers[i][1])
+    if parity is not None:
+        parity["one_step_on_timed_graph"] = one_step_check(g, alpha, dtype, seeds[0])
+        parity["ok"] = bool(parity["ok"] and parity["one_step_on_timed_graph"]["ok"])
     sampler = B.ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -231,21 +232,27 @@ def small_scale_parity(alpha, rank, world, dev):
     return out
 
 
-def fixed_point_check(g, alg, local_scores, p_local, alpha, dtype, samples: int = 512):
-    """Size-independent check on the timed graph: with r the returned scores (sum = |p|), v = alpha*M r + (1-alpha)*p
-    satisfies v_i = s*r_i with ONE s for all rows.  Evaluated on sampled rows of every rank with plain torch index
-    arithmetic over the rank's CSR rows (no engine kernel): M_ij = 1/sqrt(d_i d_j).  p_local is the rank's slice of the
-    UNnormalised personalization (|p| = the norm the scores were rescaled by)."""
-    dev = local_scores.device
+def one_step_check(g, alpha, dtype, seeds, m: int = 6, samples: int = 512):
+    """Size-independent check on the TIMED graph (any convergence state): the engine's iterates after m and m+1
+    steps (two fixed-length solves, error_type="iters") must satisfy r_{m+1} = (alpha*M r_m + (1-alpha)*p)/s with ONE
+    s for all rows.  The right-hand side is evaluated on the highest-scored rows of every rank with plain torch index
+    arithmetic over the rank's CSR rows (M_ij = 1/sqrt(d_i d_j)) — no engine kernel — and the ratios v_i / r_{m+1,i}
+    of all ranks must agree to rounding."""
+    from .dist import DistPageRank
+    dev = g.view.indptr.device
     f64 = torch.float64
+    iterates = []
+    for k in (m, m + 1):
+        alg = DistPageRank(alpha, tol=1e-9, max_iters=k + 1, dtype=dtype, error_type="iters")
+        p_local, norm = alg.local_personalization(g, seeds)
+        iterates.append(alg.rank(g, p_local=p_local, norm=norm))
+    r_m, r_next = iterates
     r_full = torch.empty(g.n_global, dtype=dtype, device=dev)
-    dist.all_gather_into_tensor(r_full, local_scores.contiguous(), group=g.group)
+    dist.all_gather_into_tensor(r_full, r_m.contiguous(), group=g.group)
     deg_local = (g.view.indptr[1:] - g.view.indptr[:-1]).to(torch.int32)
     deg_full = torch.empty(g.n_global, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(deg_full, deg_local.contiguous(), group=g.group)
-    # the highest-scored rows of this rank: tol 1e-9 bounds the mean ABSOLUTE change per node, so only rows whose
-    # score is orders of magnitude above it pin the ratio tightly
-    rows = torch.topk(local_scores, min(samples, g.n_local)).indices
+    rows = torch.topk(r_next, min(samples, g.n_local)).indices
     rows = rows[deg_local[rows] > 0][:256]
     ratios = []
     ip = g.view.indptr
@@ -253,7 +260,7 @@ def fixed_point_check(g, alg, local_scores, p_local, alpha, dtype, samples: int 
         cols = g.view.indices[int(ip[i]):int(ip[i + 1])].long()
         y = (r_full[cols].to(f64) / torch.sqrt(deg_full[cols].to(f64))).sum() / np.sqrt(float(deg_local[i]))
         v = alpha * y + (1 - alpha) * p_local[i].to(f64)
-        ratios.append(v / local_scores[i].to(f64))
+        ratios.append(v / r_next[i].to(f64))
     if ratios:
         rt = torch.stack(ratios)
         lo, hi, cnt = rt.min(), rt.max(), torch.tensor(float(len(ratios)), device=dev, dtype=f64)
@@ -264,7 +271,9 @@ def fixed_point_check(g, alg, local_scores, p_local, alpha, dtype, samples: int 
     dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=g.group)
     dist.all_reduce(cnt, group=g.group)
     spread = float((hi - lo) / ((hi + lo) / 2)) if float(cnt) > 0 else float("nan")
-    ok = float(cnt) > 0 and np.isfinite(spread) and spread <= 5e-3
-    return {"property": "v_i / r_i constant over rows, v = alpha*M r + (1-alpha)*p (torch gathers, no engine kernel)",
-            "rows_checked": int(cnt), "ratio_min": float(lo), "ratio_max": float(hi), "relative_spread": spread,
-            "tolerance": 5e-3, "ok": bool(ok)}
+    tol = 1e-4 if dtype == torch.float32 else 1e-10
+    ok = float(cnt) > 0 and np.isfinite(spread) and spread <= tol
+    return {"property": "r_{m+1,i} * s = alpha*(M r_m)_i + (1-alpha)*p_i with one s on all rows of all ranks "
+                        "(right-hand side by torch gathers over the CSR rows, no engine kernel)",
+            "steps_m": m, "rows_checked": int(cnt), "ratio_min": float(lo), "ratio_max": float(hi),
+            "relative_spread": spread, "tolerance": tol, "ok": bool(ok)}

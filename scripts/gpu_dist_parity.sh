@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1"
 port=29600
 for scale in $SCALES; do
-  for variant in "X=1" "PGB_PEER_MASK=1" "PGB_PEER_MASK=0" "PGB_PEER=0" "PGB_PEER_MULTICAST=1"; do
+  for variant in ${VARIANTS:-"X=1" "PGB_PEER_MASK=1" "PGB_PEER_MASK=0" "PGB_PEER=0" "PGB_PEER_MULTICAST=1"}; do
     port=$((port+1))
     log=gpurun_out/distpar_w${W}_s${scale}_${variant//=/}.log
     env $variant timeout 600 $TR --master-port $port tests/dist_gpu_check.py $scale $( [ "$variant" != "X=1" ] && echo --no-shard ) > $log 2>&1
