@@ -281,7 +281,7 @@ def plugin_leg(args, g, seeds, alpha, dtype, n_warm, total):
 
             def solve(i):
                 r = alg(pg.to_signal(g, {int(v): 1.0 for v in seeds[i]}))
-                host.copy_(b200.to_array(r.np), non_blocking=False)
+                host.copy_(b200.to_tensor(r.np), non_blocking=False)
                 return alg.convergence.iteration - 1
 
             for i in range(n_warm):

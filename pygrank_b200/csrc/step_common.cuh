@@ -71,10 +71,10 @@ __device__ __forceinline__ void finalize_state(double *sf, int32_t *si, double *
     if (stop != PGB_RUNNING) {
         vsi[PGB_SI_ITERATION] = it;
         vsi[PGB_SI_STOP] = stop;
-    } else if (vsi[PGB_SI_QUOTIENT]) {
-        // sum(next ranks) is linear in the current ranks: alpha * sum_i ranks_i*rowsum_i(M) + sum(bias)
-        vsf[PGB_SF_INVS] = 1.0 / (vsf[PGB_SF_ALPHA] * tacc + vsf[PGB_SF_BIAS]);
     }
+    // sum(next ranks) is linear in the current ranks: alpha * sum_i ranks_i*rowsum_i(M) + sum(bias).  Kept current
+    // on a stop too: a caller may clear STOP and go on (the plugin route does when the driver's rule differs).
+    if (vsi[PGB_SI_QUOTIENT]) vsf[PGB_SF_INVS] = 1.0 / (vsf[PGB_SF_ALPHA] * tacc + vsf[PGB_SF_BIAS]);
     __threadfence();
 }
 

@@ -91,13 +91,22 @@ def test_reference_filters_unchanged_on_b200(pg, name):
         pre = pg.preprocessor(normalization="auto", assume_immutability=True)   # the reference's own preprocessor
         M = pre(graph)
         assert M.array.__class__.__name__ == "DeviceGraph"
+        from pygrank_b200 import lazy
         for rname, make in runs.items():
             for c in (0, 3):
                 alg = make(pre)
+                lazy.reset_stats()
                 r = alg(pg.to_signal(M, P[:, c].copy()))
-                assert alg.convergence.iteration == int(z[f"run_{rname}_iters"][c]), (name, rname, c)
+                iters = int(z[f"run_{rname}_iters"][c])
+                assert alg.convergence.iteration == iters, (name, rname, c)
                 got = r.np.cpu().numpy()
                 assert rel_l1(got, z[f"run_{rname}_scores"][:, c]) <= 1e-10, (name, rname, c)
+                # the unmodified driver reached the FUSED kernels: every conv ran inside a fused step, and the number
+                # of eager elementwise kernels / host synchronisations does not grow with the iteration count
+                st = dict(lazy.STATS)
+                assert st["eager_convs"] == 0 and st["runs"] == 1 and st["recomputed_runs"] == 0, (name, rname, c, st)
+                assert st["fused_steps"] >= iters - 2, (name, rname, c, st)
+                assert st["eager_ops"] <= 16 and st["syncs"] <= 8 + (iters if rname == "heat3_tol9" else 0), (name, rname, c, st)
 
 
 def test_device_preprocessor_injected_into_reference_filter(pg):
@@ -150,3 +159,61 @@ def test_graph_dropout_on_a_directed_graph(pg):
     assert abs(float(dropped.sum()) / float(full.sum()) - 1.0) < 0.05
     assert float((dropped - full).abs().sum()) > 0
     assert float((g.conv(x) - full).abs().sum()) == 0          # the original graph is untouched
+
+
+def test_plugin_route_fp32_dict_personalization_and_device_preprocessor(pg):
+    """The route bench.py's e2e_plugin times: device preprocessor injected, dict personalization, fp32 vectors."""
+    import torch
+    import pygrank_b200
+    from pygrank_b200 import backend as b200, lazy
+    z, A, directed = load_golden("rmat10")
+    P = z["P"]
+    b200.configure(dtype=torch.float32)
+    try:
+        with pg.Backend("b200"):
+            pre = pygrank_b200.preprocessor(normalization="symmetric", assume_immutability=True)
+            graph = pre(pg.AdjacencyWrapper(A, directed=False))
+            alg = pg.PageRank(0.85, tol=1e-9, preprocessor=pre, max_iters=1000)
+            seeds = {int(i): float(P[i, 0]) for i in np.nonzero(P[:, 0])[0]}
+            lazy.reset_stats()
+            r = alg(pg.to_signal(graph, seeds))
+            assert abs(alg.convergence.iteration - int(z["run_ppr85_sym_iters"][0])) <= 1
+            assert rel_l1(r.np.cpu().numpy(), z["run_ppr85_sym_scores"][:, 0]) <= 1e-5
+            assert lazy.STATS["eager_convs"] == 0 and lazy.STATS["runs"] == 1
+            assert isinstance(r[int(np.nonzero(P[:, 0])[0][0])], float)
+    finally:
+        b200.configure(dtype=torch.float64)
+
+
+def test_plugin_route_eager_fallbacks_stay_correct(pg):
+    """Shapes the engine does not fuse (measure classes it does not know, postprocessor quotients, eigenvector
+    convergence, end_modulo > 1, max_iters cut-offs) still give the numpy backend's answer."""
+    z, A, directed = load_golden("ba2000")
+    P = z["P"]
+    cases = {
+        "end_modulo": lambda pre: pg.PageRank(0.85, tol=1e-6, end_modulo=3, preprocessor=pre),
+        "iters20": lambda pre: pg.PageRank(0.85, error_type="iters", max_iters=20, preprocessor=pre),
+        "msq": lambda pre: pg.PageRank(0.85, tol=1e-16, error_type=pg.MSQ, max_iters=1000, preprocessor=pre),
+        "maxdiff": lambda pre: pg.PageRank(0.85, tol=1e-9, error_type=pg.MaxDifference, max_iters=1000, preprocessor=pre),
+        "rmabs": lambda pre: pg.PageRank(0.85, tol=1e-7, error_type=pg.RMabs, max_iters=1000, preprocessor=pre),
+        "eig": lambda pre: pg.PageRank(0.85, tol=1e-9, converge_to_eigenvectors=True, max_iters=1000, preprocessor=pre),
+        "cheby": lambda pre: pg.HeatKernel(3, tol=1e-9, coefficient_type="chebyshev", preprocessor=pre),
+        "gen3": lambda pre: pg.GenericGraphFilter([0.5, 0.25, 0.125], tol=1e-9, preprocessor=pre),
+        "closed": lambda pre: pg.PageRankClosed(0.85, tol=1e-9, max_iters=1000, preprocessor=pre),
+        "absorb_custom": lambda pre: pg.AbsorbingWalks(0.85, tol=1e-9, max_iters=1000, preprocessor=pre),
+    }
+    results = {}
+    for backend in ["numpy", "b200"]:
+        pg.load_backend(backend)
+        graph = pg.AdjacencyWrapper(A, directed=directed)
+        pre = pg.preprocessor(normalization="auto", assume_immutability=True)
+        for cname, make in cases.items():
+            alg = make(pre)
+            kwargs = {"absorption": {i: 1.0 + (i % 3) for i in range(A.shape[0])}} if cname == "absorb_custom" else {}
+            r = alg(pg.to_signal(graph, P[:, 1].copy()), **kwargs)
+            out = r.np if backend == "numpy" else r.np.cpu().numpy()
+            results.setdefault(cname, []).append((np.asarray(out, dtype=np.float64), alg.convergence.iteration))
+    pg.load_backend("numpy")
+    for cname, ((ref, it_ref), (got, it_got)) in results.items():
+        assert it_ref == it_got, (cname, it_ref, it_got)
+        assert rel_l1(got, ref) <= 1e-10, cname
