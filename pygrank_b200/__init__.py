@@ -20,7 +20,8 @@ from . import _capi
 from ._capi import build, lib
 
 __all__ = ["build", "lib", "install", "configure", "preprocessor", "DeviceGraph", "PageRank", "PageRankClosed",
-           "HeatKernel", "GenericGraphFilter", "AbsorbingWalks", "ConvergenceManager", "RankResult"]
+           "HeatKernel", "GenericGraphFilter", "AbsorbingWalks", "ConvergenceManager", "RankResult", "Normalize", "Ordinals",
+           "Top", "Threshold", "import_snap_format_dataset", "from_fastgraph"]
 
 BACKEND_NAME = "b200"
 
@@ -34,6 +35,12 @@ def __getattr__(name):
                 "ConvergenceManager", "RankResult", "GraphFilter", "RecursiveGraphFilter", "ClosedFormGraphFilter"):
         from . import filters
         return getattr(filters, name)
+    if name in ("Normalize", "Ordinals", "Top", "Threshold", "Postprocessor"):
+        from . import postprocess
+        return getattr(postprocess, name)
+    if name in ("import_snap_format_dataset", "from_fastgraph", "read_pairs", "graph_from_pairs"):
+        from . import ingest
+        return getattr(ingest, name)
     if name == "configure":
         from . import backend
         return backend.configure

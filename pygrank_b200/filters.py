@@ -471,19 +471,179 @@ class AbsorbingWalks(RecursiveGraphFilter):
         return dict(alpha=1.0, alpha_s=1.0, w_run=w_run, c_run=c_run, coef=0.0, coefvec=coefvec)
 
 
+class _HostConvergence:
+    """ConvergenceManager.has_converged (convergence.py:77-101) for the filters that run op by op on the device
+    (Chebyshev / Krylov / cached powers): the counter, the max_iters rule, end_modulo and the error test, with the
+    error itself one reduction on the device."""
+
+    def __init__(self, cm: ConvergenceManager, n: int):
+        self.cm, self.n = cm, n
+        self.code = _error_code(cm.error_type)
+        self.last = None
+        cm.iteration = 0
+
+    def has_converged(self, ranks: torch.Tensor) -> bool:
+        cm = self.cm
+        cm.iteration += 1
+        if cm.iteration >= cm.max_iters:
+            if self.code == C.ERR_ITERS or cm.iter_exception is None:
+                return True
+            raise cm.iter_exception("Could not converge within " + str(cm.max_iters) + " iterations")
+        converged = False
+        if self.last is not None and self.code != C.ERR_ITERS and cm.iteration % max(cm.end_modulo, 1) == 0:
+            d = (self.last - ranks).to(torch.float64)
+            if self.code == C.ERR_MABS:
+                err = float(d.abs().sum()) / self.n
+            elif self.code == C.ERR_L1:
+                err = float(d.abs().sum())
+            elif self.code == C.ERR_MSQ:
+                err = float((d * d).sum()) / self.n
+            else:
+                err = float(d.abs().max())
+            converged = err <= (0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps)))
+        self.last = ranks
+        return converged
+
+
+def _obj_key(obj) -> str:
+    """obj2id of the reference (core/utils/preprocessing.py:166-171): a uuid attached to the personalization object
+    when it accepts attributes, else its identity."""
+    import uuid
+    if isinstance(obj, RankResult):
+        obj = obj.np
+    try:
+        if not hasattr(obj, "uuid"):
+            obj.uuid = uuid.uuid1()
+        return str(obj.uuid)
+    except (AttributeError, TypeError):
+        return "id" + str(id(obj))
+
+
 class ClosedFormGraphFilter(GraphFilter):
-    """Taylor-coefficient polynomial filters in the node space (abstract_filters.py:139-267)."""
+    """Polynomial filters (abstract_filters.py:139-267).  Taylor coefficients in the node space without a power cache —
+    HeatKernel / PageRankClosed / GenericGraphFilter as the BASELINE configs use them — run fused on pgb_poly_steps.
+    ``coefficient_type="chebyshev"``, ``krylov_dims`` (Lanczos, filters/krylov_space.py:16-50) and
+    ``optimization_dict`` (the power cache tuners rely on, abstract_filters.py:241-246: O(n) per candidate once the
+    powers of a personalization are known) run on the device op by op: one gather kernel per ``conv`` plus torch
+    elementwise passes, with the reference's recursion, iteration counting and exceptions."""
 
     def __init__(self, krylov_dims=None, coefficient_type: str = "taylor", optimization_dict=None, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        if krylov_dims is not None or coefficient_type.lower() != "taylor" or optimization_dict is not None:
-            raise Exception("the fused closed-form filter implements taylor coefficients in the node space; "
-                            "krylov/chebyshev/optimization_dict run on the backend plugin path")
+        self.krylov_dims = krylov_dims
+        self.coefficient_type = coefficient_type.lower()
+        self.optimization_dict = optimization_dict
+        if self.coefficient_type not in ("taylor", "chebyshev"):
+            raise Exception("Invalid coefficient type")
+        self._active_dict = None
+
+    def rank(self, graph=None, personalization=None, *args, **kwargs):
+        if self.optimization_dict is not None:                 # abstract_filters.py:230-236
+            key = _obj_key(personalization)
+            self._active_dict = self.optimization_dict.setdefault(key, dict())
+        else:
+            self._active_dict = None
+        return super().rank(graph, personalization, *args, **kwargs)
+
+    def _fusable(self) -> bool:
+        return self.krylov_dims is None and self.coefficient_type == "taylor" and self.optimization_dict is None
+
+    # -- op-by-op evaluation on the device ------------------------------------------------------------------------
+    def _retrieve_power(self, power, g, iteration):
+        nxt = lambda: g.conv(power) if self.krylov_dims is None else power @ self._krylov_H
+        if self._active_dict is not None:
+            if iteration not in self._active_dict:
+                self._active_dict[iteration] = nxt()
+            return self._active_dict[iteration]
+        return nxt()
+
+    def _recursion(self, result, next_term, coef, iteration):
+        if self.coefficient_type == "chebyshev":               # abstract_filters.py:206-217
+            if iteration == 2:
+                self._prev_term = next_term
+            if iteration > 2:
+                next_term = 2 * next_term - self._prev_term
+                self._prev_term = next_term
+                if coef == 0:
+                    return result, next_term
+            return result + next_term * coef, next_term
+        if coef == 0:
+            return result, next_term
+        return result + next_term * coef, next_term
+
+    def _run_eager(self, g, p, norm, warm):
+        f64 = torch.float64
+        dtype = self.dtype
+        pn = (p.to(f64) / norm).to(dtype)
+        conv_host = _HostConvergence(self.convergence, g.n)
+        coef = None
+        self._prev_term = 0
+        ranks = torch.zeros(g.n, dtype=dtype, device=p.device)      # abstract_filters.py:213
+        if self.krylov_dims is not None:
+            ranks = pn.clone()                                      # the Krylov branch of _start keeps the start vector
+            K = int(self.krylov_dims)
+            V, H = self._krylov_base(g, pn, K)
+            self._krylov_H = H
+            result = H * 0
+            power = torch.eye(K, dtype=dtype, device=p.device)
+            bound = self._krylov_error_bound(V, H, g, pn)
+            if bound > 0.01:
+                raise Exception("Krylov approximation with estimated relative error " + str(bound)
+                                + " > 0.01 is too rough to be meaningful (try on lager graphs)")
+        else:
+            power = pn
+        while not conv_host.has_converged(ranks):
+            it = self.convergence.iteration
+            coef = self._coefficient(coef, it)
+            if self.krylov_dims is not None:
+                result, power = self._recursion(result, power, coef, it)
+                ranks = (V @ result)[:, 0].contiguous()        # krylov2original (krylov_space.py:47-50)
+            else:
+                ranks, power = self._recursion(ranks, power, coef, it)
+            power = self._retrieve_power(power, g, it)
+        C.count_launches(self.convergence.iteration)
+        return ranks * norm if self.preserve_norm else ranks
+
+    def _krylov_base(self, g, pn, K):
+        """Lanczos basis of the Krylov space of the (symmetric) operator (krylov_space.py:16-41)."""
+        base = [pn / torch.dot(pn, pn) ** 0.5]
+        norms, alphas = [], []
+        for j in range(K):
+            v = base[j]
+            w = g.conv(v)
+            a = torch.dot(v, w)
+            alphas.append(a)
+            nw = w - a * v
+            if j > 0:
+                nw = nw - base[j - 1] * norms[j - 1]
+            nrm = (nw ** 2).sum() ** 0.5
+            norms.append(nrm)
+            if j != K - 1:
+                base.append(nw / nrm)
+        H = torch.diag(torch.stack(alphas))
+        if K > 1:
+            off = torch.stack(norms[1:])
+            # the reference places base_norms[1:] on both off-diagonals (krylov_space.py:39)
+            H = H + torch.diag(off, -1) + torch.diag(off, 1)
+        return torch.stack(base, dim=1), H
+
+    def _krylov_error_bound(self, V, H, g, pn, max_powers: int = 1) -> float:
+        x = pn / torch.dot(pn, pn) ** 0.5
+        res = torch.eye(V.shape[1], dtype=V.dtype, device=V.device)
+        errors = []
+        for power in range(max_powers + 1):
+            approx = (V @ res)[:, 0]
+            errors.append(float((x - approx).abs().sum()) / g.n)      # Mabs (supervised.py:101-106)
+            if power < max_powers:
+                res = res @ H
+                x = g.conv(x)
+        return max(errors)
 
     def _coefficient(self, previous_coefficient, iteration: int) -> float:
         raise Exception("Use a derived class of ClosedFormGraphFilter that implements the _coefficient method")
 
     def _run(self, g, p, norm, warm, **kwargs):
+        if not self._fusable():
+            return self._run_eager(g, p, norm, warm)
         lib = C.lib()
         dtype, code = self.dtype, dtype_code(self.dtype)
         dev, n = p.device, g.n

@@ -798,7 +798,10 @@ def as_device_graph(graph, normalization="auto", renormalize=False, relabel="hub
     if sp.issparse(graph):
         return DeviceGraph.from_scipy(graph, directed=False, normalization=normalization, renormalize=renormalize,
                                       relabel=relabel, device=device)
-    if hasattr(graph, "to_scipy_sparse_array"):               # fastgraph.Graph / AdjacencyWrapper
+    if hasattr(graph, "edge_row") and hasattr(graph, "edge_col") and hasattr(graph, "node_map"):
+        from .ingest import from_fastgraph                   # fastgraph.Graph: its edge lists go to the device as COO
+        return from_fastgraph(graph, normalization=normalization, renormalize=renormalize, relabel=relabel, device=device)
+    if hasattr(graph, "to_scipy_sparse_array"):               # AdjacencyWrapper
         return DeviceGraph.from_scipy(graph.to_scipy_sparse_array(), directed=bool(graph.is_directed()),
                                       normalization=normalization, renormalize=renormalize, relabel=relabel,
                                       device=device, node2id={v: i for i, v in enumerate(graph)}
