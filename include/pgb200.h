@@ -228,13 +228,21 @@ int pgb_hsell_max_block_cols(int dtype);
 /* Pass 1 — one warp per slice: hub_rounds[b*n_slices+s] = rounds (2 entries each) of the unit of
  * slice s in block b, or 0 when the slice has fewer than min_entries + round_cost * rounds entries there
  * (a unit costs about round_cost L1 wavefronts per round plus a partial row, a tail entry one wavefront:
- * sparse units stay in the tail); tail_rounds[s] = longest tail row of the slice. */
+ * sparse units stay in the tail); tail_rounds[w*n_slices+s] = longest tail row of the slice inside tail window w.
+ * TAIL WINDOWS (n_windows <= 16): a slice's tail is cut by where the gathered entry lies in the gather vector,
+ * window w = positions [w*window_len, (w+1)*window_len); the tail stream is window-major, so while the grid sweeps
+ * it only one window of z is live in L2 — what keeps the L2 gathers of a row-partitioned graph (gather vector several
+ * times the L2) from degenerating into 32-byte HBM sectors.  A slice whose longest tail row has fewer than
+ * window_min_rounds entries stays one unit, in the last window (pgb_hsell_fill recognises it by the zero rounds of
+ * its other windows).  n_windows = 1: one unit per slice. */
 int pgb_hsell_count(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
-                    int32_t min_entries, double round_cost, int32_t *hub_rounds, int32_t *tail_rounds, void *stream);
+                    int32_t min_entries, double round_cost, int32_t n_segments, int64_t seg_len, int32_t n_windows,
+                    int64_t window_len, int32_t window_min_rounds, int32_t *hub_rounds, int32_t *tail_rounds,
+                    void *stream);
 /* Pass 2 — writes the round data and piece_row.  The caller supplies, per (block, slice) in
- * block-major order and per slice for the tail: the first round of the unit in its stream and the
- * number of its first piece (exclusive scans), and slice_ptr (first partial row of every slice: the
- * pieces of a slice take consecutive rows, blocks ascending, then the tail).  hub_words must be
+ * block-major order and per (window, slice) in window-major order for the tail: the first round of the unit in its
+ * stream and the number of its first piece (exclusive scans), and slice_ptr (first partial row of every slice: the
+ * pieces of a slice take consecutive rows, blocks ascending, then its tail windows ascending).  hub_words must be
  * pre-filled with the padding word (block_cols | block_cols << 16), tail_cols with -1 and piece_row
  * with the dump row.  scratch (int32[nnz], or NULL) enables the bank-aware slot order:
  * within a unit, entry position p of lane l gets a column of shared-memory bank (l + p) mod banks
@@ -244,7 +252,8 @@ int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int
                    int32_t n_segments, int64_t seg_len, const int32_t *hub_rounds, const int32_t *tail_rounds,
                    const int64_t *hub_round_base, const int64_t *hub_part_base, const int64_t *tail_round_base,
                    const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
-                   int32_t *piece_row, int32_t *scratch, int32_t banks, void *stream);
+                   int32_t *piece_row, int32_t *scratch, int32_t banks, int32_t n_windows, int64_t window_len,
+                   void *stream);
 /* Experiment knob: warps (of 32) per CTA that prefer tail units (L2 gathers) over hub units. */
 int pgb_hsell_set_tail_warps(int warps);
 

@@ -25,6 +25,7 @@ SI_TICKET, SI_STEPS, SI_STOP, SI_ITERATION, SI_MAX_ITERS, SI_END_MODULO, SI_ERR_
 STATE_LEN = 16
 ABI_VERSION = 3
 SIGNATURE_WORDS = 8
+HSELL_MAX_WINDOWS = 16
 HSELL_CHUNK = 32   # PGB_HSELL_CHUNK: rounds per chunk of the hsell streams
 
 
@@ -68,11 +69,11 @@ _SIGNATURES = {
     "pgb_set_kernel_variant": (c_int, [c_int]),
     "pgb_hsell_max_block_cols": (c_int, [c_int]),
     "pgb_hsell_set_tail_warps": (c_int, [c_int]),
-    "pgb_hsell_count": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_void_p, c_void_p,
-                                c_void_p]),
+    "pgb_hsell_count": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_int32, c_int64,
+                                c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "pgb_hsell_fill": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_int32, c_void_p]),
+                               c_void_p, c_int32, c_int32, c_int64, c_void_p]),
     "pgb_build_item_stream": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "pgb_gather_probe": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p]),

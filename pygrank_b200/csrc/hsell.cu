@@ -58,39 +58,6 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t *__restrict__ a, in
     return lo;
 }
 
-__global__ void hsell_count_kernel(int64_t n, int64_t n_slices, const int32_t *__restrict__ indptr,
-                                   const int32_t *__restrict__ indices, int H, int K, int min_entries,
-                                   float round_cost, int32_t *__restrict__ hub_rounds,
-                                   int32_t *__restrict__ tail_rounds) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const unsigned FULL = 0xffffffffu;
-    for (int64_t s = warp; s < n_slices; s += nwarps) {
-        const int64_t row = s * 32 + lane;
-        int b = 0, e = 0;
-        if (row < n) {
-            b = indptr[row];
-            e = indptr[row + 1];
-        }
-        int pos = b, tail_len = 0;
-        for (int blk = 0; blk < K; ++blk) {
-            const int nxt = lower_bound_i32(indices, pos, e, (blk + 1) * H);
-            const int len = nxt - pos;
-            pos = nxt;
-            const int ent = __reduce_add_sync(FULL, len);
-            const int mx = __reduce_max_sync(FULL, len);
-            const int rounds = (mx + 1) / 2;
-            const bool use = ent > 0 && (float)ent >= (float)min_entries + round_cost * (float)rounds;
-            if (lane == 0) hub_rounds[(int64_t)blk * n_slices + s] = use ? rounds : 0;
-            if (!use) tail_len += len;
-        }
-        tail_len += e - pos;
-        const int tmx = __reduce_max_sync(FULL, tail_len);
-        if (lane == 0) tail_rounds[s] = tmx;
-    }
-}
-
 // virtual column (what the builders' CSR is indexed by) -> position in the gather vector
 __device__ __forceinline__ int32_t hsell_real_col(int32_t v, int H, int K, int N, int64_t seg_len) {
     if (N == 1) return v;
@@ -107,6 +74,84 @@ __device__ __forceinline__ int32_t hsell_real_col(int32_t v, int H, int K, int N
     return (int32_t)(rnk * seg_len + (int64_t)K * Hs + off);
 }
 
+constexpr int HS_MAX_WINDOWS = 16;
+
+// Tail window of a virtual column: the tail of a slice is cut by the position of the gathered entry in the gather
+// vector, window w = [w*window_len, (w+1)*window_len).  With the vector of a row-partitioned graph several times the
+// 126 MB L2, all CTAs then sweep the tail stream window by window and the L2 keeps ONE window of z (one rank's range)
+// instead of thrashing on 32-byte sectors of the whole vector.
+__device__ __forceinline__ int hsell_window(int32_t v, int H, int K, int N, int64_t seg_len, int W, int64_t window_len) {
+    if (W == 1) return 0;
+    const int w = (int)((int64_t)hsell_real_col(v, H, K, N, seg_len) / window_len);
+    return w < W ? w : W - 1;
+}
+
+__global__ void hsell_count_kernel(int64_t n, int64_t n_slices, const int32_t *__restrict__ indptr,
+                                   const int32_t *__restrict__ indices, int H, int K, int min_entries,
+                                   float round_cost, int N, int64_t seg_len, int W, int64_t window_len,
+                                   int window_min_rounds, int32_t *__restrict__ hub_rounds,
+                                   int32_t *__restrict__ tail_rounds) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned FULL = 0xffffffffu;
+    for (int64_t s = warp; s < n_slices; s += nwarps) {
+        const int64_t row = s * 32 + lane;
+        int b = 0, e = 0;
+        if (row < n) {
+            b = indptr[row];
+            e = indptr[row + 1];
+        }
+        int pos = b;
+        int tail_len[HS_MAX_WINDOWS];
+#pragma unroll
+        for (int w = 0; w < HS_MAX_WINDOWS; ++w) tail_len[w] = 0;
+        auto to_tail = [&](int from, int to) {
+            if (W == 1) {
+                tail_len[0] += to - from;
+                return;
+            }
+            for (int i = from; i < to; ++i) {
+                const int w = hsell_window(indices[i], H, K, N, seg_len, W, window_len);
+#pragma unroll
+                for (int q = 0; q < HS_MAX_WINDOWS; ++q)
+                    if (q == w) ++tail_len[q];
+            }
+        };
+        for (int blk = 0; blk < K; ++blk) {
+            const int nxt = lower_bound_i32(indices, pos, e, (blk + 1) * H);
+            const int len = nxt - pos;
+            const int ent = __reduce_add_sync(FULL, len);
+            const int mx = __reduce_max_sync(FULL, len);
+            const int rounds = (mx + 1) / 2;
+            const bool use = ent > 0 && (float)ent >= (float)min_entries + round_cost * (float)rounds;
+            if (lane == 0) hub_rounds[(int64_t)blk * n_slices + s] = use ? rounds : 0;
+            if (!use) to_tail(pos, nxt);
+            pos = nxt;
+        }
+        to_tail(pos, e);
+        if (W > 1) {
+            // a slice whose rows hold only a few tail entries stays ONE unit (in the last window): cut into windows
+            // it would pay a padded round per window for a handful of entries; the long tails — hub rows, where
+            // nearly all tail entries are — are the ones worth sweeping window by window
+            int total = 0;
+#pragma unroll
+            for (int w = 0; w < HS_MAX_WINDOWS; ++w) total += tail_len[w];
+            if (__reduce_max_sync(FULL, total) < window_min_rounds) {
+#pragma unroll
+                for (int w = 0; w < HS_MAX_WINDOWS; ++w) tail_len[w] = (w == W - 1) ? total : 0;
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < HS_MAX_WINDOWS; ++w) {
+            if (w < W) {
+                const int tmx = __reduce_max_sync(FULL, tail_len[w]);
+                if (lane == 0) tail_rounds[(int64_t)w * n_slices + s] = tmx;
+            }
+        }
+    }
+}
+
 constexpr int FILL_GROUP = 8;   // hub blocks per work item of the fill kernel
 
 // One warp per (slice, part): part j < NP-1 writes the hub units of blocks [j*FILL_GROUP, (j+1)*FILL_GROUP),
@@ -120,7 +165,8 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                                   const int64_t *__restrict__ tail_round_base,
                                   const int64_t *__restrict__ tail_part_base, const int32_t *__restrict__ slice_ptr,
                                   uint32_t *__restrict__ hub_words, int32_t *__restrict__ tail_cols,
-                                  int32_t *__restrict__ piece_row, int32_t *__restrict__ scratch, int banks) {
+                                  int32_t *__restrict__ piece_row, int32_t *__restrict__ scratch, int banks, int W,
+                                  int64_t window_len) {
     constexpr int CH = PGB_HSELL_CHUNK;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -231,28 +277,44 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
             }
             continue;
         }
-        // ---- the tail of the slice --------------------------------------------------------------------
-        const int TR = tail_rounds[s];
-        const int64_t tg0 = tail_round_base[s];
-        const int64_t tw = tg0 * 32;
-        int pos = b, t = 0;
+        // ---- the tail of the slice: one unit per window (blocks without a unit first, then the columns past the
+        //      hub blocks; a row's entries keep their column order inside every window) ---------------------
+        int t[HS_MAX_WINDOWS];
+#pragma unroll
+        for (int w = 0; w < HS_MAX_WINDOWS; ++w) t[w] = 0;
+        bool collapsed = W > 1;     // the count pass left this slice one tail unit, in the last window
+        for (int w = 0; w + 1 < W; ++w) collapsed = collapsed && tail_rounds[(int64_t)w * n_slices + s] == 0;
+        auto emit = [&](int from, int to) {
+            for (int i = from; i < to; ++i) {
+                const int32_t v = indices[i];
+                const int w = collapsed ? W - 1 : hsell_window(v, H, K, N, seg_len, W, window_len);
+                int tw = 0;
+#pragma unroll
+                for (int q = 0; q < HS_MAX_WINDOWS; ++q)
+                    if (q == w) tw = t[q]++;
+                const int64_t base = tail_round_base[(int64_t)w * n_slices + s] * 32;
+                tail_cols[base + (int64_t)tw * 32 + lane] = hsell_real_col(v, H, K, N, seg_len);
+            }
+        };
+        int pos = b;
         int64_t ord = 0;
         for (int blk = 0; blk < K; ++blk) {
             const int nxt = lower_bound_i32(indices, pos, e, (blk + 1) * H);
             const int np = pieces_of(blk);
             ord += np;
-            if (np == 0) {
-                for (int i = pos; i < nxt; ++i, ++t)
-                    tail_cols[tw + (int64_t)t * 32 + lane] = hsell_real_col(indices[i], H, K, N, seg_len);
-            }
+            if (np == 0) emit(pos, nxt);
             pos = nxt;
         }
-        for (int i = pos; i < e; ++i, ++t) tail_cols[tw + (int64_t)t * 32 + lane] = hsell_real_col(indices[i], H, K, N, seg_len);
-        for (; t < TR; ++t) tail_cols[tw + (int64_t)t * 32 + lane] = -1;
-        if (TR > 0) {
-            const int pieces = (int)((tg0 + TR - 1) / CH - tg0 / CH) + 1;
-            const int64_t p0 = tail_part_base[s];
-            for (int p = lane; p < pieces; p += 32) piece_row[p0 + p] = (int32_t)(first_part + ord + p);
+        emit(pos, e);
+        for (int w = 0; w < W; ++w) {
+            const int TR = tail_rounds[(int64_t)w * n_slices + s];
+            if (TR > 0) {
+                const int64_t tg0 = tail_round_base[(int64_t)w * n_slices + s];
+                const int pieces = (int)((tg0 + TR - 1) / CH - tg0 / CH) + 1;
+                const int64_t p0 = tail_part_base[(int64_t)w * n_slices + s];
+                for (int p = lane; p < pieces; p += 32) piece_row[p0 + p] = (int32_t)(first_part + ord + p);
+                ord += pieces;
+            }
         }
     }
 }
@@ -931,14 +993,21 @@ int pgb_hsell_set_tail_warps(int warps) {
 }
 
 int pgb_hsell_count(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
-                    int32_t min_entries, double round_cost, int32_t *hub_rounds, int32_t *tail_rounds, void *stream) {
+                    int32_t min_entries, double round_cost, int32_t n_segments, int64_t seg_len, int32_t n_windows,
+                    int64_t window_len, int32_t window_min_rounds, int32_t *hub_rounds, int32_t *tail_rounds,
+                    void *stream) {
     if (n <= 0) return 0;
     if (block_cols < 1 || block_cols > 65535) return fail("pgb_hsell_count: block_cols must be in 1..65535");
     if (n_blocks < 0 || (int64_t)n_blocks * block_cols >= (1ll << 31)) return fail("pgb_hsell_count: bad n_blocks");
+    if (n_windows < 1 || n_windows > HS_MAX_WINDOWS || (n_windows > 1 && window_len < 1))
+        return fail("pgb_hsell_count: n_windows must be in 1..%d with a positive window_len", HS_MAX_WINDOWS);
+    if (n_segments < 1 || block_cols % n_segments) return fail("pgb_hsell_count: block_cols must be a multiple of n_segments");
     const int64_t n_slices = ceil_div(n, 32);
     const int grid = stride_grid(n_slices * 32, 256);
     hsell_count_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n_slices, indptr, indices, block_cols, n_blocks,
-                                                            min_entries, (float)round_cost, hub_rounds, tail_rounds);
+                                                            min_entries, (float)round_cost, n_segments, seg_len,
+                                                            n_windows, window_len, window_min_rounds, hub_rounds,
+                                                            tail_rounds);
     PGB_LAUNCH_OK("hsell_count_kernel");
     return 0;
 }
@@ -947,17 +1016,20 @@ int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int
                    int32_t n_segments, int64_t seg_len, const int32_t *hub_rounds, const int32_t *tail_rounds,
                    const int64_t *hub_round_base, const int64_t *hub_part_base, const int64_t *tail_round_base,
                    const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
-                   int32_t *piece_row, int32_t *scratch, int32_t banks, void *stream) {
+                   int32_t *piece_row, int32_t *scratch, int32_t banks, int32_t n_windows, int64_t window_len,
+                   void *stream) {
     if (n <= 0) return 0;
     if (scratch && (banks < 1 || banks > 32 || (banks & (banks - 1)))) return fail("pgb_hsell_fill: banks must be a power of two <= 32");
     if (scratch && block_cols >= 0xffff) return fail("pgb_hsell_fill: bank-aware ordering needs block_cols < 65535");
     if (n_segments < 1 || block_cols % n_segments) return fail("pgb_hsell_fill: block_cols must be a multiple of n_segments");
+    if (n_windows < 1 || n_windows > HS_MAX_WINDOWS || (n_windows > 1 && window_len < 1))
+        return fail("pgb_hsell_fill: n_windows must be in 1..%d with a positive window_len", HS_MAX_WINDOWS);
     const int64_t n_slices = ceil_div(n, 32);
     const int grid = stride_grid(n_slices * 32 * ((n_blocks + FILL_GROUP - 1) / FILL_GROUP + 1), 256);
     hsell_fill_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n_slices, indptr, indices, block_cols, n_blocks, n_segments,
                                                            seg_len, hub_rounds, tail_rounds, hub_round_base, hub_part_base,
                                                            tail_round_base, tail_part_base, slice_ptr, hub_words,
-                                                           tail_cols, piece_row, scratch, banks);
+                                                           tail_cols, piece_row, scratch, banks, n_windows, window_len);
     PGB_LAUNCH_OK("hsell_fill_kernel");
     return 0;
 }

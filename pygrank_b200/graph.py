@@ -92,6 +92,10 @@ def hsell_config() -> dict:
         "round_cost": _env_float("PGB_HSELL_ROUND_COST", 0.0),
         "heavy_parts": min(max(_env_int("PGB_HSELL_HEAVY_PARTS", 32), 1), 32),
         "bank_order": _env_int("PGB_HSELL_BANK_ORDER", 1) != 0,
+        # tail windows: 0 = one window per segment of a row-partitioned gather vector (single GPU: one window);
+        # n > 0 = that many equal windows of the gather vector; -1 = never
+        "tail_windows": _env_int("PGB_HSELL_TAIL_WINDOWS", 0),
+        "tail_window_min": _env_int("PGB_HSELL_TAIL_WINDOW_MIN", 16),   # shorter tails stay one unit
         # 1: pieces are RED.ADDed into one accumulator row per slice and the update pass streams it (fast path);
         # 0: partial rows added in a fixed order (bit-reproducible runs; PGB_DETERMINISTIC=1 selects it too)
         "accumulate": _env_int("PGB_HSELL_ACCUM", 1) != 0 and _env_int("PGB_DETERMINISTIC", 0) == 0,
@@ -177,13 +181,16 @@ def stream_layout(rounds: torch.Tensor, base: int, chunk: int = C.HSELL_CHUNK):
 def hsell_layout(hr: torch.Tensor, tr: torch.Tensor, heavy_parts: int) -> dict:
     """Everything of a pgb_hsell that follows from the unit sizes alone (plain torch, device agnostic; the CPU
     tests run it against a numpy model of the kernels): ``hr`` int64 [K, S] rounds of every hub unit (0 = no
-    unit), ``tr`` int64 [S] tail rounds of every slice.  Streams and pieces as in :func:`stream_layout` (hub
-    stream first); first-level partial rows slice-major (a slice's pieces in block order, then its tail pieces);
+    unit), ``tr`` int64 [S] or [W, S] tail rounds of every slice (per tail window, window-major stream).  Streams and pieces as in :func:`stream_layout` (hub
+    stream first); first-level partial rows slice-major (a slice's pieces in block order, then its tail pieces, windows
+    ascending);
     slices with more than ``heavy_parts`` pieces reduced in groups of 32 consecutive rows into second-level
     rows stored after the first level; one dump row at the very end for the padding pieces."""
     i64 = torch.int64
     dev = tr.device
-    K, S = int(hr.shape[0]), int(tr.shape[0])
+    tr = tr.reshape(1, -1) if tr.dim() == 1 else tr              # [W, S]: one tail unit per (window, slice)
+    W, S = int(tr.shape[0]), int(tr.shape[1])
+    K = int(hr.shape[0])
     if K > 0:
         hub_g0, hub_p0, hub_pieces, hub_chunks, n_hub_chunks, n_hub_parts, bcb = stream_layout(hr, 0)
     else:
@@ -192,9 +199,9 @@ def hsell_layout(hr: torch.Tensor, tr: torch.Tensor, heavy_parts: int) -> dict:
         hub_chunks = torch.zeros((1, 2), dtype=torch.int32, device=dev)
         n_hub_chunks = n_hub_parts = 0
         bcb = torch.zeros(1, dtype=i64, device=dev)
-    tail_g0, tail_p0, tail_pieces, tail_chunks, n_tail_chunks, n_tail_parts, _ = stream_layout(tr.view(1, S), n_hub_parts)
+    tail_g0, tail_p0, tail_pieces, tail_chunks, n_tail_chunks, n_tail_parts, _ = stream_layout(tr, n_hub_parts)
     n_pieces = n_hub_parts + n_tail_parts                       # pieces in stream order (hub stream, then tail)
-    per_slice = tail_pieces + (hub_pieces.view(K, S).sum(0) if K > 0 else 0)
+    per_slice = tail_pieces.view(W, S).sum(0) + (hub_pieces.view(K, S).sum(0) if K > 0 else 0)
     slice_ptr64 = torch.zeros(S + 1, dtype=i64, device=dev)
     torch.cumsum(per_slice, 0, out=slice_ptr64[1:])
     n_rows1 = int(slice_ptr64[-1])                              # first-level partial rows, slice-major
@@ -245,13 +252,24 @@ class HsellForm:
         H, K = hsell_shape(dtype, n_segments, seg_len, cfg)
         S = (n + 31) // 32
         CH = C.HSELL_CHUNK
+        total_cols = n_segments * seg_len
+        tw = cfg["tail_windows"]
+        if tw > 0:
+            W = min(tw, C.HSELL_MAX_WINDOWS)
+            window_len = -(-total_cols // W)
+        elif tw == 0 and n_segments > 1:
+            W, window_len = min(n_segments, C.HSELL_MAX_WINDOWS), -(-total_cols // min(n_segments, C.HSELL_MAX_WINDOWS))
+        else:
+            W, window_len = 1, max(total_cols, 1)
         hub_rounds = torch.zeros(max(K * S, 1), dtype=torch.int32, device=dev)
-        tail_rounds = torch.zeros(max(S, 1), dtype=torch.int32, device=dev)
+        tail_rounds = torch.zeros(max(W * S, 1), dtype=torch.int32, device=dev)
         C.check(lib.pgb_hsell_count(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, cfg["min_entries"],
-                                    float(cfg["round_cost"]), C.ptr(hub_rounds), C.ptr(tail_rounds), st))
+                                    float(cfg["round_cost"]), n_segments, seg_len, W, window_len,
+                                    int(cfg["tail_window_min"]), C.ptr(hub_rounds), C.ptr(tail_rounds), st))
 
         hr = hub_rounds[:K * S].to(i64).view(K, S) if K > 0 else torch.zeros((0, S), dtype=i64, device=dev)
-        lay = hsell_layout(hr, tail_rounds[:S].to(i64), cfg["heavy_parts"])
+        lay = hsell_layout(hr, tail_rounds[:W * S].to(i64).view(W, S), cfg["heavy_parts"])
+        self.n_windows, self.window_len = W, window_len
         hub_g0, hub_p0, tail_g0, tail_p0 = lay["hub_g0"], lay["hub_p0"], lay["tail_g0"], lay["tail_p0"]
         self.hub_chunks, self.tail_chunks = lay["hub_chunks"], lay["tail_chunks"]
         n_hub_chunks, n_tail_chunks, bcb = lay["n_hub_chunks"], lay["n_tail_chunks"], lay["block_chunk_begin"]
@@ -273,7 +291,7 @@ class HsellForm:
                                    C.ptr(hub_rounds), C.ptr(tail_rounds), C.ptr(hub_g0), C.ptr(hub_p0),
                                    C.ptr(tail_g0), C.ptr(tail_p0), C.ptr(self.slice_ptr), C.ptr(self.hub_words),
                                    C.ptr(self.tail_cols), C.ptr(self.piece_row), C.ptr(scratch),
-                                   32 if dtype == torch.float32 else 16, st))
+                                   32 if dtype == torch.float32 else 16, W, window_len, st))
         del scratch
         # slice of every piece (accumulate mode): first-level rows are slice-major, padding pieces -> row n_slices
         ps = torch.searchsorted(lay["slice_ptr"].to(i64), self.piece_row.to(i64), right=True) - 1

@@ -12,8 +12,10 @@ pytestmark = pytest.mark.gpu
 FP64_TOL = 1e-10
 FP32_TOL = 1e-5
 
-# (block_cols, max_blocks, min_entries, heavy_parts): tiny blocks -> many blocks + a real tail + heavy slices
-SHAPES = [(64, 3, 1, 2), (128, 16, 16, 32), (256, 2, 40, 1), (0, 16, 16, 32)]
+# (block_cols, max_blocks, min_entries, heavy_parts[, tail_windows, tail_window_min]): tiny blocks -> many blocks + a
+# real tail + heavy slices; the last two cut the tail into windows of the gather vector (with / without the
+# short-tail exemption)
+SHAPES = [(64, 3, 1, 2), (128, 16, 16, 32), (256, 2, 40, 1), (0, 16, 16, 32), (64, 3, 1, 2, 4, 0), (128, 4, 16, 32, 3, 6)]
 
 
 @pytest.fixture(scope="module")
@@ -26,7 +28,8 @@ def pgb():
 
 
 def _set_shape(monkeypatch, shape):
-    names = ["PGB_HSELL_BLOCK_COLS", "PGB_HSELL_BLOCKS", "PGB_HSELL_MIN_ENTRIES", "PGB_HSELL_HEAVY_PARTS"]
+    names = ["PGB_HSELL_BLOCK_COLS", "PGB_HSELL_BLOCKS", "PGB_HSELL_MIN_ENTRIES", "PGB_HSELL_HEAVY_PARTS",
+             "PGB_HSELL_TAIL_WINDOWS", "PGB_HSELL_TAIL_WINDOW_MIN"]
     for k, v in zip(names, shape):
         monkeypatch.setenv(k, str(v))
 

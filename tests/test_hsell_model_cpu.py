@@ -15,46 +15,58 @@ from pygrank_b200.graph import hsell_layout
 CH = 32
 
 
-def count_np(indptr, indices, n, H, K, min_entries):
+def count_np(indptr, indices, n, H, K, min_entries, W=1, window_of=lambda v: 0, window_min=0):
     """hsell_count_kernel: rounds of the unit of (slice, block) — 0 when the slice has fewer than
-    ``min_entries`` entries there — and the tail rounds of every slice."""
+    ``min_entries`` entries there — and the tail rounds of every slice in every tail window (``window_of`` maps a
+    virtual column to its window)."""
     S = (n + 31) // 32
     hub = np.zeros((K, S), dtype=np.int64)
-    tail = np.zeros(S, dtype=np.int64)
+    tail = np.zeros((W, S), dtype=np.int64)
     for s in range(S):
         lens = np.zeros((32, K + 1), dtype=np.int64)
+        rows = []
         for lane in range(32):
             r = s * 32 + lane
-            if r >= n:
-                continue
-            cols = indices[indptr[r]:indptr[r + 1]]
+            cols = indices[indptr[r]:indptr[r + 1]] if r < n else indices[:0]
+            rows.append(cols)
             blk = np.minimum(cols // H, K)
             lens[lane] = np.bincount(blk, minlength=K + 1)
-        tail_len = lens[:, K].copy()
+        unit = np.zeros(K + 1, dtype=bool)
         for b in range(K):
             ent, mx = lens[:, b].sum(), lens[:, b].max()
             if ent >= min_entries and ent > 0:
                 hub[b, s] = (mx + 1) // 2
-            else:
-                tail_len += lens[:, b]
-        tail[s] = tail_len.max()
-    return hub, tail
+                unit[b] = True
+        tail_len = np.zeros((32, W), dtype=np.int64)
+        for lane, cols in enumerate(rows):
+            for c in cols[~unit[np.minimum(cols // H, K)]]:
+                tail_len[lane, window_of(c)] += 1
+        if W > 1 and tail_len.sum(axis=1).max() < window_min:   # short tails stay one unit, in the last window
+            total = tail_len.sum(axis=1)
+            tail_len[:] = 0
+            tail_len[:, W - 1] = total
+        tail[:, s] = tail_len.max(axis=0)
+    return (hub, tail[0]) if W == 1 else (hub, tail)
 
 
-def fill_np(indptr, indices, n, H, K, hub, tail, lay, real_col=lambda v: v):
+def fill_np(indptr, indices, n, H, K, hub, tail, lay, real_col=lambda v: v, W=1, window_of=lambda v: 0):
     """hsell_fill_kernel without the bank-aware order: round data [round][lane] and piece_row.  ``real_col``
-    maps the (virtual) columns of the tail to positions in the gather vector (hsell_real_col)."""
+    maps the (virtual) columns of the tail to positions in the gather vector (hsell_real_col); the tail of a slice
+    is one unit per window."""
     S = (n + 31) // 32
+    tail = np.asarray(tail).reshape(W, S)
     hub_words = np.full((lay["n_hub_chunks"] * CH * 32, 2), H, dtype=np.int64)      # (lo, hi) per word
     tail_cols = np.full(lay["n_tail_chunks"] * CH * 32, -1, dtype=np.int64)
     piece_row = np.full(max(lay["n_pieces"], 1), lay["dump_row"], dtype=np.int64)
     hub_g0 = lay["hub_g0"].numpy().reshape(K, S) if K else None
     hub_p0 = lay["hub_p0"].numpy().reshape(K, S) if K else None
-    tail_g0, tail_p0 = lay["tail_g0"].numpy(), lay["tail_p0"].numpy()
+    tail_g0, tail_p0 = lay["tail_g0"].numpy().reshape(W, S), lay["tail_p0"].numpy().reshape(W, S)
     slice_ptr = lay["slice_ptr"].numpy().astype(np.int64)
     for s in range(S):
         ord_ = 0
-        t = np.zeros(32, dtype=np.int64)
+        t = np.zeros((32, W), dtype=np.int64)
+        collapsed = W > 1 and not tail[:W - 1, s].any()
+        win = (lambda c: W - 1) if collapsed else window_of
         for b in range(K):
             R = hub[b, s]
             for lane in range(32):
@@ -68,10 +80,10 @@ def fill_np(indptr, indices, n, H, K, hub, tail, lay, real_col=lambda v: v):
                     for i, c in enumerate(mine):
                         hub_words[(g0 + i // 2) * 32 + lane, i % 2] = c - b * H
                 else:
-                    tg0 = tail_g0[s]
                     for c in mine:
-                        tail_cols[(tg0 + t[lane]) * 32 + lane] = real_col(c)
-                        t[lane] += 1
+                        w = win(c)
+                        tail_cols[(tail_g0[w, s] + t[lane, w]) * 32 + lane] = real_col(c)
+                        t[lane, w] += 1
             if R > 0:
                 g0 = hub_g0[b, s]
                 pieces = (g0 + R - 1) // CH - g0 // CH + 1
@@ -83,13 +95,16 @@ def fill_np(indptr, indices, n, H, K, hub, tail, lay, real_col=lambda v: v):
                 continue
             cols = indices[indptr[r]:indptr[r + 1]]
             for c in cols[cols // H >= K]:
-                tail_cols[(tail_g0[s] + t[lane]) * 32 + lane] = real_col(c)
-                t[lane] += 1
-        TR = tail[s]
-        if TR > 0:
-            tg0 = tail_g0[s]
-            pieces = (tg0 + TR - 1) // CH - tg0 // CH + 1
-            piece_row[tail_p0[s]:tail_p0[s] + pieces] = slice_ptr[s] + ord_ + np.arange(pieces)
+                w = win(c)
+                tail_cols[(tail_g0[w, s] + t[lane, w]) * 32 + lane] = real_col(c)
+                t[lane, w] += 1
+        for w in range(W):
+            TR = tail[w, s]
+            if TR > 0:
+                tg0 = tail_g0[w, s]
+                pieces = (tg0 + TR - 1) // CH - tg0 // CH + 1
+                piece_row[tail_p0[w, s]:tail_p0[w, s] + pieces] = slice_ptr[s] + ord_ + np.arange(pieces)
+                ord_ += pieces
     return hub_words, tail_cols, piece_row
 
 
@@ -194,14 +209,27 @@ def test_model_row_partitioned_form(world, H, K):
                        shape=(n_local, max(int(v.max()) + 1, n_global))).tocsr()
     Av.sort_indices()
     indptr, vidx = Av.indptr.astype(np.int64), Av.indices.astype(np.int64)
-    hub, tail = count_np(indptr, vidx, n_local, H, K, 8)
-    lay = hsell_layout(torch.from_numpy(hub), torch.from_numpy(tail), 4)
-
     def real_col(vc):
         return int(real_columns(torch.tensor([vc]), n_local, world, H, K)[0])
 
-    hub_words, tail_cols, piece_row = fill_np(indptr, vidx, n_local, H, K, hub, tail, lay, real_col)
-    assert (hub_words != H).sum() + (tail_cols >= 0).sum() == A.nnz
     z = rng.uniform(0.5, 1.5, n_global)
-    y = execute_np(n_local, H, K, lay, hub_words, tail_cols, piece_row, z, n_segments=world, seg_len=n_local)
-    assert np.allclose(y, A @ z, rtol=1e-12, atol=0)
+    # one tail unit per slice, then one per (owner segment, slice): the tail stream is then window-major
+    for W, wmin in ((1, 0), (world, 0), (world, 12)):
+        window_of = (lambda v: 0) if W == 1 else (lambda v: min(real_col(v) // n_local, W - 1))
+        hub, tail = count_np(indptr, vidx, n_local, H, K, 8, W, window_of, wmin)
+        lay = hsell_layout(torch.from_numpy(hub), torch.from_numpy(tail), 4)
+        hub_words, tail_cols, piece_row = fill_np(indptr, vidx, n_local, H, K, hub, tail, lay, real_col, W, window_of)
+        assert (hub_words != H).sum() + (tail_cols >= 0).sum() == A.nnz
+        y = execute_np(n_local, H, K, lay, hub_words, tail_cols, piece_row, z, n_segments=world, seg_len=n_local)
+        assert np.allclose(y, A @ z, rtol=1e-12, atol=0)
+        if W > 1 and wmin == 0 and lay["n_tail_chunks"] > 1:
+            # window-major: the windows of the gathered positions never decrease along the tail stream
+            flat = tail_cols[tail_cols >= 0]
+            order = np.nonzero(tail_cols >= 0)[0]
+            win = flat // n_local
+            first_chunk = {}
+            for pos, w_ in zip(order // (CH * 32), win):
+                first_chunk.setdefault(int(w_), int(pos))
+                assert pos >= first_chunk[int(w_)]
+            starts = [first_chunk[k] for k in sorted(first_chunk)]
+            assert starts == sorted(starts)
