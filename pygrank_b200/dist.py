@@ -373,6 +373,16 @@ class DistPageRank:
         st = C.stream_ptr()
         t0 = time.perf_counter()
         n_loc, off = g.n_local, g.offset
+        timing = os.environ.get("PGB_DIST_TIMING", "0") == "1"     # phase breakdown of one solve (CUDA events)
+        marks = []
+
+        def mark(name):
+            if timing:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev, time.perf_counter()))
+
+        mark("start")
         if p_local is None:
             p, norm = self.local_personalization(g, seeds, values)
         else:
@@ -426,6 +436,7 @@ class DistPageRank:
         kernels_per_step = g.view.kernels_per_step(dtype, form is not None)
         acc = state_f64[C.SF_TACC:C.SF_EACC + 1]
 
+        mark("init")
         budget, done = self.max_iters - 1, 0
         stop, steps, iteration = C.RUNNING, 0, 1
         # run-ahead chunk: a previous solve on this graph is the best guess of how many steps this one needs,
@@ -468,12 +479,19 @@ class DistPageRank:
         self.errors = err_hist[1:steps + 1]
         if stop == C.MAX_ITERS and err_code != C.ERR_ITERS:
             raise Exception("Could not converge within " + str(self.max_iters) + " iterations")
+        mark("loop")
         if peer is not None:
             peer["hz"].barrier(channel=1)   # nobody starts the next solve (overwriting buffer 0) before all have read
         result = torch.empty(n_loc, dtype=dtype, device=dev)
         zl = zfull[steps & 1][off:off + n_loc]
         C.check(lib.pgb_unscale(n_loc, code, C.ptr(zl.contiguous()), C.ptr(sq), None, norm, None, C.ptr(result), st))
         C.count_launches(1)
+        mark("end")
+        if timing:
+            torch.cuda.synchronize()
+            self.timing = {"steps": steps, "launched": done,
+                           "gpu_ms": {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])},
+                           "host_ms": {b[0]: (b[2] - a[2]) * 1e3 for a, b in zip(marks, marks[1:])}}
         self.elapsed_time = time.perf_counter() - t0
         return result
 

@@ -83,6 +83,8 @@ def run(args):
         return calls
 
     dev_ms, conv_calls = timed(resident)
+    if os.environ.get("PGB_DIST_TIMING", "0") == "1" and rank == 0:
+        print("DIST TIMING", json.dumps(getattr(alg, "timing", None)), flush=True)
     launches = C.LAUNCHES[0] - launches0
     value = g.nnz_global * conv_calls / (dev_ms * 1e-3) / 1e9
 
