@@ -217,3 +217,26 @@ def test_plugin_route_eager_fallbacks_stay_correct(pg):
     for cname, ((ref, it_ref), (got, it_got)) in results.items():
         assert it_ref == it_got, (cname, it_ref, it_got)
         assert rel_l1(got, ref) <= 1e-10, cname
+
+
+def test_parameter_tuner_runs_unchanged_on_b200(pg):
+    """pg.ParameterTuner (algorithms/autotune/parameterized.py:117-167 with optimization.py's line search) evaluates
+    its candidates through the fused runs on the b200 backend and lands on the parameters the numpy backend finds."""
+    z, A, directed = load_golden("ba2000")
+    rng = np.random.default_rng(0)
+    n = A.shape[0]
+    members = rng.choice(n, 200, replace=False)
+    found = {}
+    for backend in ["numpy", "b200"]:
+        pg.load_backend(backend)
+        graph = pg.AdjacencyWrapper(A, directed=directed)
+        signal = pg.to_signal(graph, {int(v): 1.0 for v in members})
+        pre = pg.preprocessor(normalization="symmetric", assume_immutability=True)
+        tuner = pg.ParameterTuner(lambda params: pg.PageRank(params[0], preprocessor=pre, tol=1e-9, max_iters=1000),
+                                  max_vals=[0.99], min_vals=[0.5], measure=pg.AUC, deviation_tol=0.01,
+                                  tuning_backend=backend)
+        ranks = tuner(graph, signal)
+        found[backend] = (list(tuner.last_params), np.asarray(ranks.np if backend == "numpy" else ranks.np.cpu().numpy()))
+    pg.load_backend("numpy")
+    assert found["numpy"][0] == pytest.approx(found["b200"][0], abs=1e-9)
+    assert rel_l1(found["b200"][1], found["numpy"][1]) <= 1e-9
