@@ -343,6 +343,10 @@ int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *
                          const void *q, void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64,
                          int32_t *state_i32, double *err_hist, pgb_span_ws ws, int step, const pgb_peers *peers,
                          void *stream);
+/* pgb_poly_steps for ONE step with the same fused exchange (closed-form filters on a row-partitioned graph). */
+int pgb_poly_step_peer(const pgb_csr *g, int dtype, const void *w, const void *sq, const double *coef, void *ranks,
+                       void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64, int32_t *state_i32,
+                       double *err_hist, pgb_span_ws ws, int step, const pgb_peers *peers, void *stream);
 /* pgb_affine_init whose start vector z0 (this rank's rows) is written into buffer 0 of EVERY rank — replaces
  * the all-gather of the start vector; the caller puts a cross-device barrier before the first step. */
 int pgb_affine_init_peer(int64_t n, int dtype, const void *p, const void *warm, const void *sq, const void *c,

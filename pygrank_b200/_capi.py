@@ -110,6 +110,8 @@ _SIGNATURES = {
     "pgb_affine_step_peer": (c_int, [POINTER(Csr), c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, POINTER(Peers),
                                      c_void_p]),
+    "pgb_poly_step_peer": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, POINTER(Peers), c_void_p]),
     "pgb_state_finalize_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "pgb_affine_init_peer": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
                                      c_void_p, c_int64, c_void_p, c_void_p, POINTER(Peers), c_void_p]),

@@ -584,6 +584,48 @@ int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *
     return dispatch<MODE_AFFINE>(P, dtype, symdeg, as_stream(stream));
 }
 
+// pgb_poly_steps for ONE step with the exchange fused into it (see pgb_affine_step_peer).
+int pgb_poly_step_peer(const pgb_csr *g, int dtype, const void *w, const void *sq, const double *coef, void *ranks,
+                       void *zbuf0, void *zbuf1, int64_t out_offset, double *state_f64, int32_t *state_i32,
+                       double *err_hist, pgb_span_ws ws, int step, const pgb_peers *peers, void *stream) {
+    StepParams P;
+    memset(&P, 0, sizeof(P));
+    if (fill_graph(P, g)) return 1;
+    if (P.n == 0) return 0;
+    if (!peers || peers->n < 1 || peers->n > PGB_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->n)
+        return fail("pgb_poly_step_peer: bad peer description");
+    const bool symdeg = (w == nullptr && sq == nullptr);
+    if (!symdeg && (!w || !sq)) return fail("pgb_poly_step_peer: w and sq must both be given or both be NULL");
+    if (symdeg && g->values) return fail("pgb_poly_step_peer: degree-derived scales need an unweighted graph");
+    if (step < 1) return fail("pgb_poly_step_peer: step must be >= 1");
+    P.w = w;
+    P.sq = sq;
+    P.coef = coef;
+    P.ranks = ranks;
+    P.out_offset = out_offset;
+    P.sf = state_f64;
+    P.si = state_i32;
+    P.err_hist = err_hist;
+    P.span_acc = ws.acc;
+    P.span_cnt = ws.cnt;
+    P.partials = ws.partials;
+    P.yacc = ws.yacc;
+    P.finalize = 0;
+    void *buf[2] = {zbuf0, zbuf1};
+    P.zin = buf[(step - 1) & 1];
+    P.zout = buf[step & 1];
+    P.n_peers = peers->n;
+    P.peer_rank = peers->rank;
+    for (int r = 0; r < peers->n; ++r) {
+        P.peer_zout[r] = (step & 1) ? peers->zbuf1[r] : peers->zbuf0[r];
+        P.peer_acc[r] = peers->acc[r];
+        if (!P.peer_zout[r] || !P.peer_acc[r]) return fail("pgb_poly_step_peer: peer %d has no buffer", r);
+    }
+    P.mc_zout = (step & 1) ? peers->mc_zbuf1 : peers->mc_zbuf0;
+    P.peer_mask = peers->row_mask;
+    return dispatch<MODE_POLY>(P, dtype, symdeg, as_stream(stream));
+}
+
 __global__ void state_finalize_peer_kernel(double *sf, int32_t *si, double *err_hist, const double *slots, int n) {
     if (si[PGB_SI_STOP] != PGB_RUNNING) return;
     double t = 0.0, e = 0.0;

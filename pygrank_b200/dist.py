@@ -126,9 +126,12 @@ class DistGraph:
         self.rank = self.world = 0
         self.n_global = self.n_local = self.n_nodes = 0
         self.nnz_local = self.nnz_global = 0
-        self.view = None            # CsrView: local rows x global columns
+        self.view = None            # CsrView: local rows x global columns (pull structure: sources of every local node)
+        self.out_view = None        # directed graphs: CsrView of the targets of every local node (None: same as view)
         self.new_id = None          # int32[n_nodes]: user node -> internal id
         self.group = None
+        self.directed = False
+        self.normalization = "symmetric"
         self._cache = {}
 
     @property
@@ -197,6 +200,102 @@ class DistGraph:
         dist.all_reduce(tot, group=group)
         g.nnz_global = int(tot.item())
         return g
+
+    @staticmethod
+    def from_edges(n: int, src: torch.Tensor, dst: torch.Tensor, directed: bool = False, normalization: str = "auto",
+                   group=None) -> "DistGraph":
+        """An arbitrary unweighted graph, row-partitioned: every rank passes the SAME edge list (device tensors,
+        user node ids; an undirected edge named once) and keeps the pull rows of the nodes it owns — for a directed
+        graph also their push rows, which the row sums of the normalised operator need.  Normalisations as in
+        preprocessing.py:101-138 ("auto": col when directed, else symmetric), kept factorised like DeviceGraph."""
+        from .graph import CsrView, build_csr, _SCALE_KINDS
+        g = DistGraph()
+        g.group = group
+        g.rank, g.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = src.device
+        g.n_nodes = int(n)
+        g.n_global = padded_size(g.n_nodes, g.world)
+        g.n_local = g.n_global // g.world
+        g.directed = bool(directed)
+        normalization = normalization.lower()
+        if normalization == "auto":
+            normalization = "col" if directed else "symmetric"
+        if normalization not in _SCALE_KINDS or normalization == "laplacian":
+            raise Exception("row-partitioned graphs support the normalizations none, col, symmetric, both, auto")
+        g.normalization = normalization
+        s64, d64 = src.long(), dst.long()
+        if not directed:                                  # both directions, self loops once
+            loops = s64 == d64
+            s64, d64 = torch.cat([s64, d64[~loops]]), torch.cat([d64, s64[~loops]])
+        # canonical entry set (duplicates collapse: unweighted)
+        key = torch.unique(s64 * g.n_nodes + d64)
+        s64, d64 = key // g.n_nodes, key % g.n_nodes
+        del key
+        rowsum = torch.bincount(s64, minlength=g.n_global)          # out-degree (row sums of the adjacency)
+        colsum = torch.bincount(d64, minlength=g.n_global)          # in-degree
+        full_id = interleaved_ids((rowsum + colsum).to(torch.int32), g.world)
+        g.new_id = full_id[: g.n_nodes].contiguous()
+        lo = g.rank * g.n_local
+        u, v = full_id[s64].long(), full_id[d64].long()              # entry a_uv: u -> v
+        mine = (v >= lo) & (v < lo + g.n_local)                      # pull row of v lists its sources u
+        indptr, indices, _ = build_csr(g.n_global, (v[mine] - lo).to(torch.int32), u[mine].to(torch.int32), None,
+                                       C.BUILD_BINARY)
+        g.view = CsrView(g.n_local, indptr[: g.n_local + 1].clone(), indices, None)
+        if directed:
+            own = (u >= lo) & (u < lo + g.n_local)                   # push row of u lists its targets v
+            ip, ix, _ = build_csr(g.n_global, (u[own] - lo).to(torch.int32), v[own].to(torch.int32), None, C.BUILD_BINARY)
+            g.out_view = CsrView(g.n_local, ip[: g.n_local + 1].clone(), ix, None)
+        inv = torch.empty(g.n_global, dtype=torch.int64, device=dev)
+        inv[full_id.long()] = torch.arange(g.n_global, device=dev)
+        mine_nodes = inv[lo: lo + g.n_local]                          # padded-user id of every local row
+        g._cache[("rowsum", torch.float64)] = rowsum[mine_nodes].to(torch.float64)
+        g._cache[("colsum", torch.float64)] = colsum[mine_nodes].to(torch.float64)
+        g.user_of_local = mine_nodes
+        g.nnz_local = g.view.nnz
+        tot = torch.tensor([g.nnz_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, group=group)
+        g.nnz_global = int(tot.item())
+        return g
+
+    @staticmethod
+    def from_scipy(A, directed: bool = False, normalization: str = "auto", group=None, device=None) -> "DistGraph":
+        """A host scipy adjacency every rank holds (what pg.AdjacencyWrapper carries); must be unweighted."""
+        import scipy.sparse as sp
+        A = sp.coo_matrix(A)
+        if not bool(np.all(A.data == 1.0)):
+            raise Exception("row-partitioned graphs are unweighted (weighted graphs: single-GPU DeviceGraph)")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        src = torch.from_numpy(A.row.astype(np.int64)).to(dev)
+        dst = torch.from_numpy(A.col.astype(np.int64)).to(dev)
+        if not directed:                                   # stored symmetric: name every edge once
+            once = src <= dst
+            src, dst = src[once], dst[once]
+        return DistGraph.from_edges(A.shape[0], src, dst, directed=directed, normalization=normalization, group=group)
+
+    @property
+    def symdeg(self) -> bool:
+        """Scales derivable from the local row pointers inside the kernels (undirected, symmetric normalisation)."""
+        return (not self.directed) and self.normalization == "symmetric"
+
+    def local_vector(self, dense, dtype: torch.dtype) -> torch.Tensor:
+        """This rank's slice (internal order) of a dense vector in USER node order (host array or device tensor)."""
+        dev = self.view.indptr.device
+        x = torch.as_tensor(dense).to(device=dev, dtype=dtype).reshape(-1)
+        if x.numel() != self.n_nodes:
+            raise Exception("Graph signal array dimensions " + str(x.numel()) + " should be equal to graph nodes " + str(self.n_nodes))
+        if self.n_global != self.n_nodes:
+            x = torch.cat([x, torch.zeros(self.n_global - self.n_nodes, dtype=dtype, device=dev)])
+        return x[self._user_of_local()].contiguous()
+
+    def _user_of_local(self) -> torch.Tensor:
+        if getattr(self, "user_of_local", None) is None:
+            dev = self.view.indptr.device
+            full = torch.full((self.n_global,), -1, dtype=torch.int64, device=dev)
+            full[self.new_id.long()] = torch.arange(self.n_nodes, device=dev)
+            pad = torch.nonzero(full < 0).reshape(-1)
+            full[pad] = torch.arange(self.n_nodes, self.n_nodes + pad.numel(), device=dev)
+            self.user_of_local = full[self.offset: self.offset + self.n_local]
+        return self.user_of_local
 
     def hsell(self, dtype: torch.dtype):
         """Hub-blocked sliced-ELL form of this rank's rows (csrc/hsell.cu) against the all-gathered
@@ -302,6 +401,21 @@ class DistGraph:
         self._cache[key] = out
         return out
 
+    def push_sum(self, right_local: torch.Tensor) -> torch.Tensor:
+        """L_i * sum_{k: i -> k} right_k for the local nodes i (fp64): one all-gather of the local factors and one plain
+        gather pass over the push structure.  Row sums of M (right = R) and of M diag(d) (right = R o d)."""
+        from .graph import dtype_code, span_struct
+        lib = C.lib()
+        f64 = torch.float64
+        full = torch.empty(self.n_global, dtype=f64, device=self.view.indptr.device)
+        dist.all_gather_into_tensor(full, right_local.to(f64).contiguous(), group=self.group)
+        out = torch.empty(self.n_local, dtype=f64, device=full.device)
+        view = self.out_view if self.out_view is not None else self.view
+        cs = view.cstruct(f64, hsell=False)
+        C.check(lib.pgb_spmv(ctypes.byref(cs), dtype_code(f64), C.ptr(full), C.ptr(self.vec("L", f64)), None, None,
+                             C.ptr(out), span_struct(view.span_ws()), C.stream_ptr()))
+        return out
+
     # per-dtype node vectors for the local rows ------------------------------------------------
     def vec(self, name: str, dtype: torch.dtype) -> torch.Tensor:
         from .graph import dtype_code, span_struct
@@ -311,22 +425,28 @@ class DistGraph:
         f64 = torch.float64
         if dtype != f64:
             out = self.vec(name, f64).to(dtype)
-        elif name == "deg":
+        elif name == "rowsum":                               # out-degree of the local nodes (undirected: the degree)
             out = (self.view.indptr[1:] - self.view.indptr[:-1]).to(f64)
-        elif name == "sq":                                   # 1/L with L = 1/sqrt(deg), deg 0 -> 1
-            d = self.vec("deg", f64)
-            out = torch.where(d > 0, torch.sqrt(d), torch.ones_like(d))
-        elif name == "R":                                    # 1/sqrt(deg), zeros kept (preprocessing.py:133-136)
-            d = self.vec("deg", f64)
-            out = torch.where(d > 0, 1.0 / torch.sqrt(d), torch.zeros_like(d))
-        elif name == "degM":                                 # row sums of the normalised matrix
-            lib = C.lib()
-            r_full = torch.empty(self.n_global, dtype=f64, device=self.view.indptr.device)
-            dist.all_gather_into_tensor(r_full, self.vec("R", f64).contiguous(), group=self.group)
-            out = torch.empty(self.n_local, dtype=f64, device=r_full.device)
-            cs = self.view.cstruct(f64, hsell=False)
-            C.check(lib.pgb_spmv(ctypes.byref(cs), dtype_code(f64), C.ptr(r_full), C.ptr(self.vec("R", f64)), None,
-                                 None, C.ptr(out), span_struct(self.view.span_ws()), C.stream_ptr()))
+        elif name == "colsum":
+            out = self.vec("rowsum", f64)
+        elif name in ("L", "R"):                             # preprocessing.py:109-138, zeros kept (S[S != 0] = 1/S)
+            from .graph import _SCALE_KINDS
+            kind = _SCALE_KINDS[self.normalization][0 if name == "L" else 1]
+            d = self.vec("rowsum" if name == "L" else "colsum", f64)
+            if kind == C.SCALE_ONE:
+                out = torch.ones_like(d)
+            else:
+                base = torch.sqrt(d) if kind == C.SCALE_RSQRT else d
+                out = torch.where(base != 0, 1.0 / torch.where(base != 0, base, torch.ones_like(base)), torch.zeros_like(base))
+        elif name == "Lp":
+            L = self.vec("L", f64)
+            out = torch.where(L == 0, torch.ones_like(L), L)
+        elif name == "w":
+            out = self.vec("Lp", f64) * self.vec("R", f64)
+        elif name == "sq":
+            out = 1.0 / self.vec("Lp", f64)
+        elif name == "degM":                                 # row sums of the normalised matrix: L_i * sum_k a_ik R_k
+            out = self.push_sum(self.vec("R", f64))
         elif name == "c":
             out = self.vec("sq", f64) * self.vec("degM", f64)
         else:
@@ -335,19 +455,22 @@ class DistGraph:
         return out
 
 
-class DistPageRank:
-    """``pg.PageRank`` semantics (adhoc.py:34-36 + abstract_filters.py:44-65,126-136 +
-    convergence.py:77-101) on a :class:`DistGraph`.  Every rank calls ``rank`` collectively."""
+class DistFilter:
+    """Driver shared by the row-partitioned filters: the reference's rank() prologue (abstract_filters.py:44-65) on this
+    rank's slice, then one fused step per iteration with the exchange inside the update kernel (symmetric memory) or
+    an NCCL all-gather after it, the convergence test of convergence.py:77-101 decided identically on every rank from
+    the rank-ordered sums, and the run-ahead / read-back loop of the single-GPU filters.  Every rank calls ``rank``
+    collectively and gets its slice of the scores (internal id order, ``g.offset`` onwards)."""
 
-    def __init__(self, alpha: float = 0.85, tol: Optional[float] = 1e-6, max_iters: int = 100, end_modulo: int = 1,
-                 error_type: str = "mabs", use_quotient: bool = True, dtype: torch.dtype = torch.float32,
-                 chunk: int = 4):
-        self.alpha, self.tol, self.max_iters, self.end_modulo = alpha, tol, int(max_iters), int(end_modulo)
-        self.error_type, self.use_quotient, self.dtype, self.chunk = error_type, use_quotient, dtype, int(chunk)
+    def __init__(self, tol: Optional[float] = 1e-6, max_iters: int = 100, end_modulo: int = 1, error_type: str = "mabs",
+                 dtype: torch.dtype = torch.float32, chunk: int = 4, preserve_norm: bool = True):
+        self.tol, self.max_iters, self.end_modulo = tol, int(max_iters), int(end_modulo)
+        self.error_type, self.dtype, self.chunk, self.preserve_norm = error_type, dtype, int(chunk), preserve_norm
         self.poison = os.environ.get("PGB_PEER_POISON", "0") == "1"   # NaN-fill the exchanged buffers before a solve
         self.iteration = 0
         self.elapsed_time = None
 
+    # -- personalization -------------------------------------------------------------------------------------------
     def local_personalization(self, g: DistGraph, seeds, values=None):
         """Host seed list -> (this rank's slice of the personalization vector, its L1 norm)."""
         dev = g.view.indptr.device
@@ -361,10 +484,19 @@ class DistPageRank:
             p[ids[mine] - g.offset] = torch.from_numpy(vals).to(device=dev, dtype=self.dtype)[mine]
         return p, norm
 
-    def rank(self, g: DistGraph, seeds=None, values=None, p_local=None, norm=None) -> torch.Tensor:
-        """``seeds``: user node ids (host array) with optional ``values`` (default 1), or a prebuilt
-        ``p_local``/``norm`` pair from :meth:`local_personalization`.  Returns this rank's slice of
-        the scores (internal id order, ``g.offset`` onwards)."""
+    def _personalization(self, g, seeds, values, p_local, norm, dense):
+        if dense is not None:
+            p = g.local_vector(dense, self.dtype)
+            nrm = torch.tensor([float(p.abs().sum(dtype=torch.float64))], dtype=torch.float64, device=p.device)
+            dist.all_reduce(nrm, group=g.group)
+            return p, float(nrm.item())
+        if p_local is None:
+            return self.local_personalization(g, seeds, values)
+        return p_local, norm
+
+    # -- the loop ---------------------------------------------------------------------------------------------------
+    def _solve(self, g: DistGraph, p, norm, kind, alpha, w, sq, c, coef, coefvec, coef_table, quotient):
+        """kind "affine": z' = (alpha*w*acc + q)/S with q = (coefvec or coef)*p/sq;  kind "poly": ranks += coef_table[k]*pow."""
         from .filters import _error_code
         from .graph import dtype_code, span_struct
         lib = C.lib()
@@ -383,48 +515,44 @@ class DistPageRank:
                 marks.append((name, ev, time.perf_counter()))
 
         mark("start")
-        if p_local is None:
-            p, norm = self.local_personalization(g, seeds, values)
-        else:
-            p = p_local
-        if norm == 0:
-            self.iteration = 0
-            return p
-
         err_code = _error_code(self.error_type)
         if err_code == C.ERR_MAX and g.peer_buffers(dtype) is None:
             raise Exception("MaxDifference on the row-partitioned path needs the symmetric-memory exchange")
         sf = [0.0] * C.STATE_LEN
         si = [0] * C.STATE_LEN
-        sf[C.SF_ALPHA], sf[C.SF_INVS] = float(self.alpha), 1.0
+        sf[C.SF_ALPHA], sf[C.SF_INVS] = float(alpha), 1.0
         sf[C.SF_TOL] = 0.0 if self.tol is None else max(float(self.tol), float(np.finfo(float).eps))
         sf[C.SF_MEAN] = 1.0 if err_code in (C.ERR_L1, C.ERR_MAX) else float(g.n_nodes)   # Mabs divides by the node count
         sf[C.SF_NORM] = norm
         si[C.SI_MAX_ITERS], si[C.SI_END_MODULO] = self.max_iters, max(self.end_modulo, 1)
-        si[C.SI_ERR_MODE], si[C.SI_QUOTIENT] = err_code, int(bool(self.use_quotient))
+        si[C.SI_ERR_MODE], si[C.SI_QUOTIENT] = err_code, int(bool(quotient))
         state_f64 = torch.tensor(sf, dtype=torch.float64, device=dev)
         state_i32 = torch.tensor(si, dtype=torch.int32, device=dev)
         err_hist = torch.zeros(self.max_iters + 2, dtype=torch.float64, device=dev)
 
-        sq, cvec = g.vec("sq", dtype), g.vec("c", dtype)
+        sq_full = g.vec("sq", dtype)
         peer = g.peer_buffers(dtype)
         if peer is not None:
             zfull = [peer["z"][:g.n_global], peer["z"][g.n_global:]]
         else:
             zfull = [torch.empty(g.n_global, dtype=dtype, device=dev), torch.empty(g.n_global, dtype=dtype, device=dev)]
-        q = torch.empty(n_loc, dtype=dtype, device=dev)
+        affine = kind == "affine"
+        q = torch.empty(n_loc, dtype=dtype, device=dev) if affine else None
+        ranks = torch.zeros(n_loc, dtype=dtype, device=dev) if not affine else None
+        coef_dev = torch.tensor(coef_table, dtype=torch.float64, device=dev) if not affine else None
         if peer is not None and self.poison:
             # parity runs: every entry a peer fails to deliver (reader masks leave unread entries alone) is a NaN
             peer["z"].fill_(float("nan"))
             peer["hz"].barrier(channel=1)
         if peer is not None:
             # start vector straight into every rank's buffer 0 (no all-gather); the barrier orders it before step 1
-            C.check(lib.pgb_affine_init_peer(n_loc, code, C.ptr(p), None, C.ptr(sq), C.ptr(cvec), 1 - self.alpha, None,
-                                             None, off, C.ptr(q), C.ptr(state_f64), ctypes.byref(peer["peers"][0]), st))
+            C.check(lib.pgb_affine_init_peer(n_loc, code, C.ptr(p), None, C.ptr(sq_full), C.ptr(c), float(coef),
+                                             C.ptr(coefvec), None, off, C.ptr(q), C.ptr(state_f64),
+                                             ctypes.byref(peer["peers"][0]), st))
             peer["hz"].barrier(channel=2)
         else:
-            C.check(lib.pgb_affine_init(n_loc, code, C.ptr(p), None, C.ptr(sq), C.ptr(cvec), 1 - self.alpha, None, None,
-                                        off, C.ptr(zfull[0]), C.ptr(q), C.ptr(state_f64), st))
+            C.check(lib.pgb_affine_init(n_loc, code, C.ptr(p), None, C.ptr(sq_full), C.ptr(c), float(coef), C.ptr(coefvec),
+                                        None, off, C.ptr(zfull[0]), C.ptr(q), C.ptr(state_f64), st))
             dist.all_gather_into_tensor(zfull[0], zfull[0][off:off + n_loc], group=g.group)
         # BIAS (slot 1) and TACC (slot 3) in one call; INVS (slot 2) between them is rewritten by init_finish
         dist.all_reduce(state_f64[C.SF_BIAS:C.SF_TACC + 1], group=g.group)
@@ -435,8 +563,38 @@ class DistPageRank:
         ws = g.view.new_span_ws(dtype if form is not None else None)
         kernels_per_step = g.view.kernels_per_step(dtype, form is not None)
         acc = state_f64[C.SF_TACC:C.SF_EACC + 1]
-
         mark("init")
+
+        def step(k):
+            if peer is not None:
+                # exchange fused into the step: the update kernel writes z' and the convergence sums into every
+                # rank; a symmetric-memory barrier (one small kernel) replaces all-gather + all-reduce
+                pk = ctypes.byref(peer["peers"][k & 1])
+                if affine:
+                    C.check(lib.pgb_affine_step_peer(ctypes.byref(cs), code, float(alpha), C.ptr(w), C.ptr(sq), C.ptr(c),
+                                                     C.ptr(q), C.ptr(zfull[0]), C.ptr(zfull[1]), off, C.ptr(state_f64),
+                                                     C.ptr(state_i32), C.ptr(err_hist), span_struct(ws), k, pk, st))
+                else:
+                    C.check(lib.pgb_poly_step_peer(ctypes.byref(cs), code, C.ptr(w), C.ptr(sq), C.ptr(coef_dev),
+                                                   C.ptr(ranks), C.ptr(zfull[0]), C.ptr(zfull[1]), off, C.ptr(state_f64),
+                                                   C.ptr(state_i32), C.ptr(err_hist), span_struct(ws), k, pk, st))
+                peer["hz"].barrier(channel=0)
+                C.check(lib.pgb_state_finalize_peer(C.ptr(state_f64), C.ptr(state_i32), C.ptr(err_hist),
+                                                    peer["acc"].data_ptr() + (k & 1) * 2 * C.MAX_PEERS * 8, g.world, st))
+                return
+            if affine:
+                C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, float(alpha), C.ptr(w), C.ptr(sq), C.ptr(c), C.ptr(q),
+                                             C.ptr(zfull[0]), C.ptr(zfull[1]), off, C.ptr(state_f64), C.ptr(state_i32),
+                                             C.ptr(err_hist), span_struct(ws), k, 1, 0, st))
+            else:
+                C.check(lib.pgb_poly_steps(ctypes.byref(cs), code, C.ptr(w), C.ptr(sq), C.ptr(coef_dev), C.ptr(ranks),
+                                           C.ptr(zfull[0]), C.ptr(zfull[1]), off, C.ptr(state_f64), C.ptr(state_i32),
+                                           C.ptr(err_hist), span_struct(ws), k, 1, 0, st))
+            out = zfull[k & 1]
+            dist.all_gather_into_tensor(out, out[off:off + n_loc], group=g.group)
+            dist.all_reduce(acc, group=g.group)
+            C.check(lib.pgb_state_finalize(C.ptr(state_f64), C.ptr(state_i32), C.ptr(err_hist), st))
+
         budget, done = self.max_iters - 1, 0
         stop, steps, iteration = C.RUNNING, 0, 1
         # run-ahead chunk: a previous solve on this graph is the best guess of how many steps this one needs,
@@ -445,26 +603,7 @@ class DistPageRank:
         while done < budget:
             count = min(chunk, budget - done)
             for j in range(count):
-                k = done + 1 + j
-                if peer is not None:
-                    # exchange fused into the step: the update kernel writes z' and the convergence sums into
-                    # every rank; a symmetric-memory barrier (one small kernel) replaces all-gather + all-reduce
-                    C.check(lib.pgb_affine_step_peer(ctypes.byref(cs), code, float(self.alpha), None, None,
-                                                     C.ptr(cvec), C.ptr(q), C.ptr(zfull[0]), C.ptr(zfull[1]), off,
-                                                     C.ptr(state_f64), C.ptr(state_i32), C.ptr(err_hist),
-                                                     span_struct(ws), k, ctypes.byref(peer["peers"][k & 1]), st))
-                    peer["hz"].barrier(channel=0)
-                    C.check(lib.pgb_state_finalize_peer(C.ptr(state_f64), C.ptr(state_i32), C.ptr(err_hist),
-                                                        peer["acc"].data_ptr() + (k & 1) * 2 * C.MAX_PEERS * 8,
-                                                        g.world, st))
-                    continue
-                C.check(lib.pgb_affine_steps(ctypes.byref(cs), code, float(self.alpha), None, None, C.ptr(cvec),
-                                             C.ptr(q), C.ptr(zfull[0]), C.ptr(zfull[1]), off, C.ptr(state_f64),
-                                             C.ptr(state_i32), C.ptr(err_hist), span_struct(ws), k, 1, 0, st))
-                out = zfull[k & 1]
-                dist.all_gather_into_tensor(out, out[off:off + n_loc], group=g.group)
-                dist.all_reduce(acc, group=g.group)
-                C.check(lib.pgb_state_finalize(C.ptr(state_f64), C.ptr(state_i32), C.ptr(err_hist), st))
+                step(done + 1 + j)
             C.count_launches((kernels_per_step + 1) * count)
             done += count
             host = state_i32.cpu()
@@ -483,8 +622,12 @@ class DistPageRank:
         if peer is not None:
             peer["hz"].barrier(channel=1)   # nobody starts the next solve (overwriting buffer 0) before all have read
         result = torch.empty(n_loc, dtype=dtype, device=dev)
-        zl = zfull[steps & 1][off:off + n_loc]
-        C.check(lib.pgb_unscale(n_loc, code, C.ptr(zl.contiguous()), C.ptr(sq), None, norm, None, C.ptr(result), st))
+        scale = norm if self.preserve_norm else 1.0
+        if affine:
+            zl = zfull[steps & 1][off:off + n_loc]
+            C.check(lib.pgb_unscale(n_loc, code, C.ptr(zl.contiguous()), C.ptr(sq_full), None, scale, None, C.ptr(result), st))
+        else:
+            C.check(lib.pgb_unscale(n_loc, code, C.ptr(ranks), None, None, scale, None, C.ptr(result), st))
         C.count_launches(1)
         mark("end")
         if timing:
@@ -495,11 +638,111 @@ class DistPageRank:
         self.elapsed_time = time.perf_counter() - t0
         return result
 
+    def _scales(self, g: DistGraph):
+        """(w, sq) the kernels read, or (None, None) when they derive them from the row pointers."""
+        if g.symdeg:
+            return None, None
+        return g.vec("w", self.dtype), g.vec("sq", self.dtype)
+
     def gather_user_order(self, g: DistGraph, local_scores: torch.Tensor) -> torch.Tensor:
         """All ranks: the full score vector in USER node order (testing / small graphs)."""
         full = torch.empty(g.n_global, dtype=local_scores.dtype, device=local_scores.device)
         dist.all_gather_into_tensor(full, local_scores.contiguous(), group=g.group)
         return full[g.new_id.long()][: g.n_nodes]
+
+
+class DistPageRank(DistFilter):
+    """``pg.PageRank`` (adhoc.py:34-36 with RecursiveGraphFilter's quotient, abstract_filters.py:126-136)."""
+
+    def __init__(self, alpha: float = 0.85, *args, use_quotient: bool = True, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alpha, self.use_quotient = alpha, use_quotient
+
+    def rank(self, g: DistGraph, seeds=None, values=None, p_local=None, norm=None, personalization=None) -> torch.Tensor:
+        """``seeds``: user node ids (host array) with optional ``values`` (default 1); or a prebuilt ``p_local``/``norm``
+        pair from :meth:`local_personalization`; or ``personalization``: a dense vector in user order."""
+        p, norm = self._personalization(g, seeds, values, p_local, norm, personalization)
+        if norm == 0:
+            self.iteration = 0
+            return p
+        w, sq = self._scales(g)
+        return self._solve(g, p, norm, "affine", self.alpha, w, sq, g.vec("c", self.dtype), 1 - self.alpha, None, None,
+                           self.use_quotient)
+
+
+class DistAbsorbingWalks(DistFilter):
+    """``pg.AbsorbingWalks`` (adhoc.py:157-169): (conv(r, M) o deg + p o absorb) / (absorb + deg) with deg the row sums of
+    the normalised operator; ``absorption`` is a dense user-order vector (default: ones)."""
+
+    def __init__(self, alpha: float = 1 - 1.E-6, *args, use_quotient: bool = True, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alpha, self.use_quotient = alpha, use_quotient
+
+    def rank(self, g: DistGraph, seeds=None, values=None, p_local=None, norm=None, personalization=None,
+             absorption=None) -> torch.Tensor:
+        p, norm = self._personalization(g, seeds, values, p_local, norm, personalization)
+        if norm == 0:
+            self.iteration = 0
+            return p
+        f64 = torch.float64
+        dev = g.view.indptr.device
+        rate = (1 - self.alpha) / self.alpha                  # adhoc.py:158
+        ab = (torch.ones(g.n_local, dtype=f64, device=dev) if absorption is None else g.local_vector(absorption, f64)) * rate
+        degM = g.vec("degM", f64)
+        denom = ab + degM
+        d1 = degM / denom
+        w_run = (g.vec("w", f64) * d1).to(self.dtype)         # coefficient of the gathered sum
+        coefvec = (ab / denom).to(self.dtype)                 # coefficient of the personalization
+        gsum = g.push_sum(g.vec("R", f64) * d1)               # row sums of M diag(d1): the next normaliser stays linear
+        c_run = (g.vec("sq", f64) * gsum).to(self.dtype)
+        return self._solve(g, p, norm, "affine", 1.0, w_run, g.vec("sq", self.dtype), c_run, 0.0, coefvec, None,
+                           self.use_quotient)
+
+
+class DistClosedFormGraphFilter(DistFilter):
+    """Taylor-coefficient polynomial filters in the node space (abstract_filters.py:196-256) on pgb_poly_step_peer."""
+
+    def _coefficient(self, previous_coefficient, iteration: int) -> float:
+        raise Exception("Use a derived class of DistClosedFormGraphFilter that implements the _coefficient method")
+
+    def rank(self, g: DistGraph, seeds=None, values=None, p_local=None, norm=None, personalization=None) -> torch.Tensor:
+        p, norm = self._personalization(g, seeds, values, p_local, norm, personalization)
+        if norm == 0:
+            self.iteration = 0
+            return p
+        coefs, prev = [0.0], None
+        for k in range(1, max(self.max_iters, 1) + 1):        # step k runs with convergence.iteration == k
+            prev = self._coefficient(prev, k)
+            coefs.append(float(prev))
+        w, sq = self._scales(g)
+        return self._solve(g, p, norm, "poly", 1.0, w, sq, None, 0.0, None, coefs, False)
+
+
+class DistHeatKernel(DistClosedFormGraphFilter):
+    def __init__(self, t: float = 3, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.t = t
+
+    def _coefficient(self, previous_coefficient, iteration):   # adhoc.py:113-116
+        return 1. if previous_coefficient is None else previous_coefficient * self.t / (iteration + 1)
+
+
+class DistPageRankClosed(DistClosedFormGraphFilter):
+    def __init__(self, alpha: float = 0.85, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alpha = alpha
+
+    def _coefficient(self, previous_coefficient, iteration):   # adhoc.py:83-84
+        return 1. if previous_coefficient is None else previous_coefficient * self.alpha
+
+
+class DistGenericGraphFilter(DistClosedFormGraphFilter):
+    def __init__(self, weights=None, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.weights = list(weights) if weights is not None else [0.9] * 10
+
+    def _coefficient(self, _, iteration):                      # low_pass.py:23-26
+        return 0 if iteration > len(self.weights) else self.weights[iteration - 1]
 
 
 # ------------------------------------------------------------------------------------------------
