@@ -118,7 +118,8 @@ def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional
         # auto: hub blocks cover ~1/8 of the columns, between 64 and 256 blocks.  Measured (ms per step): fp32,
         # 16.8 M columns: 64 -> .685, 96 -> .670, 128 -> .70; fp64 (blocks half as wide): 64 -> 1.00, 128 -> .965;
         # fp32, 134 M columns on 8 ranks: 64 -> 1.40, 128 -> 1.28, 256 -> 1.19, 512 -> 1.36
-        max_blocks = max(64, min(_env_int("PGB_HSELL_BLOCKS_CAP", 256), (n_segments * seg_len) // (8 * H)))
+        # round 2 (TEX tail + RED pieces, 16.8 M columns): 48 -> .562, 64 -> .531, 80 -> .522 ms: ~1/6.4 of the columns
+        max_blocks = max(64, min(_env_int("PGB_HSELL_BLOCKS_CAP", 256), (5 * n_segments * seg_len) // (32 * H)))
     K = max(min(max_blocks, -(-seg_len // Hs)), 0)
     if n_segments > 1 and K * Hs > seg_len:
         K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail
