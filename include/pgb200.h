@@ -254,6 +254,13 @@ int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int
                    const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
                    int32_t *piece_row, int32_t *scratch, int32_t banks, int32_t n_windows, int64_t window_len,
                    void *stream);
+/* K8 — graph_dropout inside the gather kernel of the hsell form (torch backends' semantics,
+ * /root/reference/pygrank/core/backend/pytorch.py:34-38; called once per iteration, abstract_filters.py:59-62): while
+ * p > 0 every stored entry is dropped with probability p by a counter-based hash of (seed, gather launches since this
+ * call, slot) and the survivors are rescaled by 1/(1-p); a new mask every launch, nothing streamed, no values array.  Process-global like
+ * the backend selection of the reference; p = 0 switches it off.  The linear next-normaliser of the quotient
+ * (PGB_SI_QUOTIENT) assumes the unmasked operator: callers run dropout with the quotient off. */
+int pgb_hsell_set_dropout(double p, uint64_t seed);
 /* Experiment knob: warps (of 32) per CTA that prefer tail units (L2 gathers) over hub units. */
 int pgb_hsell_set_tail_warps(int warps);
 

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "pgb_set_kernel_variant": (c_int, [c_int]),
     "pgb_hsell_max_block_cols": (c_int, [c_int]),
     "pgb_hsell_set_tail_warps": (c_int, [c_int]),
+    "pgb_hsell_set_dropout": (c_int, [c_double, c_uint64]),
     "pgb_hsell_count": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_int32, c_int64,
                                 c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "pgb_hsell_fill": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p,

@@ -322,6 +322,21 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
 // ---------------------------------------------------------------------------------------------
 // kernel A: the gather.  One CTA of 32 warps per SM; shared memory holds one hub block of z.
 // ---------------------------------------------------------------------------------------------
+// graph_dropout inside the gather (K8; semantics of the torch backends' graph_dropout,
+// /root/reference/pygrank/core/backend/pytorch.py:34-38: every stored entry is dropped with probability p and the
+// survivors are rescaled by 1/(1-p), a fresh mask per call): the Bernoulli draw of an entry is a counter-based hash of
+// (seed, step, position of the entry's slot in its stream) — no mask array, no values array, nothing streamed.
+struct DropParams {
+    uint64_t key;      // mix of the seed and the step: a new mask every iteration
+    uint32_t thr;      // drop when the 32 hash bits are below thr = p * 2^32
+    float scale;       // 1 / (1 - p), applied when a piece is flushed
+};
+template <bool DROP>
+__device__ __forceinline__ bool kept(const DropParams &D, uint64_t slot) {
+    if (!DROP) return true;
+    return (uint32_t)(mix64(D.key ^ (slot * 0xD1342543DE82EF95ull)) >> 32) >= D.thr;
+}
+
 struct GatherParams {
     pgb_hsell h;
     const void *z;
@@ -332,6 +347,7 @@ struct GatherParams {
     int tail_batch;        // tail chunks taken per grab of the global queue
     int debug_skip;        // timing experiments only (PGB_HSELL_DEBUG_SKIP): 1 = skip hub chunks, 2 = skip tail chunks
     cudaTextureObject_t ztex;   // linear texture over z (TEX kernels): tail gathers go through the TEX pipe
+    DropParams drop;            // DROP kernels: in-kernel graph_dropout
 };
 
 // A piece's 32 lane sums leave the gather kernel either as one 128-byte partial row (deterministic path: the
@@ -352,10 +368,12 @@ constexpr int BATCH = 8;              // rounds loaded ahead per lane
 static_assert(CH == 32 && CH % BATCH == 0, "the end mask of a chunk is one 32-bit word");
 
 // One chunk of the hub stream: 32 rounds, two shared-memory gathers per lane and round.
-template <typename T, bool ACCUM>
+template <typename T, bool ACCUM, bool DROP>
 __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, int64_t chunk, uint32_t p_first,
                                           uint32_t endmask, const int32_t *__restrict__ piece_row, const T *s_z,
-                                          T *__restrict__ partials, int lane) {
+                                          T *__restrict__ partials, int lane, const DropParams &D) {
+    const T dscale = DROP ? (T)D.scale : (T)1;
+    const uint64_t slot0 = ((uint64_t)chunk * (CH * 32) + (uint64_t)lane) * 2;   // + round * 64 + half
     const uint32_t *d = words + chunk * (CH * 32) + lane;
     endmask |= 0x80000000u;   // the chunk end closes the last piece
     // a chunk has at most 32 pieces: lane j fetches the partial row of piece j
@@ -375,16 +393,20 @@ __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, in
         if (m8 == 0u) {
 #pragma unroll
             for (int u = 0; u < BATCH; ++u) {
-                a0 += s_z[w[u] & 0xffffu];
-                a1 += s_z[w[u] >> 16];
+                const uint64_t sl = slot0 + (uint64_t)(bt * BATCH + u) * 64;
+                const T x0 = s_z[w[u] & 0xffffu], x1 = s_z[w[u] >> 16];
+                a0 += kept<DROP>(D, sl) ? x0 : (T)0;
+                a1 += kept<DROP>(D, sl + 1) ? x1 : (T)0;
             }
         } else {
 #pragma unroll
             for (int u = 0; u < BATCH; ++u) {
-                a0 += s_z[w[u] & 0xffffu];
-                a1 += s_z[w[u] >> 16];
+                const uint64_t sl = slot0 + (uint64_t)(bt * BATCH + u) * 64;
+                const T x0 = s_z[w[u] & 0xffffu], x1 = s_z[w[u] >> 16];
+                a0 += kept<DROP>(D, sl) ? x0 : (T)0;
+                a1 += kept<DROP>(D, sl + 1) ? x1 : (T)0;
                 if ((m8 >> u) & 1u) {
-                    flush_piece<ACCUM>(partials, __shfl_sync(0xffffffffu, my_row, p), lane, a0 + a1);
+                    flush_piece<ACCUM>(partials, __shfl_sync(0xffffffffu, my_row, p), lane, (a0 + a1) * dscale);
                     ++p;
                     a0 = a1 = (T)0;
                 }
@@ -406,11 +428,13 @@ __device__ __forceinline__ double tex_fetch(cudaTextureObject_t t, int c, double
 }
 
 // One chunk of the tail stream: 32 rounds, one L2 gather per lane and round (padding lanes are off).
-template <typename T, bool TEX, bool ACCUM>
+template <typename T, bool TEX, bool ACCUM, bool DROP>
 __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int64_t chunk, uint32_t p_first,
                                            uint32_t endmask, const int32_t *__restrict__ piece_row,
                                            const T *__restrict__ z, cudaTextureObject_t ztex,
-                                           T *__restrict__ partials, int lane) {
+                                           T *__restrict__ partials, int lane, const DropParams &D) {
+    const T dscale = DROP ? (T)D.scale : (T)1;
+    const uint64_t tslot0 = (1ull << 62) + (uint64_t)chunk * (CH * 32) + (uint64_t)lane;   // + round * 32
     const int32_t *d = cols + chunk * (CH * 32) + lane;
     endmask |= 0x80000000u;
     const int my_row = (lane < __popc(endmask)) ? __ldg(piece_row + p_first + lane) : 0;
@@ -424,10 +448,11 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
         T x[BATCH];
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
+            const bool on = c[u] >= 0 && kept<DROP>(D, tslot0 + (uint64_t)(bt * BATCH + u) * 32);
             if (TEX)
-                x[u] = (c[u] >= 0) ? tex_fetch(ztex, c[u], (T)0) : (T)0;
+                x[u] = on ? tex_fetch(ztex, c[u], (T)0) : (T)0;
             else
-                x[u] = (c[u] >= 0) ? __ldg(z + c[u]) : (T)0;
+                x[u] = on ? __ldg(z + c[u]) : (T)0;
         }
         if (bt + 1 < CH / BATCH) {
 #pragma unroll
@@ -445,7 +470,7 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
             for (int u = 0; u < BATCH; ++u) {
                 a0 += x[u];
                 if ((m8 >> u) & 1u) {
-                    flush_piece<ACCUM>(partials, __shfl_sync(0xffffffffu, my_row, p), lane, a0 + a1);
+                    flush_piece<ACCUM>(partials, __shfl_sync(0xffffffffu, my_row, p), lane, (a0 + a1) * dscale);
                     ++p;
                     a0 = a1 = (T)0;
                 }
@@ -456,7 +481,7 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
     }
 }
 
-template <typename T, bool TEX, bool ACCUM>
+template <typename T, bool TEX, bool ACCUM, bool DROP>
 __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const GatherParams G) {
     extern __shared__ __align__(16) unsigned char hs_smem[];
     T *s_z = reinterpret_cast<T *>(hs_smem);   // [block_cols + 1]; the last entry is the padding target (0)
@@ -486,7 +511,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
         const int u1 = (u0 + TB < tail_hi) ? u0 + TB : tail_hi;
         for (int u = u0; u < u1; ++u) {
             const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.tail_chunks) + u);
-            tail_chunk<T, TEX, ACCUM>(h.tail_cols, u, d.x, d.y, piece_dst, z, G.ztex, partials, lane);
+            tail_chunk<T, TEX, ACCUM, DROP>(h.tail_cols, u, d.x, d.y, piece_dst, z, G.ztex, partials, lane, G.drop);
         }
     };
 
@@ -545,7 +570,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
             if (kind == 1) {
                 if (!(G.debug_skip & 1)) {
                     const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.hub_chunks) + u);
-                    hub_chunk<T, ACCUM>(h.hub_words, u, d.x, d.y, piece_dst, s_z, partials, lane);
+                    hub_chunk<T, ACCUM, DROP>(h.hub_words, u, d.x, d.y, piece_dst, s_z, partials, lane, G.drop);
                 }
             } else {
                 run_tail(u);
@@ -819,24 +844,36 @@ static cudaTextureObject_t texture_for(const void *z, size_t elems, int dtype) {
     return t;
 }
 
-template <typename T>
-static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool accum, const int32_t *stop,
-                         uint32_t *tail_queue, cudaStream_t st) {
+static inline uint64_t mix64_host(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static double g_drop_p = 0.0;
+static uint64_t g_drop_seed = 0;
+static uint64_t g_drop_launch = 0;   // gather launches since pgb_hsell_set_dropout: every launch draws a new mask
+
+template <typename T, bool TEX, bool ACCUM, bool DROP>
+static int launch_gather_variant(const GatherParams &G, int n_ctas, size_t smem, cudaStream_t st) {
     static PerDeviceInt configured_on;
-    const size_t smem = ((size_t)h->block_cols + 1) * sizeof(T);
-    if (smem > (size_t)HS_SMEM_LIMIT - 64) return fail("hsell: block_cols=%d does not fit in shared memory", h->block_cols);
     int &configured = configured_on.here();
     if (!configured) {
-        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         HS_SMEM_LIMIT - 64));
-        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         HS_SMEM_LIMIT - 64));
-        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         HS_SMEM_LIMIT - 64));
-        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, TEX, ACCUM, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HS_SMEM_LIMIT - 64));
         configured = 1;
     }
+    hsell_gather_kernel<T, TEX, ACCUM, DROP><<<n_ctas, HS_THREADS, smem, st>>>(G);
+    PGB_LAUNCH_OK("hsell_gather_kernel");
+    return 0;
+}
+
+template <typename T>
+static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool accum, const int32_t *stop,
+                         uint32_t *tail_queue, int step, cudaStream_t st) {
+    const size_t smem = ((size_t)h->block_cols + 1) * sizeof(T);
+    if (smem > (size_t)HS_SMEM_LIMIT - 64) return fail("hsell: block_cols=%d does not fit in shared memory", h->block_cols);
     GatherParams G;
     G.h = *h;
     G.z = z;
@@ -859,16 +896,23 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool
     G.tail_batch = tail_batch;
     G.ztex = h->n_tail_chunks > 0 ? texture_for(z, (size_t)h->seg_len * (size_t)h->n_segments, sizeof(T) == 4 ? PGB_F32 : PGB_F64) : 0;
     if (accum && !h->piece_slice) return fail("hsell: accumulate mode needs pgb_hsell.piece_slice");
-    if (G.ztex && accum)
-        hsell_gather_kernel<T, true, true><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
-    else if (G.ztex)
-        hsell_gather_kernel<T, true, false><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
-    else if (accum)
-        hsell_gather_kernel<T, false, true><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
-    else
-        hsell_gather_kernel<T, false, false><<<h->n_ctas, HS_THREADS, smem, st>>>(G);
-    PGB_LAUNCH_OK("hsell_gather_kernel");
-    return 0;
+    const bool drop = g_drop_p > 0.0;
+    (void)step;
+    G.drop.key = mix64_host(g_drop_seed ^ ((drop ? ++g_drop_launch : 0) * 0x9E3779B97F4A7C15ull));
+    G.drop.thr = drop ? (uint32_t)(g_drop_p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : g_drop_p * 4294967296.0) : 0u;
+    G.drop.scale = drop ? (float)(1.0 / (1.0 - g_drop_p)) : 1.0f;
+    const int n = h->n_ctas;
+    const int sel = (G.ztex ? 4 : 0) | (accum ? 2 : 0) | (drop ? 1 : 0);
+    switch (sel) {
+        case 0: return launch_gather_variant<T, false, false, false>(G, n, smem, st);
+        case 1: return launch_gather_variant<T, false, false, true>(G, n, smem, st);
+        case 2: return launch_gather_variant<T, false, true, false>(G, n, smem, st);
+        case 3: return launch_gather_variant<T, false, true, true>(G, n, smem, st);
+        case 4: return launch_gather_variant<T, true, false, false>(G, n, smem, st);
+        case 5: return launch_gather_variant<T, true, false, true>(G, n, smem, st);
+        case 6: return launch_gather_variant<T, true, true, false>(G, n, smem, st);
+        default: return launch_gather_variant<T, true, true, true>(G, n, smem, st);
+    }
 }
 
 template <typename T>
@@ -935,7 +979,7 @@ static int launch_update_accum(const StepParams &P, void *yacc, cudaStream_t st)
 
 template <typename T, int MODE>
 static int hsell_step_accum(const StepParams &P, const pgb_hsell *h, bool symdeg, const int32_t *stop, cudaStream_t st) {
-    if (launch_gather<T>(h, P.zin, P.yacc, true, stop, P.span_cnt, st)) return 1;
+    if (launch_gather<T>(h, P.zin, P.yacc, true, stop, P.span_cnt, P.step, st)) return 1;
     return symdeg ? launch_update_accum<T, MODE, true>(P, P.yacc, st) : launch_update_accum<T, MODE, false>(P, P.yacc, st);
 }
 
@@ -955,12 +999,12 @@ int hsell_step(const StepParams &P, const pgb_hsell *h, void *partials, int dtyp
     if (h->n_rows != P.n) return fail("hsell: form built for %lld rows, graph has %lld", (long long)h->n_rows, (long long)P.n);
     const int32_t *stop = (MODE == MODE_CONV) ? nullptr : P.si + PGB_SI_STOP;
     if (dtype == PGB_F32) {
-        if (launch_gather<float>(h, P.zin, partials, false, stop, P.span_cnt, st)) return 1;
+        if (launch_gather<float>(h, P.zin, partials, false, stop, P.span_cnt, P.step, st)) return 1;
         if (launch_reduce<float>(h, partials, stop, st)) return 1;
         return symdeg ? launch_update<float, MODE, true>(P, h, partials, st)
                       : launch_update<float, MODE, false>(P, h, partials, st);
     } else if (dtype == PGB_F64) {
-        if (launch_gather<double>(h, P.zin, partials, false, stop, P.span_cnt, st)) return 1;
+        if (launch_gather<double>(h, P.zin, partials, false, stop, P.span_cnt, P.step, st)) return 1;
         if (launch_reduce<double>(h, partials, stop, st)) return 1;
         return symdeg ? launch_update<double, MODE, true>(P, h, partials, st)
                       : launch_update<double, MODE, false>(P, h, partials, st);
@@ -984,6 +1028,14 @@ int pgb_hsell_max_block_cols(int dtype) {
     int cols = (HS_SMEM_LIMIT - 64) / bytes - 1;
     if (cols > 65535) cols = 65535;
     return cols & ~63;   // keeps every block start 16-byte aligned for the vector loader
+}
+
+int pgb_hsell_set_dropout(double p, uint64_t seed) {
+    if (!(p >= 0.0) || p >= 1.0) return fail("pgb_hsell_set_dropout: p must be in [0, 1)");
+    g_drop_p = p;
+    g_drop_seed = seed;
+    g_drop_launch = 0;
+    return 0;
 }
 
 int pgb_hsell_set_tail_warps(int warps) {

@@ -502,6 +502,7 @@ int pgb_affine_steps(const pgb_csr *g, int dtype, double alpha, const void *w, c
         const int k = first_step + j;
         P.zin = buf[(k - 1) & 1];
         P.zout = buf[k & 1];
+        P.step = k;
         if (dispatch<MODE_AFFINE>(P, dtype, symdeg, as_stream(stream))) return 1;
     }
     return 0;
@@ -536,6 +537,7 @@ int pgb_poly_steps(const pgb_csr *g, int dtype, const void *w, const void *sq, c
         const int k = first_step + j;
         P.zin = buf[(k - 1) & 1];
         P.zout = buf[k & 1];
+        P.step = k;
         if (dispatch<MODE_POLY>(P, dtype, symdeg, as_stream(stream))) return 1;
     }
     return 0;
@@ -572,6 +574,7 @@ int pgb_affine_step_peer(const pgb_csr *g, int dtype, double alpha, const void *
     void *buf[2] = {zbuf0, zbuf1};
     P.zin = buf[(step - 1) & 1];
     P.zout = buf[step & 1];
+    P.step = step;
     P.n_peers = peers->n;
     P.peer_rank = peers->rank;
     for (int r = 0; r < peers->n; ++r) {
@@ -614,6 +617,7 @@ int pgb_poly_step_peer(const pgb_csr *g, int dtype, const void *w, const void *s
     void *buf[2] = {zbuf0, zbuf1};
     P.zin = buf[(step - 1) & 1];
     P.zout = buf[step & 1];
+    P.step = step;
     P.n_peers = peers->n;
     P.peer_rank = peers->rank;
     for (int r = 0; r < peers->n; ++r) {

@@ -30,6 +30,7 @@ struct StepParams {
     double *span_acc;
     uint32_t *span_cnt;
     int finalize;
+    int step;                // index of this step in its run (in-kernel dropout draws a new mask per step)
     const pgb_hsell *hsell;  // host pointer: hub-blocked sliced-ELL form of the same graph (or NULL)
     void *partials;          // its per-filter workspace
     void *yacc;              // accumulate mode: y [n_slices + 1][32], zero between steps (or NULL: partial rows)

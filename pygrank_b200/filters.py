@@ -26,7 +26,8 @@ import numpy as np
 import torch
 
 from . import _capi as C
-from .graph import DeviceGraph, as_device_graph, dtype_code, preprocessor as device_preprocessor, span_struct
+from .graph import (DeviceGraph, as_device_graph, dtype_code, in_kernel_dropout, preprocessor as device_preprocessor,
+                    span_struct)
 
 _ERROR_NAMES = {"mabs": C.ERR_MABS, "l1": C.ERR_L1, "msq": C.ERR_MSQ, "iters": C.ERR_ITERS,
                 "max": C.ERR_MAX, "maxdifference": C.ERR_MAX}
@@ -143,7 +144,7 @@ class GraphFilter:
             graph = personalization.graph
         g = self._device_graph(graph)
         if graph_dropout != 0:
-            raise Exception("graph_dropout with the fused filters is not supported; use the backend plugin path")
+            self._check_dropout(g)
         p, norm = _personalization(g, personalization, self.dtype)
         cm = self.convergence
         cm.iteration, cm.errors = 0, None
@@ -156,7 +157,8 @@ class GraphFilter:
         warm = None
         if warm_start is not None:
             warm, _ = _personalization(g, warm_start, self.dtype)
-        out = self._run(g, p, norm, warm, **kwargs)
+        with in_kernel_dropout(graph_dropout):
+            out = self._run(g, p, norm, warm, **kwargs)
         cm.elapsed_time = time.perf_counter() - t0
         return RankResult(g, out)
 
@@ -179,6 +181,15 @@ class GraphFilter:
 
     def _can_batch(self, g, *args, **kwargs) -> bool:
         return False
+
+    def _check_dropout(self, g: DeviceGraph):
+        """graph_dropout (abstract_filters.py:59-62) is drawn inside the gather kernel of the hub-blocked form."""
+        if g.in_view.hsell(self.dtype) is None:
+            raise Exception("in-kernel graph_dropout needs an unweighted graph (hub-blocked form); weighted graphs: "
+                            "use the backend plugin path")
+        if getattr(self, "use_quotient", False):
+            raise Exception("graph_dropout with use_quotient=True is not fused (the next normaliser is no longer linear "
+                            "in the iterate); pass use_quotient=False or use the backend plugin path")
 
     def _device_graph(self, graph) -> DeviceGraph:
         """The preprocessor's output as a DeviceGraph.  A custom preprocessor that returns a host matrix (the

@@ -237,6 +237,30 @@ def hsell_layout(hr: torch.Tensor, tr: torch.Tensor, heavy_parts: int) -> dict:
     }
 
 
+_dropout_calls = [0]
+
+
+class in_kernel_dropout:
+    """``with in_kernel_dropout(p):`` — gather launches inside draw Bernoulli edge masks in the kernel
+    (pgb_hsell_set_dropout).  The seed follows torch's global seed and the number of dropout scopes opened so far, so
+    ``torch.manual_seed`` makes runs repeatable."""
+
+    def __init__(self, p: float):
+        self.p = float(p)
+
+    def __enter__(self):
+        if self.p > 0:
+            _dropout_calls[0] += 1
+            seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + _dropout_calls[0]) & 0xFFFFFFFFFFFFFFFF
+            C.check(C.lib().pgb_hsell_set_dropout(self.p, seed))
+        return self
+
+    def __exit__(self, *exc):
+        if self.p > 0:
+            C.check(C.lib().pgb_hsell_set_dropout(0.0, 0))
+        return False
+
+
 class HsellForm:
     """Device arrays of one pgb_hsell (kept alive here; the C struct holds raw pointers)."""
 
@@ -717,7 +741,8 @@ class DeviceGraph:
         C.check(lib.pgb_scale(self.n, code, C.ptr(x), C.ptr(self.vec("L", dtype)), 1.0, C.ptr(self.perm), C.ptr(z),
                               C.stream_ptr()))
         rscale = None if self.normalization in ("none", "col") else self.vec("R", dtype)
-        y = self._spmv_raw(self.in_view, z, rscale, dtype, out_perm=self.perm, hsell=True)
+        with in_kernel_dropout(getattr(self, "drop_p", 0.0)):
+            y = self._spmv_raw(self.in_view, z, rscale, dtype, out_perm=self.perm, hsell=True)
         if self.normalization == "laplacian":                 # preprocessing.py:122: -M + I
             y = x - y
         return y
@@ -752,14 +777,20 @@ class DeviceGraph:
         return self.rowsum[p], self.colsum[p]
 
     def dropout(self, p: float) -> "DeviceGraph":
-        """``graph_dropout`` with the torch backends' semantics (pytorch.py:34-38): every stored
-        entry is zeroed with probability p and survivors are rescaled by 1/(1-p); a fresh mask per call."""
+        """``graph_dropout`` with the torch backends' semantics (pytorch.py:34-38): every stored entry is zeroed with
+        probability p and survivors are rescaled by 1/(1-p); a fresh mask per conv.  Unweighted graphs: the mask is
+        drawn INSIDE the gather kernel (``pgb_hsell_set_dropout``: counter-based hash, nothing allocated or streamed);
+        weighted graphs: an explicit value array on the item-stream kernels."""
         p = float(p)
         if p == 0:
             return self
         g = object.__new__(DeviceGraph)
         g.__dict__.update(self.__dict__)
         g._cache = {}
+        g.array = g
+        if not self.in_view.weighted and hsell_config()["enabled"] and self.nnz > 0:
+            g.drop_p = p
+            return g
         view = self.in_view
         base = view.values(torch.float64)
         keep = (torch.rand(view.nnz, device=view.indptr.device) >= p).to(torch.float64) / (1.0 - p)
@@ -767,7 +798,6 @@ class DeviceGraph:
         g.in_view = dropped                       # conv (the only consumer of a dropped graph, abstract_filters.py:59-62)
         if self.symmetric_structure:              # reads the pull structure; a directed graph keeps its push view
             g.out_view = dropped
-        g.array = g
         return g
 
     def to_scipy_normalized(self):

@@ -221,3 +221,47 @@ def test_hsell_equals_item_stream_kernel_rmat17(pgb, monkeypatch, shape):
     assert float((r4 - r3).abs().sum()) <= 1e-13 * float(r3.abs().sum())
     e4, e3 = a4.convergence.errors.cpu().numpy(), a3.convergence.errors.cpu().numpy()
     assert np.allclose(e4, e3, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[3]])
+def test_in_kernel_graph_dropout(pgb, monkeypatch, shape):
+    """K8: graph_dropout drawn inside the gather kernel (pgb_hsell_set_dropout; semantics of
+    /root/reference/pygrank/core/backend/pytorch.py:34-38).  Independent masks per step make the expectation of a
+    polynomial filter the undropped filter exactly; runs repeat under torch.manual_seed; hub and tail entries are both
+    masked (tiny blocks force a tail)."""
+    import torch
+    _set_shape(monkeypatch, shape)
+    z, A, directed = load_golden("ba2000")
+    g = pgb.DeviceGraph.from_scipy(A, directed=directed, normalization="symmetric")
+    p = z["P"][:, 0].copy()
+    make = lambda: pgb.GenericGraphFilter([0.5, 0.3, 0.2, 0.1], error_type="iters", max_iters=5)
+    base = make()(g, p).numpy()
+    assert np.array_equal(make()(g, p, graph_dropout=0).numpy(), base)
+    torch.manual_seed(3)
+    first = make()(g, p, graph_dropout=0.25).numpy()
+    assert np.abs(first - base).sum() > 1e-3 * np.abs(base).sum()
+    runs = [first] + [make()(g, p, graph_dropout=0.25).numpy() for _ in range(39)]
+    assert np.abs(runs[1] - runs[0]).sum() > 0                         # a fresh mask per call
+    mean = np.mean(runs, axis=0)
+    assert rel_l1(mean, base) <= 0.04, rel_l1(mean, base)              # E[filter] = undropped filter (1/sqrt(40) noise)
+    # the plain conv of a dropped graph (the plugin route's graph_dropout): expectation preserved, mask fresh per call
+    x = torch.ones(g.n, dtype=torch.float64, device="cuda")
+    full = g.conv(x)
+    d1, d2 = g.dropout(0.5).conv(x), g.dropout(0.5).conv(x)
+    assert abs(float(d1.sum()) / float(full.sum()) - 1.0) < 0.05 and float((d1 - d2).abs().sum()) > 0
+    # repeatable: same torch seed and the same sequence of calls -> the same masks
+    from pygrank_b200 import graph as G
+    G._dropout_calls[0] = 0
+    torch.manual_seed(11)
+    a = make()(g, p, graph_dropout=0.25).numpy()
+    G._dropout_calls[0] = 0
+    torch.manual_seed(11)
+    b = make()(g, p, graph_dropout=0.25).numpy()
+    assert np.allclose(a, b, rtol=1e-12, atol=0)
+    # PageRank without the quotient runs fused with dropout; with it, it refuses
+    r = pgb.PageRank(0.85, tol=1e-9, max_iters=200, use_quotient=False, error_type="iters")
+    r.convergence.max_iters = 20
+    out = r(g, p, graph_dropout=0.1).numpy()
+    assert np.isfinite(out).all() and out.sum() > 0
+    with pytest.raises(Exception, match="use_quotient"):
+        pgb.PageRank(0.85)(g, p, graph_dropout=0.1)
