@@ -45,10 +45,12 @@ def graph_from_pairs(names, src: np.ndarray, dst: np.ndarray, directed: bool = F
     s = torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32)).to(dev)
     d = torch.from_numpy(np.ascontiguousarray(dst, dtype=np.int32)).to(dev)
     node2id = {v: i for i, v in enumerate(names)}
-    # an undirected edge is stored in both directions and repeated edges add up, exactly like fastgraph.add_edge +
-    # coo -> csr; from_edges drops the value array again when every summed weight is 1
+    # an undirected edge is stored in both directions (a self loop twice, too) and repeated edges add up, exactly like
+    # fastgraph.add_edge + coo -> csr; from_edges drops the value array again when every summed weight is 1
+    if not directed:
+        s, d = torch.cat([s, d]), torch.cat([d, s])
     w = torch.ones(s.numel(), dtype=torch.float64, device=dev)
-    return DeviceGraph.from_edges(n, s, d, w, directed=directed, symmetrize=not directed, drop_self_loops=False,
+    return DeviceGraph.from_edges(n, s, d, w, directed=directed, symmetrize=False, drop_self_loops=False,
                                   binary=False, normalization=normalization, renormalize=renormalize, relabel=relabel,
                                   node2id=node2id)
 

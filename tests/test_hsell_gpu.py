@@ -236,7 +236,7 @@ def test_in_kernel_graph_dropout(pgb, monkeypatch, shape):
     p = z["P"][:, 0].copy()
     make = lambda: pgb.GenericGraphFilter([0.5, 0.3, 0.2, 0.1], error_type="iters", max_iters=5)
     base = make()(g, p).numpy()
-    assert np.array_equal(make()(g, p, graph_dropout=0).numpy(), base)
+    assert np.allclose(make()(g, p, graph_dropout=0).numpy(), base, rtol=1e-12, atol=0)   # RED order: not bitwise
     torch.manual_seed(3)
     first = make()(g, p, graph_dropout=0.25).numpy()
     assert np.abs(first - base).sum() > 1e-3 * np.abs(base).sum()
