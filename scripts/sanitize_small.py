@@ -28,6 +28,22 @@ for dtype in (torch.float32, torch.float64):
     m = pgb.PageRank(0.85, tol=1e-8, max_iters=200, dtype=dtype, error_type="max")(g, p.to(dtype))
     y = g.conv(p.to(dtype))
     print(dtype, a.convergence.iteration, float(r.np.sum()), float(h.np.sum()), float(w.np.sum()), float(y.sum()))
+# round 2: hub-signature order + tail windows, in-kernel dropout, the deterministic partial-row path, the plugin route
+d = pgb.GenericGraphFilter([0.5, 0.3, 0.2], error_type="iters", max_iters=4)(g, p, graph_dropout=0.3)
+print("dropout", float(d.np.sum()), float(g.dropout(0.5).conv(p).sum()))
+os.environ["PGB_HSELL_TAIL_WINDOWS"] = "3"
+os.environ["PGB_HSELL_TAIL_WINDOW_MIN"] = "4"
+g3 = device_synthetic.rmat_graph_device(scale, 16, seed=2)
+print("windows", float(pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=torch.float32)(g3, p.float()).np.sum()))
+os.environ["PGB_DETERMINISTIC"] = "1"
+g4 = device_synthetic.rmat_graph_device(scale, 16, seed=2)
+print("deterministic", float(pgb.PageRank(0.85, tol=1e-9, max_iters=200)(g4, p).np.sum()))
+del os.environ["PGB_DETERMINISTIC"], os.environ["PGB_HSELL_TAIL_WINDOWS"]
+from pygrank_b200 import backend as B  # noqa: E402
+x = B.to_array(p)
+num = B.conv(x, g) * 0.85 + x * 0.15
+nxt = num / B.sum(num)
+print("lazy", float(B.sum(B.abs(x - nxt)) / n), float(B.sum(nxt)))
 os.environ["PGB_PANEL"] = "1"
 out = pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=torch.float32).propagate(g, torch.stack([p, p * 2, p * 0], 1).float())
 print("panel", tuple(out.shape), float(out.sum()))
