@@ -75,9 +75,9 @@ def test_hsell_shape_and_config_defaults(monkeypatch):
     for k in ("PGB_HSELL_BLOCK_COLS", "PGB_HSELL_BLOCKS"):
         monkeypatch.delenv(k, raising=False)
     H, K = graph.hsell_shape(torch.float32, 1, 1 << 24)
-    assert H == 32768 and K == 64
+    assert H == 32768 and K == 80
     H, K = graph.hsell_shape(torch.float64, 1, 1 << 24)
-    assert H == 16384 and K == 128
+    assert H == 16384 and K == 160
     H, K = graph.hsell_shape(torch.float32, 8, 1 << 24)         # 8 ranks x 16.8 M rows: 134 M columns
     assert H == 32768 and K == 256
     monkeypatch.setenv("PGB_HSELL_BLOCKS_CAP", "128")
