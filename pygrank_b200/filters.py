@@ -173,11 +173,11 @@ class GraphFilter:
         if self._can_batch(g, *args, **kwargs):
             return self._propagate_batched(g, cols, *args, **kwargs)
         self.convergence.iterations = []
-        outs = []
+        out = torch.empty((g.n, int(cols.shape[1])), dtype=self.dtype, device=g.out_view.indptr.device)
         for c in range(cols.shape[1]):
-            outs.append(self.rank(g, cols[:, c].contiguous(), *args, **kwargs).np)
+            out[:, c] = self.rank(g, cols[:, c].contiguous(), *args, **kwargs).np
             self.convergence.iterations.append(self.convergence.iteration)
-        return torch.stack(outs, dim=1)
+        return out
 
     def _can_batch(self, g, *args, **kwargs) -> bool:
         return False
@@ -265,6 +265,20 @@ class GraphFilter:
 
     def _run(self, g, p, norm, warm, **kwargs):
         raise Exception("Use a derived class of GraphFilter")
+
+    def _work_buffers(self, g: DeviceGraph, dtype, dev):
+        """Both iterate buffers, the affine term and the step workspace of this filter on this graph, kept between
+        solves (propagate() and tuner sweeps issue hundreds of solves on one graph: 4 allocations and a 64 MB memset
+        each otherwise).  Results are never views of these: every solve returns a fresh vector."""
+        key = (id(g.in_view), dtype)
+        cache = self.__dict__.setdefault("_buffers", {})
+        if key not in cache:
+            cache.clear()                                     # one graph at a time: do not pin the memory of old ones
+            n = g.n
+            cache[key] = ([torch.empty(n, dtype=dtype, device=dev), torch.empty(n, dtype=dtype, device=dev)],
+                          torch.empty(n, dtype=dtype, device=dev), g.in_view.new_span_ws(dtype), g.in_view)
+        zbuf, q, ws, _ = cache[key]
+        return zbuf, q, ws
 
 
 class RecursiveGraphFilter(GraphFilter):
@@ -416,15 +430,13 @@ class RecursiveGraphFilter(GraphFilter):
         state_f64, state_i32, err_hist = self._new_state(g, norm, alpha_s, self.use_quotient)
         sq = g.vec("sq", dtype)
         c = c_run if c_run is not None else g.vec("c", dtype)
-        zbuf = [torch.empty(n, dtype=dtype, device=dev), torch.empty(n, dtype=dtype, device=dev)]
-        q = torch.empty(n, dtype=dtype, device=dev)
+        view = g.in_view
+        zbuf, q, ws = self._work_buffers(g, dtype, dev)
         C.check(lib.pgb_affine_init(n, code, C.ptr(p), C.ptr(warm), C.ptr(sq), C.ptr(c), float(coef), C.ptr(coefvec),
                                     C.ptr(g.perm), 0, C.ptr(zbuf[0]), C.ptr(q), C.ptr(state_f64), st))
         C.check(lib.pgb_affine_init_finish(C.ptr(state_f64), C.ptr(state_i32), st))
         C.count_launches(3)                                   # init, init_finish, final unscale
-        view = g.in_view
         cs = view.cstruct(dtype)
-        ws = view.new_span_ws(dtype)
         symdeg = g.symdeg and w_run is None
         w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
         sq_arg = None if symdeg else sq

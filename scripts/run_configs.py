@@ -39,7 +39,7 @@ def timed(fn, reps=1):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tag", default="r1")
+    ap.add_argument("--tag", default="r2")
     ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
     import torch
@@ -92,6 +92,35 @@ def main():
             calls = (alg.convergence.iteration - 1) * len(seeds)
             c2[f"{label}_{name}"] = {"iterations": alg.convergence.iteration, "s_per_solve": dt / len(seeds),
                                      "gteps": g.nnz * calls / dt / 1e9}
+    # the same filters issued by the UNMODIFIED reference through the b200 backend plugin (deferred vectors -> PolyRun)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from refutil import import_pygrank
+        pg = import_pygrank()
+        if pg is not None:
+            from pygrank_b200 import backend as b200, lazy
+            pgb.install(pg)
+            b200.configure(dtype=torch.float32)
+            with pg.Backend("b200"):
+                pre = pgb.preprocessor(normalization="symmetric", assume_immutability=True)
+                pers = []
+                for s in seeds:
+                    pv = torch.zeros(n, dtype=torch.float32, device="cuda")
+                    pv[torch.from_numpy(s).cuda()] = 1.0
+                    pers.append(pv)
+                for label, mk in (("heat3", lambda: pg.HeatKernel(3, preprocessor=pre)),
+                                  ("generic40", lambda: pg.GenericGraphFilter(w40, error_type="iters", max_iters=41, preprocessor=pre))):
+                    alg = mk()
+                    b200.to_tensor(alg(pg.to_signal(g, pers[0])).np)
+                    lazy.reset_stats()
+                    dt, _ = timed(lambda: [b200.to_tensor(alg(pg.to_signal(g, pv)).np) for pv in pers])
+                    calls = (alg.convergence.iteration - 1) * len(seeds)
+                    c2[f"{label}_f32_plugin"] = {"iterations": alg.convergence.iteration, "s_per_solve": dt / len(seeds),
+                                                 "gteps": g.nnz * calls / dt / 1e9, "lazy_stats": dict(lazy.STATS)}
+            pg.load_backend("numpy")
+            b200.configure(dtype=torch.float64)
+    except Exception as exc:   # reported, not fatal
+        c2["plugin_error"] = repr(exc)[:300]
     # parity at a CPU-sized scale
     ps = 16
     gs = device_synthetic.rmat_graph_device(ps, 16, seed=1)
