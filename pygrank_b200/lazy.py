@@ -481,8 +481,11 @@ def _pure_key(v, depth=0):
 
 
 def _pure_value(v: LazyVec, key) -> torch.Tensor:
+    """Value of a conv-free expression, memoised by structure + identity of its leaf tensors.  A hit is only valid while
+    no leaf has been written in place since (``signal[v] = x`` mutates the backend vector of a GraphSignal,
+    core/signals.py:92-93): torch's per-tensor version counters tell."""
     hit = _pure_cache.get(key)
-    if hit is not None:
+    if hit is not None and all(t._version == ver for t, ver in zip(hit[1], hit[2])):
         return hit[0]
     leaves = []
 
@@ -497,7 +500,8 @@ def _pure_value(v: LazyVec, key) -> torch.Tensor:
     out = _materialize_copy(v)
     if len(_pure_cache) > 64:
         _pure_cache.pop(next(iter(_pure_cache)))
-    _pure_cache[key] = (out, leaves)      # the leaves stay referenced so their ids cannot be recycled
+    # the leaves stay referenced so their ids cannot be recycled
+    _pure_cache[key] = (out, leaves, [t._version for t in leaves])
     return out
 
 

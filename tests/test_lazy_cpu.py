@@ -144,3 +144,16 @@ def test_lazy_scalar_and_vector_arithmetic_matches_numpy(setup):
     for _ in range(3000):                                           # chains as deep as max_iters do not recurse
         deep = deep * 1.0 + p * 0.0
     assert np.allclose(np.asarray(deep), xn)
+
+
+def test_loop_invariant_cache_notices_in_place_writes(setup):
+    """personalization * (1 - alpha) is evaluated once per run and memoised by tensor identity; writing into the
+    personalization (GraphSignal.__setitem__, core/signals.py:92-93) must invalidate it."""
+    g, M, p, x = setup
+    expr = lambda: p * 0.15
+    k = lazy._pure_key(expr())
+    first = lazy._pure_value(expr(), k).clone()
+    assert lazy._pure_value(expr(), k) is lazy._pure_value(expr(), k)            # memoised
+    p[3] = 100.0
+    second = lazy._pure_value(expr(), lazy._pure_key(expr()))
+    assert float(second[3]) == pytest.approx(15.0) and float(first[3]) != float(second[3])
