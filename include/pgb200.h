@@ -324,6 +324,25 @@ int pgb_affine_steps_batched(const pgb_csr *g, int dtype, double alpha, const vo
                              int32_t *state_i32, double *err_hist, int32_t hist_stride, pgb_span_ws ws,
                              int first_step, int num_launches, void *stream);
 
+/* K3 on the hub-blocked form — the fast path of NodeRanking.propagate (core/signals.py:225-226) and of alpha sweeps
+ * (algorithms/autotune/optimization.py:160-180 evaluates one candidate after the other): PB =
+ * pgb_hsell_panel_width(dtype) columns (4 x fp32 / 2 x fp64 = 16 bytes per node) advance together through a pgb_hsell
+ * built with block_cols = pgb_hsell_panel_block_cols() (8192 nodes = 128 KB of [node][PB] per hub block; the builders
+ * do not depend on the element type).  The gather kernel is the single-vector one instantiated on 16-byte elements:
+ * one 16-bit hub index feeds one LDS.128, one tail index one 16-byte texel, a piece leaves as one 16-byte RED per
+ * lane into yacc [(n_slices + 1) * 32][PB] (zero at the first launch; the update pass re-zeroes it).  Vectors z, q are
+ * [n][PB] row-major, w / sq / c per row as in pgb_affine_steps (w = sq = NULL: derived from `indptr`).  alpha is a HOST
+ * array of PB per-column multipliers.  state_f64 [PB][PGB_STATE_F64_LEN]; state_i32 [PB][PGB_STATE_I32_LEN] followed
+ * by TWO shared words (ticket, panel stop word: set once every column has stopped, later launches are no-ops);
+ * err_hist [PB][hist_stride].  Columns stop one by one exactly as in pgb_affine_steps_batched.  tail_queue: one zeroed
+ * uint32 (pgb_span_ws.cnt).  Single-GPU forms only (n_segments == 1), accumulate mode, no in-kernel dropout. */
+int pgb_hsell_panel_width(int dtype);
+int pgb_hsell_panel_block_cols(void);
+int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype, const double *alpha, const void *w,
+                           const void *sq, const void *c, const void *q, void *zbuf0, void *zbuf1, double *state_f64,
+                           int32_t *state_i32, double *err_hist, int32_t hist_stride, void *yacc, uint32_t *tail_queue,
+                           int first_step, int num_launches, void *stream);
+
 /* ---- row-partitioned multi-GPU: the exchange fused into the step (no reference counterpart) ----------
  * Every rank keeps the full gather vector (both buffers) and a slot array for the convergence sums in
  * PEER-MAPPED memory (e.g. torch symmetric memory over NVLink / NVSwitch).  The update kernel then

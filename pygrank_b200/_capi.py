@@ -107,6 +107,11 @@ _SIGNATURES = {
     "pgb_affine_steps_batched": (c_int, [POINTER(Csr), c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, SpanWs,
                                          c_int, c_int, c_void_p]),
+    "pgb_hsell_panel_width": (c_int, [c_int]),
+    "pgb_hsell_panel_block_cols": (c_int, []),
+    "pgb_affine_steps_panel": (c_int, [POINTER(Hsell), c_void_p, c_int, POINTER(c_double), c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                       c_void_p, c_int, c_int, c_void_p]),
     "pgb_state_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgb_affine_step_peer": (c_int, [POINTER(Csr), c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, POINTER(Peers),

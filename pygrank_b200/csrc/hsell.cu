@@ -337,6 +337,63 @@ __device__ __forceinline__ bool kept(const DropParams &D, uint64_t slot) {
     return (uint32_t)(mix64(D.key ^ (slot * 0xD1342543DE82EF95ull)) >> 32) >= D.thr;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Panel elements.  The same gather kernel runs on a PANEL of seed columns when the element type of z is a 16-byte
+// vector — 4 x fp32 or 2 x fp64 per node (z is [n_cols][PB] row-major): one 16-bit hub index (or one 32-bit tail
+// index) then fetches PB useful values with one LDS.128 / one 16-byte texel, the index streams, the chunk
+// bookkeeping and the hub-block reloads are paid once per panel instead of once per column, and a piece leaves
+// as one 16-byte RED per lane (red.global.add.v4.f32 on sm_100a).  Hub blocks hold 8192 nodes (128 KB).
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) f32x4 {
+    float4 v;
+    __device__ __forceinline__ f32x4() {}
+    __device__ __forceinline__ f32x4(float s) { v = make_float4(s, s, s, s); }
+    __device__ __forceinline__ f32x4(float4 q) : v(q) {}
+    __device__ __forceinline__ f32x4 &operator+=(const f32x4 &o) {
+        v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w;
+        return *this;
+    }
+};
+__device__ __forceinline__ f32x4 operator+(f32x4 a, const f32x4 &b) { return a += b; }
+__device__ __forceinline__ f32x4 operator*(const f32x4 &a, const f32x4 &b) {
+    return f32x4(make_float4(a.v.x * b.v.x, a.v.y * b.v.y, a.v.z * b.v.z, a.v.w * b.v.w));
+}
+struct __align__(16) f64x2 {
+    double2 v;
+    __device__ __forceinline__ f64x2() {}
+    __device__ __forceinline__ f64x2(double s) { v = make_double2(s, s); }
+    __device__ __forceinline__ f64x2(double2 q) : v(q) {}
+    __device__ __forceinline__ f64x2 &operator+=(const f64x2 &o) {
+        v.x += o.v.x; v.y += o.v.y;
+        return *this;
+    }
+};
+__device__ __forceinline__ f64x2 operator+(f64x2 a, const f64x2 &b) { return a += b; }
+__device__ __forceinline__ f64x2 operator*(const f64x2 &a, const f64x2 &b) {
+    return f64x2(make_double2(a.v.x * b.v.x, a.v.y * b.v.y));
+}
+
+// what the gather kernel needs of an element type: a read-only load, a RED, a texel fetch, a texture format
+enum { ELEM_F32 = 0, ELEM_F64 = 1, ELEM_F32X4 = 2, ELEM_F64X2 = 3 };
+template <typename T> struct Elem;
+template <> struct Elem<float> { static constexpr int kind = ELEM_F32; };
+template <> struct Elem<double> { static constexpr int kind = ELEM_F64; };
+template <> struct Elem<f32x4> { static constexpr int kind = ELEM_F32X4; };
+template <> struct Elem<f64x2> { static constexpr int kind = ELEM_F64X2; };
+
+__device__ __forceinline__ float ld_ro(const float *p) { return __ldg(p); }
+__device__ __forceinline__ double ld_ro(const double *p) { return __ldg(p); }
+__device__ __forceinline__ f32x4 ld_ro(const f32x4 *p) { return f32x4(__ldg(reinterpret_cast<const float4 *>(p))); }
+__device__ __forceinline__ f64x2 ld_ro(const f64x2 *p) { return f64x2(__ldg(reinterpret_cast<const double2 *>(p))); }
+
+__device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(f32x4 *p, const f32x4 &v) { atomicAdd(reinterpret_cast<float4 *>(p), v.v); }
+__device__ __forceinline__ void red_add(f64x2 *p, const f64x2 &v) {
+    atomicAdd(reinterpret_cast<double *>(p), v.v.x);
+    atomicAdd(reinterpret_cast<double *>(p) + 1, v.v.y);
+}
+
 struct GatherParams {
     pgb_hsell h;
     const void *z;
@@ -358,14 +415,17 @@ struct GatherParams {
 template <bool ACCUM, typename T>
 __device__ __forceinline__ void flush_piece(T *__restrict__ dst, int row, int lane, T v) {
     if (ACCUM)
-        atomicAdd(dst + (int64_t)row * 32 + lane, v);
+        red_add(dst + (int64_t)row * 32 + lane, v);
     else
         dst[(int64_t)row * 32 + lane] = v;
 }
 
 constexpr int CH = PGB_HSELL_CHUNK;   // rounds per chunk
-constexpr int BATCH = 8;              // rounds loaded ahead per lane
+constexpr int BATCH = 8;              // rounds loaded ahead per lane (scalar elements)
 static_assert(CH == 32 && CH % BATCH == 0, "the end mask of a chunk is one 32-bit word");
+// 16-byte elements keep 4 rounds in flight: the same bytes per lane, and the gathered values still fit the 64
+// registers a 1024-thread CTA leaves each thread
+template <typename T> struct BatchOf { static constexpr int value = sizeof(T) > 8 ? 4 : BATCH; };
 
 // One chunk of the hub stream: 32 rounds, two shared-memory gathers per lane and round.
 template <typename T, bool ACCUM, bool DROP>
@@ -426,6 +486,13 @@ __device__ __forceinline__ double tex_fetch(cudaTextureObject_t t, int c, double
     const int2 v = tex1Dfetch<int2>(t, c);
     return __hiloint2double(v.y, v.x);
 }
+__device__ __forceinline__ f32x4 tex_fetch(cudaTextureObject_t t, int c, const f32x4 &) {
+    return f32x4(tex1Dfetch<float4>(t, c));
+}
+__device__ __forceinline__ f64x2 tex_fetch(cudaTextureObject_t t, int c, const f64x2 &) {
+    const int4 v = tex1Dfetch<int4>(t, c);
+    return f64x2(make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z)));
+}
 
 // One chunk of the tail stream: 32 rounds, one L2 gather per lane and round (padding lanes are off).
 template <typename T, bool TEX, bool ACCUM, bool DROP>
@@ -433,41 +500,42 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
                                            uint32_t endmask, const int32_t *__restrict__ piece_row,
                                            const T *__restrict__ z, cudaTextureObject_t ztex,
                                            T *__restrict__ partials, int lane, const DropParams &D) {
+    constexpr int B = BatchOf<T>::value;
     const T dscale = DROP ? (T)D.scale : (T)1;
     const uint64_t tslot0 = (1ull << 62) + (uint64_t)chunk * (CH * 32) + (uint64_t)lane;   // + round * 32
     const int32_t *d = cols + chunk * (CH * 32) + lane;
     endmask |= 0x80000000u;
     const int my_row = (lane < __popc(endmask)) ? __ldg(piece_row + p_first + lane) : 0;
-    int32_t c[BATCH], nx[BATCH];
+    int32_t c[B], nx[B];
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) c[u] = ld_stream(d + u * 32);
+    for (int u = 0; u < B; ++u) c[u] = ld_stream(d + u * 32);
     T a0 = (T)0, a1 = (T)0;
     int p = 0;
 #pragma unroll
-    for (int bt = 0; bt < CH / BATCH; ++bt) {
-        T x[BATCH];
+    for (int bt = 0; bt < CH / B; ++bt) {
+        T x[B];
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const bool on = c[u] >= 0 && kept<DROP>(D, tslot0 + (uint64_t)(bt * BATCH + u) * 32);
+        for (int u = 0; u < B; ++u) {
+            const bool on = c[u] >= 0 && kept<DROP>(D, tslot0 + (uint64_t)(bt * B + u) * 32);
             if (TEX)
-                x[u] = on ? tex_fetch(ztex, c[u], (T)0) : (T)0;
+                x[u] = on ? tex_fetch(ztex, c[u], T()) : (T)0;
             else
-                x[u] = on ? __ldg(z + c[u]) : (T)0;
+                x[u] = on ? ld_ro(z + c[u]) : (T)0;
         }
-        if (bt + 1 < CH / BATCH) {
+        if (bt + 1 < CH / B) {
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) nx[u] = ld_stream(d + ((bt + 1) * BATCH + u) * 32);
+            for (int u = 0; u < B; ++u) nx[u] = ld_stream(d + ((bt + 1) * B + u) * 32);
         }
-        const uint32_t m8 = (endmask >> (bt * BATCH)) & 0xffu;
+        const uint32_t m8 = (endmask >> (bt * B)) & ((1u << B) - 1u);
         if (m8 == 0u) {
 #pragma unroll
-            for (int u = 0; u < BATCH; u += 2) {
+            for (int u = 0; u < B; u += 2) {
                 a0 += x[u];
                 a1 += x[u + 1];
             }
         } else {
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
+            for (int u = 0; u < B; ++u) {
                 a0 += x[u];
                 if ((m8 >> u) & 1u) {
                     flush_piece<ACCUM>(partials, __shfl_sync(0xffffffffu, my_row, p), lane, (a0 + a1) * dscale);
@@ -477,7 +545,7 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
             }
         }
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) c[u] = nx[u];
+        for (int u = 0; u < B; ++u) c[u] = nx[u];
     }
 }
 
@@ -536,9 +604,9 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
                 const float4 *s4 = reinterpret_cast<const float4 *>(src);
                 float4 *d4 = reinterpret_cast<float4 *>(dst);
                 for (int i = tid; i < nv; i += HS_THREADS) d4[i] = __ldg(s4 + i);
-                for (int i = nv * V + tid; i < cnt; i += HS_THREADS) dst[i] = __ldg(src + i);
+                for (int i = nv * V + tid; i < cnt; i += HS_THREADS) dst[i] = ld_ro(src + i);
             } else {
-                for (int i = tid; i < cnt; i += HS_THREADS) dst[i] = __ldg(src + i);
+                for (int i = tid; i < cnt; i += HS_THREADS) dst[i] = ld_ro(src + i);
             }
             for (int i = cnt + tid; i < Hs; i += HS_THREADS) dst[i] = (T)0;
         }
@@ -787,6 +855,195 @@ __global__ void __launch_bounds__(UPA_BLOCK) hsell_update_accum_kernel(const Ste
     if (MODE != MODE_CONV) step_epilogue(P, update, s_red);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Kernel B of the PANEL path (K3 on the hub-blocked form): PB seed columns advance together, every column with its
+// own alpha, normaliser, error sum and stop decision (finalize_column) — NodeRanking.propagate
+// (/root/reference/pygrank/core/signals.py:225-226) runs one solve per column; a frozen column keeps z' = z from the
+// iteration at which the reference's per-column loop would have stopped.  One thread per row and pass: the row's PB
+// gathered sums (y, then zeroed), z, q move as 16-byte vectors, the per-row factors once for all columns.
+// ---------------------------------------------------------------------------------------------
+struct PanelStep {
+    int64_t n;
+    const int32_t *indptr;   // SYMDEG: degree-derived w / sq
+    const void *zin, *q;     // [n][PB]
+    void *zout;              // [n][PB]
+    const void *w, *sq, *c;  // per row
+    void *y;                 // [(n_slices + 1) * 32][PB]
+    double alpha[4];         // per column
+    double *sf;              // [PB][PGB_STATE_F64_LEN]
+    int32_t *si;             // [PB][PGB_STATE_I32_LEN], then the shared ticket and the panel stop word
+    double *err_hist;        // [PB][hist_stride]
+    int32_t hist_stride;
+    uint32_t *tail_queue;
+};
+
+template <typename S, int PB> struct alignas(16) Pack { S v[PB]; };
+__device__ __forceinline__ Pack<float, 4> ld_pack(const float *p) {
+    const float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
+    Pack<float, 4> r;
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    return r;
+}
+__device__ __forceinline__ Pack<double, 2> ld_pack(const double *p) {
+    const double2 t = __ldcs(reinterpret_cast<const double2 *>(p));
+    Pack<double, 2> r;
+    r.v[0] = t.x; r.v[1] = t.y;
+    return r;
+}
+__device__ __forceinline__ void st_pack(float *p, const Pack<float, 4> &r) {
+    *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+__device__ __forceinline__ void st_pack(double *p, const Pack<double, 2> &r) {
+    *reinterpret_cast<double2 *>(p) = make_double2(r.v[0], r.v[1]);
+}
+
+constexpr int UPP_BLOCK = 256;
+constexpr int UPP_ROWS = 2;
+template <typename S, int PB, bool SYMDEG>
+__global__ void __launch_bounds__(UPP_BLOCK) hsell_update_panel_kernel(const PanelStep P) {
+    __shared__ double s_red[2][UPP_BLOCK / 32][PB];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool active[PB];
+    S invS[PB], alpha[PB];
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < PB; ++c) {
+        active[c] = P.si[c * PGB_STATE_I32_LEN + PGB_SI_STOP] == PGB_RUNNING;
+        invS[c] = (S)P.sf[c * PGB_STATE_F64_LEN + PGB_SF_INVS];
+        alpha[c] = (S)P.alpha[c];
+        any = any || active[c];
+    }
+    if (!any) return;   // run-ahead launch after every column has stopped
+    const int err_mode = P.si[PGB_SI_ERR_MODE];
+    const bool is_max = err_mode == PGB_ERR_MAX;
+    double err[PB], tsum[PB];
+#pragma unroll
+    for (int c = 0; c < PB; ++c) err[c] = tsum[c] = 0.0;
+    const S *__restrict__ zin = (const S *)P.zin;
+    const S *__restrict__ qv = (const S *)P.q;
+    S *__restrict__ zout = (S *)P.zout;
+    S *__restrict__ y = (S *)P.y;
+    const int64_t n = P.n;
+    const int64_t stride = (int64_t)gridDim.x * UPP_BLOCK;
+    for (int64_t base = blockIdx.x * (int64_t)UPP_BLOCK + tid; base < n; base += stride * UPP_ROWS) {
+        Pack<S, PB> acc[UPP_ROWS], zi[UPP_ROWS], qi[UPP_ROWS];
+        S wi[UPP_ROWS], sqi[UPP_ROWS], ci[UPP_ROWS];
+        int ip0[UPP_ROWS], ip1[UPP_ROWS];
+#pragma unroll
+        for (int k = 0; k < UPP_ROWS; ++k) {
+            const int64_t row = base + k * stride;
+            ip0[k] = ip1[k] = 0;
+            wi[k] = sqi[k] = ci[k] = (S)0;
+            if (row < n) {
+                acc[k] = ld_pack(y + row * PB);
+                zi[k] = ld_pack(zin + row * PB);
+                qi[k] = ld_pack(qv + row * PB);
+                ci[k] = ld_stream((const S *)P.c + row);
+                if (SYMDEG) {
+                    ip0[k] = P.indptr[row];
+                    ip1[k] = P.indptr[row + 1];
+                } else {
+                    wi[k] = ld_stream((const S *)P.w + row);
+                    sqi[k] = ld_stream((const S *)P.sq + row);
+                }
+            }
+        }
+        S berr[PB], bt[PB];
+#pragma unroll
+        for (int c = 0; c < PB; ++c) berr[c] = bt[c] = (S)0;
+#pragma unroll
+        for (int k = 0; k < UPP_ROWS; ++k) {
+            const int64_t row = base + k * stride;
+            if (row < n) {
+                if (SYMDEG) {
+                    const int deg = ip1[k] - ip0[k];
+                    wi[k] = deg > 0 ? RowMath<S>::inv((S)deg) : (S)0;
+                    sqi[k] = deg > 0 ? RowMath<S>::root((S)deg) : (S)1;
+                }
+                Pack<S, PB> zn, zero;
+#pragma unroll
+                for (int c = 0; c < PB; ++c) {
+                    zero.v[c] = (S)0;
+                    zn.v[c] = zi[k].v[c];
+                    if (active[c]) {
+                        const S znew = (alpha[c] * wi[k] * acc[k].v[c] + qi[k].v[c]) * invS[c];
+                        zn.v[c] = znew;
+                        S d = znew - zi[k].v[c];
+                        d = sqi[k] * (d < (S)0 ? -d : d);
+                        if (is_max)
+                            berr[c] = berr[c] > d ? berr[c] : d;
+                        else
+                            berr[c] += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+                        bt[c] += znew * ci[k];
+                    }
+                }
+                st_pack(y + row * PB, zero);
+                st_pack(zout + row * PB, zn);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < PB; ++c) {
+            if (is_max)
+                err[c] = err[c] > (double)berr[c] ? err[c] : (double)berr[c];
+            else
+                err[c] += (double)berr[c];
+            tsum[c] += (double)bt[c];
+        }
+    }
+    if (tid == 0 && blockIdx.x == 0 && P.tail_queue) P.tail_queue[0] = 0u;   // tail queue of the next gather
+    // per-column grid reduction: warp, CTA, one atomic per CTA and column; the last CTA plays ConvergenceManager
+#pragma unroll
+    for (int c = 0; c < PB; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double e2 = __shfl_xor_sync(0xffffffffu, err[c], o);
+            err[c] = is_max ? (err[c] > e2 ? err[c] : e2) : err[c] + e2;
+            tsum[c] += __shfl_xor_sync(0xffffffffu, tsum[c], o);
+        }
+        if (lane == 0) {
+            s_red[0][warp][c] = err[c];
+            s_red[1][warp][c] = tsum[c];
+        }
+    }
+    __syncthreads();
+    if (tid < PB) {
+        double e = 0.0, t = 0.0;
+        for (int wv = 0; wv < UPP_BLOCK / 32; ++wv) {
+            const double e2 = s_red[0][wv][tid];
+            e = is_max ? (e > e2 ? e : e2) : e + e2;
+            t += s_red[1][wv][tid];
+        }
+        if (is_max)
+            atomicMax((unsigned long long *)&P.sf[tid * PGB_STATE_F64_LEN + PGB_SF_EACC], (unsigned long long)__double_as_longlong(e));
+        else
+            atomicAdd(&P.sf[tid * PGB_STATE_F64_LEN + PGB_SF_EACC], e);
+        atomicAdd(&P.sf[tid * PGB_STATE_F64_LEN + PGB_SF_TACC], t);
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int ticket = atomicAdd(&P.si[PB * PGB_STATE_I32_LEN], 1);
+        s_last = (ticket == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (tid < PB)
+            finalize_column(P.sf + tid * PGB_STATE_F64_LEN, P.si + tid * PGB_STATE_I32_LEN,
+                            P.err_hist ? P.err_hist + (int64_t)tid * P.hist_stride : nullptr);
+        __syncthreads();
+        if (tid == 0) {
+            volatile int32_t *vsi = P.si;
+            bool running = false;
+            for (int c = 0; c < PB; ++c) running = running || vsi[c * PGB_STATE_I32_LEN + PGB_SI_STOP] == PGB_RUNNING;
+            vsi[PB * PGB_STATE_I32_LEN + 1] = running ? PGB_RUNNING : PGB_CONVERGED;   // the gather's stop word
+            vsi[PB * PGB_STATE_I32_LEN] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // Linear texture objects over gather vectors, keyed by (device, address, bytes): the filters alternate two z
 // buffers per solve and torch's allocator hands the same blocks out again, so a small LRU table suffices.
 // Returns 0 when the vector cannot be a linear texture (alignment, size): the caller then gathers with LDG.
@@ -801,14 +1058,14 @@ static TexEntry g_tex[64];
 static uint64_t g_tex_stamp = 0;
 static std::mutex g_tex_mutex;
 
-static cudaTextureObject_t texture_for(const void *z, size_t elems, int dtype) {
+static cudaTextureObject_t texture_for(const void *z, size_t elems, int dtype /* ELEM_* */) {
     static int enabled = -1;
     if (enabled < 0) {
         const char *e = getenv("PGB_HSELL_TEX");
         enabled = e ? atoi(e) : 1;
     }
     if (!enabled || !z || elems == 0) return 0;
-    const size_t bytes = elems * (dtype == PGB_F32 ? 4 : 8);
+    const size_t bytes = elems * (dtype == ELEM_F32 ? 4 : (dtype == ELEM_F64 ? 8 : 16));
     const int dev = current_device();
     std::lock_guard<std::mutex> lock(g_tex_mutex);
     int victim = 0;
@@ -828,7 +1085,10 @@ static cudaTextureObject_t texture_for(const void *z, size_t elems, int dtype) {
     memset(&rd, 0, sizeof(rd));
     rd.resType = cudaResourceTypeLinear;
     rd.res.linear.devPtr = const_cast<void *>(z);
-    rd.res.linear.desc = dtype == PGB_F32 ? cudaCreateChannelDesc<float>() : cudaCreateChannelDesc<int2>();
+    rd.res.linear.desc = dtype == ELEM_F32     ? cudaCreateChannelDesc<float>()
+                         : dtype == ELEM_F64   ? cudaCreateChannelDesc<int2>()
+                         : dtype == ELEM_F32X4 ? cudaCreateChannelDesc<float4>()
+                                               : cudaCreateChannelDesc<int4>();
     rd.res.linear.sizeInBytes = bytes;
     cudaTextureDesc td;
     memset(&td, 0, sizeof(td));
@@ -894,7 +1154,7 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool
         if (tail_batch < 1) tail_batch = 1;
     }
     G.tail_batch = tail_batch;
-    G.ztex = h->n_tail_chunks > 0 ? texture_for(z, (size_t)h->seg_len * (size_t)h->n_segments, sizeof(T) == 4 ? PGB_F32 : PGB_F64) : 0;
+    G.ztex = h->n_tail_chunks > 0 ? texture_for(z, (size_t)h->seg_len * (size_t)h->n_segments, Elem<T>::kind) : 0;
     if (accum && !h->piece_slice) return fail("hsell: accumulate mode needs pgb_hsell.piece_slice");
     const bool drop = g_drop_p > 0.0;
     (void)step;
@@ -902,17 +1162,56 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool
     G.drop.thr = drop ? (uint32_t)(g_drop_p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : g_drop_p * 4294967296.0) : 0u;
     G.drop.scale = drop ? (float)(1.0 / (1.0 - g_drop_p)) : 1.0f;
     const int n = h->n_ctas;
-    const int sel = (G.ztex ? 4 : 0) | (accum ? 2 : 0) | (drop ? 1 : 0);
-    switch (sel) {
-        case 0: return launch_gather_variant<T, false, false, false>(G, n, smem, st);
-        case 1: return launch_gather_variant<T, false, false, true>(G, n, smem, st);
-        case 2: return launch_gather_variant<T, false, true, false>(G, n, smem, st);
-        case 3: return launch_gather_variant<T, false, true, true>(G, n, smem, st);
-        case 4: return launch_gather_variant<T, true, false, false>(G, n, smem, st);
-        case 5: return launch_gather_variant<T, true, false, true>(G, n, smem, st);
-        case 6: return launch_gather_variant<T, true, true, false>(G, n, smem, st);
-        default: return launch_gather_variant<T, true, true, true>(G, n, smem, st);
+    if constexpr (sizeof(T) == 16) {   // panel elements: accumulate mode, no dropout
+        if (!accum || drop) return fail("hsell panel: only the accumulate mode without graph_dropout is built");
+        return G.ztex ? launch_gather_variant<T, true, true, false>(G, n, smem, st)
+                      : launch_gather_variant<T, false, true, false>(G, n, smem, st);
+    } else {
+        const int sel = (G.ztex ? 4 : 0) | (accum ? 2 : 0) | (drop ? 1 : 0);
+        switch (sel) {
+            case 0: return launch_gather_variant<T, false, false, false>(G, n, smem, st);
+            case 1: return launch_gather_variant<T, false, false, true>(G, n, smem, st);
+            case 2: return launch_gather_variant<T, false, true, false>(G, n, smem, st);
+            case 3: return launch_gather_variant<T, false, true, true>(G, n, smem, st);
+            case 4: return launch_gather_variant<T, true, false, false>(G, n, smem, st);
+            case 5: return launch_gather_variant<T, true, false, true>(G, n, smem, st);
+            case 6: return launch_gather_variant<T, true, true, false>(G, n, smem, st);
+            default: return launch_gather_variant<T, true, true, true>(G, n, smem, st);
+        }
     }
+}
+
+template <typename S, typename V, int PB>
+static int panel_steps(const pgb_hsell *h, const PanelStep &P0, void *zbuf0, void *zbuf1, int first_step, int num_launches,
+                       bool symdeg, cudaStream_t st) {
+    PanelStep P = P0;
+    void *buf[2] = {zbuf0, zbuf1};
+    const int32_t *stop = P.si + PB * PGB_STATE_I32_LEN + 1;
+    static PerDeviceInt ctas_on[2];
+    int &ctas = ctas_on[symdeg ? 1 : 0].here();
+    if (ctas == 0) {
+        int v = 0;
+        const cudaError_t e = symdeg
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_panel_kernel<S, PB, true>, UPP_BLOCK, 0)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_panel_kernel<S, PB, false>, UPP_BLOCK, 0);
+        ctas = (e == cudaSuccess && v >= 1) ? v : 4;
+    }
+    int64_t want = ceil_div(P.n, (int64_t)UPP_BLOCK * UPP_ROWS);
+    const int64_t cap = (int64_t)sm_count() * ctas;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    for (int j = 0; j < num_launches; ++j) {
+        const int k = first_step + j;
+        P.zin = buf[(k - 1) & 1];
+        P.zout = buf[k & 1];
+        if (launch_gather<V>(h, P.zin, P.y, true, stop, P.tail_queue, k, st)) return 1;
+        if (symdeg)
+            hsell_update_panel_kernel<S, PB, true><<<(int)want, UPP_BLOCK, 0, st>>>(P);
+        else
+            hsell_update_panel_kernel<S, PB, false><<<(int)want, UPP_BLOCK, 0, st>>>(P);
+        PGB_LAUNCH_OK("hsell_update_panel_kernel");
+    }
+    return 0;
 }
 
 template <typename T>
@@ -1028,6 +1327,44 @@ int pgb_hsell_max_block_cols(int dtype) {
     int cols = (HS_SMEM_LIMIT - 64) / bytes - 1;
     if (cols > 65535) cols = 65535;
     return cols & ~63;   // keeps every block start 16-byte aligned for the vector loader
+}
+
+int pgb_hsell_panel_width(int dtype) { return dtype == PGB_F32 ? 4 : (dtype == PGB_F64 ? 2 : 0); }
+
+int pgb_hsell_panel_block_cols(void) { return (128 * 1024) / 16; }
+
+int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype, const double *alpha, const void *w,
+                           const void *sq, const void *c, const void *q, void *zbuf0, void *zbuf1, double *state_f64,
+                           int32_t *state_i32, double *err_hist, int32_t hist_stride, void *yacc, uint32_t *tail_queue,
+                           int first_step, int num_launches, void *stream) {
+    if (!h) return fail("pgb_affine_steps_panel: null hsell form");
+    if (h->n_segments != 1) return fail("pgb_affine_steps_panel: row-partitioned forms are not supported");
+    if (!h->piece_slice) return fail("pgb_affine_steps_panel needs pgb_hsell.piece_slice");
+    if ((w == nullptr) != (sq == nullptr)) return fail("pgb_affine_steps_panel: w and sq must both be given or both be NULL");
+    if (!w && !indptr) return fail("pgb_affine_steps_panel: degree-derived factors need the row pointers");
+    if (first_step < 1) return fail("pgb_affine_steps_panel: first_step must be >= 1");
+    if (!alpha || !yacc || !tail_queue) return fail("pgb_affine_steps_panel: alpha, yacc and tail_queue are required");
+    if (h->n_rows == 0) return 0;
+    const int PB = pgb_hsell_panel_width(dtype);
+    if (!PB) return fail("pgb_affine_steps_panel: unknown dtype %d", dtype);
+    PanelStep P;
+    memset(&P, 0, sizeof(P));
+    P.n = h->n_rows;
+    P.indptr = indptr;
+    P.q = q;
+    P.w = w;
+    P.sq = sq;
+    P.c = c;
+    P.y = yacc;
+    for (int i = 0; i < PB; ++i) P.alpha[i] = alpha[i];
+    P.sf = state_f64;
+    P.si = state_i32;
+    P.err_hist = err_hist;
+    P.hist_stride = hist_stride;
+    P.tail_queue = tail_queue;
+    const bool symdeg = (w == nullptr);
+    if (dtype == PGB_F32) return panel_steps<float, f32x4, 4>(h, P, zbuf0, zbuf1, first_step, num_launches, symdeg, as_stream(stream));
+    return panel_steps<double, f64x2, 2>(h, P, zbuf0, zbuf1, first_step, num_launches, symdeg, as_stream(stream));
 }
 
 int pgb_hsell_set_dropout(double p, uint64_t seed) {

@@ -79,6 +79,33 @@ __device__ __forceinline__ void finalize_state(double *sf, int32_t *si, double *
     __threadfence();
 }
 
+// per-column ConvergenceManager (same rules as finalize_state; used by the panel kernels of spmm_fused.cu and hsell.cu)
+__device__ __forceinline__ void finalize_column(double *sf, int32_t *si, double *err_hist) {
+    volatile double *vsf = sf;
+    volatile int32_t *vsi = si;
+    const double tacc = vsf[PGB_SF_TACC], eacc = vsf[PGB_SF_EACC];
+    vsf[PGB_SF_TACC] = 0.0;
+    vsf[PGB_SF_EACC] = 0.0;
+    if (vsi[PGB_SI_STOP] != PGB_RUNNING) return;
+    const int k = vsi[PGB_SI_STEPS] + 1;
+    vsi[PGB_SI_STEPS] = k;
+    const int it = k + 1;
+    const double errv = eacc / vsf[PGB_SF_MEAN];
+    vsf[PGB_SF_LASTERR] = errv;
+    if (err_hist) err_hist[k] = errv;
+    int stop = PGB_RUNNING;
+    if (it >= vsi[PGB_SI_MAX_ITERS])
+        stop = PGB_MAX_ITERS;
+    else if (vsi[PGB_SI_ERR_MODE] != PGB_ERR_ITERS && (it % vsi[PGB_SI_END_MODULO]) == 0 && errv <= vsf[PGB_SF_TOL])
+        stop = PGB_CONVERGED;
+    if (stop != PGB_RUNNING) {
+        vsi[PGB_SI_ITERATION] = it;
+        vsi[PGB_SI_STOP] = stop;
+    } else if (vsi[PGB_SI_QUOTIENT]) {
+        vsf[PGB_SF_INVS] = 1.0 / (vsf[PGB_SF_ALPHA] * tacc + vsf[PGB_SF_BIAS]);
+    }
+}
+
 template <typename T>
 struct RowMath;
 template <>

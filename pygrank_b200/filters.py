@@ -170,7 +170,7 @@ class GraphFilter:
         cols = features if isinstance(features, torch.Tensor) else torch.as_tensor(np.asarray(features))
         if cols.dim() != 2 or cols.shape[0] != g.n:
             raise Exception("propagate expects a features matrix with one row per node")
-        if self._can_batch(g, *args, **kwargs):
+        if self._can_batch(g, *args, n_columns=int(cols.shape[1]), **kwargs):
             return self._propagate_batched(g, cols, *args, **kwargs)
         self.convergence.iterations = []
         out = torch.empty((g.n, int(cols.shape[1])), dtype=self.dtype, device=g.out_view.indptr.device)
@@ -179,7 +179,7 @@ class GraphFilter:
             self.convergence.iterations.append(self.convergence.iteration)
         return out
 
-    def _can_batch(self, g, *args, **kwargs) -> bool:
+    def _can_batch(self, g, *args, n_columns: int = 2, **kwargs) -> bool:
         return False
 
     def _check_dropout(self, g: DeviceGraph):
@@ -298,21 +298,39 @@ class RecursiveGraphFilter(GraphFilter):
     def _run(self, g, p, norm, warm, **kwargs):
         return self._affine(g, p, norm, warm, **self._affine_args(g, **kwargs))
 
-    def _can_batch(self, g, warm_start=None, graph_dropout: float = 0, **kwargs) -> bool:
-        # The panel kernel streams no edge values (every BASELINE config is unweighted).  It gathers from
-        # L2/HBM (8 columns per 32-byte sector); measured on RMAT-24 it advances a column-iteration in
-        # 1.09 ms, the hub-blocked single-vector kernel (csrc/hsell.cu) in 0.67 ms, so propagate() runs the
-        # columns one after the other through hsell whenever that form exists and uses the panel kernel
-        # otherwise (PGB_PANEL=1 forces it: parity tests and A/B timing).
-        if g.in_view.weighted or warm_start is not None or graph_dropout != 0 or g.pathological:
-            return False
-        if _error_code(self.convergence.error_type) == C.ERR_MAX:
-            return False                                      # the panel kernel has no max reduction
+    def _column_alphas(self, n_columns: int):
+        """Per-column (alpha, alpha_s, coef) of a panel, or None when every column runs this filter's own parameters
+        (set by sweep())."""
+        return getattr(self, "_sweep", None)
+
+    def _panel_family(self, g) -> Optional[str]:
+        """Which batched kernel propagate() uses: "hsell" = panels of 4 fp32 / 2 fp64 columns through the hub-blocked
+        form (pgb_affine_steps_panel: 16-byte shared-memory / texture gathers, the index streams read once per panel);
+        "csr" = panels of 8 / 4 columns through the item-stream kernel (pgb_affine_steps_batched); None = column by
+        column.  PGB_PANEL: 0 = never, csr = the item-stream panel, anything else = batch with the best family."""
         import os
         forced = os.environ.get("PGB_PANEL")
-        if forced not in (None, ""):
-            return forced != "0"
-        return g.in_view.hsell(self.dtype) is None
+        if forced == "0":
+            return None
+        if forced == "csr":
+            return "csr"
+        return "hsell" if g.in_view.hsell_panel() is not None else "csr"
+
+    def _can_batch(self, g, warm_start=None, graph_dropout: float = 0, n_columns: int = 2, **kwargs) -> bool:
+        # Both panel kernels stream no edge values (every BASELINE config is unweighted).
+        if g.in_view.weighted or warm_start is not None or graph_dropout != 0 or g.pathological:
+            return False
+        family = self._panel_family(g)
+        if family is None:
+            return False
+        if family == "csr" and _error_code(self.convergence.error_type) == C.ERR_MAX:
+            return False                                      # the item-stream panel kernel has no max reduction
+        import os
+        if os.environ.get("PGB_PANEL") not in (None, ""):
+            return True
+        # default: a single column is cheaper through the single-vector kernel (a panel would carry padding columns);
+        # without the hub-blocked form the item-stream panel is the only fast path
+        return n_columns >= 2 or family == "csr"
 
     def _propagate_batched(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
         """All feature columns through ``pgb_affine_steps_batched``: panels of ``pgb_panel_width``
@@ -326,7 +344,9 @@ class RecursiveGraphFilter(GraphFilter):
         st = C.stream_ptr()
         cm = self.convergence
         B = int(cols.shape[1])
-        PB = lib.pgb_panel_width(code)
+        family = self._panel_family(g)
+        PB = lib.pgb_hsell_panel_width(code) if family == "hsell" else lib.pgb_panel_width(code)
+        kwargs.pop("n_columns", None)
         a = self._affine_args(g, **kwargs)
         alpha, alpha_s, w_run, c_run, coef, coefvec = (a["alpha"], a["alpha_s"], a["w_run"], a["c_run"], a["coef"],
                                                        a["coefvec"])
@@ -336,14 +356,23 @@ class RecursiveGraphFilter(GraphFilter):
         w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
         sq_arg = None if symdeg else sq
         view = g.in_view
-        cs = view.cstruct(dtype, hsell=False)                 # the panel kernel reads the item stream
+        if family == "hsell":
+            form = view.hsell_panel()
+            yacc = torch.zeros((form.n_slices + 1) * 32 * PB, dtype=dtype, device=dev)
+            tail_queue = torch.zeros(1, dtype=torch.int32, device=dev)
+            kernels_per_step = 2
+        else:
+            cs = view.cstruct(dtype, hsell=False)             # the item-stream panel kernel
+            kernels_per_step = 1
+        col_alphas = self._column_alphas(B)                   # per column (alpha, alpha_s, coef) or None
         err_code = _error_code(cm.error_type)
         tol = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))
         perm = None if g.perm is None else g.perm.long()
         out = torch.empty((n, B), dtype=dtype, device=dev)
-        acc = torch.zeros(max(view.n_tiles, 1) * PB, dtype=f64, device=dev)
-        cnt = torch.zeros(max(view.n_tiles, 1), dtype=torch.int32, device=dev)
-        ws = (acc, cnt)
+        if family == "csr":
+            acc = torch.zeros(max(view.n_tiles, 1) * PB, dtype=f64, device=dev)
+            cnt = torch.zeros(max(view.n_tiles, 1), dtype=torch.int32, device=dev)
+            ws = (acc, cnt)
         hist = cm.max_iters + 2
         budget = cm.max_iters - 1
         iterations, errors = [], []
@@ -360,15 +389,23 @@ class RecursiveGraphFilter(GraphFilter):
             zbuf = [torch.zeros((n, PB), dtype=dtype, device=dev), torch.zeros((n, PB), dtype=dtype, device=dev)]
             q = torch.zeros((n, PB), dtype=dtype, device=dev)
             zbuf[0][:, :nb] = pn / sq[:, None]
-            qc = coefvec.to(f64)[:, None] if coefvec is not None else float(coef)
+            a_mul = np.full(PB, float(alpha))                 # multiplier of the gathered sum, per column
+            a_state = torch.full((PB,), float(alpha_s), dtype=f64, device=dev)
+            if col_alphas is not None:
+                trip = col_alphas[c0:c0 + nb]
+                a_mul[:nb] = [t[0] for t in trip]
+                a_state[:nb] = torch.tensor([t[1] for t in trip], dtype=f64, device=dev)
+                qc = torch.tensor([t[2] for t in trip], dtype=f64, device=dev)[None, :]
+            else:
+                qc = coefvec.to(f64)[:, None] if coefvec is not None else float(coef)
             q[:, :nb] = (qc * pn.to(f64)).to(dtype) / sq[:, None]
             del pn
             tacc = (zbuf[0].to(f64) * c.to(f64)[:, None]).sum(dim=0)
             bias = (q.to(f64) * sq.to(f64)[:, None]).sum(dim=0)
             sf = torch.zeros((PB, C.STATE_LEN), dtype=f64, device=dev)
-            sf[:, C.SF_ALPHA] = float(alpha_s)
+            sf[:, C.SF_ALPHA] = a_state
             sf[:, C.SF_BIAS] = bias
-            sf[:, C.SF_INVS] = 1.0 / (float(alpha_s) * tacc + bias) if self.use_quotient else 1.0
+            sf[:, C.SF_INVS] = 1.0 / (a_state * tacc + bias) if self.use_quotient else 1.0
             sf[:, C.SF_TOL] = tol
             sf[:, C.SF_MEAN] = 1.0 if err_code == C.ERR_L1 else float(n)
             sf[:nb, C.SF_NORM] = norms
@@ -380,17 +417,29 @@ class RecursiveGraphFilter(GraphFilter):
             live_host = live.cpu().numpy()
             si_host[:, C.SI_STOP] = C.CONVERGED                                 # padding / zero columns never run
             si_host[:nb, C.SI_STOP] = np.where(live_host, C.RUNNING, C.CONVERGED)
-            si = torch.from_numpy(np.concatenate([si_host.reshape(-1), np.zeros(1, np.int32)])).to(dev)
+            # two shared words after the columns: the ticket, and the panel stop word of the hsell family
+            si = torch.from_numpy(np.concatenate([si_host.reshape(-1), np.zeros(2, np.int32)])).to(dev)
+            alpha_arr = (ctypes.c_double * PB)(*a_mul.tolist())
+            uniform_alpha = bool((a_mul == a_mul[0]).all())
             err_hist = torch.zeros((PB, hist), dtype=f64, device=dev)
             C.count_launches(1)
             done, chunk = 0, max(self.chunk, 1)
             host = si_host
             while done < budget and (host[:, C.SI_STOP] == C.RUNNING).any():
                 k = min(chunk, budget - done)
-                C.check(lib.pgb_affine_steps_batched(ctypes.byref(cs), code, float(alpha), C.ptr(w), C.ptr(sq_arg),
-                                                     C.ptr(c), C.ptr(q), C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(sf),
-                                                     C.ptr(si), C.ptr(err_hist), hist, span_struct(ws), done + 1, k, st))
-                C.count_launches(k)
+                if family == "hsell":
+                    C.check(lib.pgb_affine_steps_panel(ctypes.byref(form.struct), C.ptr(view.indptr), code, alpha_arr,
+                                                       C.ptr(w), C.ptr(sq_arg), C.ptr(c), C.ptr(q), C.ptr(zbuf[0]),
+                                                       C.ptr(zbuf[1]), C.ptr(sf), C.ptr(si), C.ptr(err_hist), hist,
+                                                       C.ptr(yacc), C.ptr(tail_queue), done + 1, k, st))
+                else:
+                    if not uniform_alpha:
+                        raise Exception("per-column alpha needs the hub-blocked panel kernel (unweighted graph, PGB_HSELL=1)")
+                    C.check(lib.pgb_affine_steps_batched(ctypes.byref(cs), code, float(a_mul[0]), C.ptr(w), C.ptr(sq_arg),
+                                                         C.ptr(c), C.ptr(q), C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(sf),
+                                                         C.ptr(si), C.ptr(err_hist), hist, span_struct(ws), done + 1, k,
+                                                         st))
+                C.count_launches(k * kernels_per_step)
                 done += k
                 host = si.cpu().numpy()[:PB * C.STATE_LEN].reshape(PB, C.STATE_LEN)
                 chunk = min(chunk * 2, 64)
@@ -464,6 +513,34 @@ class PageRank(RecursiveGraphFilter):
 
     def _affine_args(self, g, **kwargs):
         return dict(alpha=self.alpha, alpha_s=self.alpha, w_run=None, c_run=None, coef=1 - self.alpha, coefvec=None)
+
+    def sweep(self, graph, personalization, alphas: Sequence[float], **kwargs) -> torch.Tensor:
+        """One solve per restart parameter in ``alphas`` for the same personalization — the candidates that
+        ParameterTuner / optimize evaluate one after the other (autotune/parameterized.py:117-167,
+        optimization.py:160-180) — as panels of the hub-blocked panel kernel: every column has its own alpha, normaliser,
+        error and stop decision, the graph is streamed once per panel iteration instead of once per candidate.
+        Returns scores [n, len(alphas)]; ``convergence.iterations`` holds each candidate's iteration count."""
+        g = self._device_graph(graph)
+        alphas = [float(a) for a in alphas]
+        p, _ = _personalization(g, personalization, self.dtype)
+        cols = p.unsqueeze(1).expand(g.n, len(alphas))        # no copy: the panels slice it
+        if self._can_batch(g, n_columns=len(alphas), **kwargs) and self._panel_family(g) == "hsell":
+            self._sweep = [(a, a, 1.0 - a) for a in alphas]
+            try:
+                return self._propagate_batched(g, cols, **kwargs)
+            finally:
+                self._sweep = None
+        out = torch.empty((g.n, len(alphas)), dtype=self.dtype, device=p.device)
+        iterations, keep = [], self.alpha
+        try:
+            for j, a in enumerate(alphas):
+                self.alpha = a
+                out[:, j] = self.rank(g, p, **kwargs).np
+                iterations.append(self.convergence.iteration)
+        finally:
+            self.alpha = keep
+        self.convergence.iterations = iterations
+        return out
 
 
 class AbsorbingWalks(RecursiveGraphFilter):

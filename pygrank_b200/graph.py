@@ -102,12 +102,22 @@ def hsell_config() -> dict:
     }
 
 
-def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional[dict] = None):
+PANEL_ELEM_BYTES = 16        # one node of a panel: 4 x fp32 or 2 x fp64 (pgb_hsell_panel_width)
+
+
+def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional[dict] = None,
+                elem_bytes: Optional[int] = None):
     """(block_cols, n_blocks) the builder will use for a gather vector of ``n_segments`` ranges of
-    ``seg_len`` entries (pure arithmetic: the row-partitioned path needs it before it relabels columns)."""
+    ``seg_len`` entries (pure arithmetic: the row-partitioned path needs it before it relabels columns).
+    ``elem_bytes``: bytes per node of the gather vector when it is not one ``dtype`` scalar (panel forms: 16)."""
     cfg = dict(hsell_config(), **(cfg or {}))
-    cap = C.lib().pgb_hsell_max_block_cols(dtype_code(dtype))
-    H = cfg["block_cols"] if cfg["block_cols"] > 0 else (128 * 1024) // (4 if dtype == torch.float32 else 8)
+    if elem_bytes is None:
+        eb = 4 if dtype == torch.float32 else 8
+        cap = C.lib().pgb_hsell_max_block_cols(dtype_code(dtype))
+    else:
+        eb = int(elem_bytes)
+        cap = ((232448 - 64) // eb - 1) & ~63            # same rule as pgb_hsell_max_block_cols
+    H = cfg["block_cols"] if cfg["block_cols"] > 0 else (128 * 1024) // eb
     H = min(H, cap)
     H -= H % (4 * n_segments)                        # equal 16-byte aligned parts per segment
     if H < 4 * n_segments:
@@ -264,8 +274,8 @@ class in_kernel_dropout:
 class HsellForm:
     """Device arrays of one pgb_hsell (kept alive here; the C struct holds raw pointers)."""
 
-    def __init__(self, view: "CsrView", dtype: torch.dtype, n_segments: int = 1, seg_len: Optional[int] = None,
-                 cfg: Optional[dict] = None):
+    def __init__(self, view: "CsrView", dtype: Optional[torch.dtype], n_segments: int = 1, seg_len: Optional[int] = None,
+                 cfg: Optional[dict] = None, elem_bytes: Optional[int] = None):
         lib = C.lib()
         cfg = dict(hsell_config(), **(cfg or {}))
         st = C.stream_ptr()
@@ -274,7 +284,8 @@ class HsellForm:
         n_cols = view.n_cols
         seg_len = int(seg_len) if seg_len is not None else n_cols
         i64 = torch.int64
-        H, K = hsell_shape(dtype, n_segments, seg_len, cfg)
+        H, K = hsell_shape(dtype, n_segments, seg_len, cfg, elem_bytes)
+        eb = int(elem_bytes) if elem_bytes is not None else (4 if dtype == torch.float32 else 8)
         S = (n + 31) // 32
         CH = C.HSELL_CHUNK
         total_cols = n_segments * seg_len
@@ -316,7 +327,7 @@ class HsellForm:
                                    C.ptr(hub_rounds), C.ptr(tail_rounds), C.ptr(hub_g0), C.ptr(hub_p0),
                                    C.ptr(tail_g0), C.ptr(tail_p0), C.ptr(self.slice_ptr), C.ptr(self.hub_words),
                                    C.ptr(self.tail_cols), C.ptr(self.piece_row), C.ptr(scratch),
-                                   32 if dtype == torch.float32 else 16, W, window_len, st))
+                                   128 // eb, W, window_len, st))      # shared-memory banks per element
         del scratch
         # slice of every piece (accumulate mode): first-level rows are slice-major, padding pieces -> row n_slices
         ps = torch.searchsorted(lay["slice_ptr"].to(i64), self.piece_row.to(i64), right=True) - 1
@@ -342,7 +353,7 @@ class HsellForm:
         self.n_reduce, self.n_pieces, self.n_rows1 = n_reduce, n_pieces, n_rows1
         self.n_hub_words, self.n_tail_words = n_hub_words, n_tail_words
         self.n_slices, self.n_segments, self.seg_len = S, n_segments, seg_len
-        self.dtype = dtype
+        self.dtype, self.elem_bytes = dtype, eb
         self.struct = C.Hsell(n, S, n_partials, seg_len, n_segments, H, K, n_ctas, n_hub_chunks, n_tail_chunks,
                               n_heavy, heavy_parts, n_reduce, 0, C.ptr(self.hub_chunks), C.ptr(self.tail_chunks),
                               C.ptr(self.hub_words), C.ptr(self.tail_cols), C.ptr(self.piece_row),
@@ -385,6 +396,15 @@ class CsrView:
         if dtype not in self._hsell:
             self._hsell[dtype] = HsellForm(self, dtype, self.hsell_segments[0], self.hsell_segments[1])
         return self._hsell[dtype]
+
+    def hsell_panel(self) -> Optional[HsellForm]:
+        """Hub-blocked form for PANELS of seed columns (16 bytes per node: 4 x fp32 or 2 x fp64, blocks of 8192 nodes);
+        one form serves both dtypes.  None for weighted / row-partitioned views or when hsell is disabled."""
+        if self.weighted or self.nnz == 0 or not hsell_config()["enabled"] or self.hsell_segments[0] != 1:
+            return None
+        if "panel" not in self._hsell:
+            self._hsell["panel"] = HsellForm(self, None, 1, None, elem_bytes=PANEL_ELEM_BYTES)
+        return self._hsell["panel"]
 
     def istream(self) -> torch.Tensor:
         """Item-space index stream (row entries + terminator -1-deg) read by the fused kernels."""

@@ -154,8 +154,11 @@ def _eval_scalar(t):
     if op == "add": return a + b
     if op == "sub": return a - b
     if op == "mul": return a * b
-    if op == "div": return a / b
-    if op == "pow": return a ** b
+    # numpy's scalar semantics, like the reference's numpy backend: x/0 is inf or nan (RMabs against an all-zero
+    # previous iterate, measures/supervised.py:114), never ZeroDivisionError
+    with np.errstate(all="ignore"):
+        if op == "div": return float(np.float64(a) / np.float64(b))
+        if op == "pow": return float(np.float64(a) ** np.float64(b))
     raise Exception("pygrank_b200.lazy: unknown scalar node " + str(op))
 
 
@@ -320,7 +323,7 @@ class LazyVec:
         if kind == "vec":
             return self._new("sub", self, v)
         if kind in ("num", "lazy"):
-            return self._new("adds", self, -v if kind == "num" else -v)
+            return self._new("adds", self, -v)
         return NotImplemented
 
     def __rsub__(self, o):
@@ -420,6 +423,9 @@ def _materialize(v: LazyVec) -> torch.Tensor:
                 continue
         pending = [a for a in node.args if isinstance(a, LazyVec) and a._val is None]
         if pending:
+            if len(pending) > 1:      # iterates of one run are read in step order (prev before cur): no recomputation
+                step = lambda a: (lambda h: h.args[1] if h is not None else -1)(_resolve_iter(a))
+                pending.sort(key=step, reverse=True)
             stack.extend(pending)
             continue
         node._val = _eager(node)
@@ -1052,9 +1058,17 @@ class PolyRun:
         if handle.op == "res":
             if t > self.done:
                 self._run_to(t)
-            if t != self.done:
-                raise Exception("pygrank_b200: an earlier result of a fused polynomial filter was read after the filter "
-                                "moved on; take backend.copy() of a value that must outlive the next step")
+            if t != self.done:                           # an earlier result read after the run moved on: recompute it
+                STATS["recomputed_runs"] += 1
+                acc, x = self.res0_node.materialize().to(self.dtype), self._seed_keep
+                for j in range(1, t + 1):
+                    if j in self.coefs:
+                        STATS["eager_ops"] += 1
+                        acc = acc + x * self.coefs[j]
+                    if j < t:
+                        STATS["eager_convs"] += 1
+                        x = self.g.conv(x)
+                return acc * scale if scale != 1.0 else acc
             C.check(lib.pgb_unscale(self.n, self.code, C.ptr(self.ranks), None, None, float(scale), C.ptr(self.g.perm),
                                     C.ptr(out), C.stream_ptr()))
             C.count_launches(1)

@@ -148,22 +148,39 @@ def main():
     P[idx, torch.arange(B, device="cuda")[None, :].expand(10, B)] = 1.0
     alg = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=torch.float32)
     alg.propagate(g, P[:, :8].contiguous())
-    dt, out = timed(lambda: alg.propagate(g, P))            # default route: columns one by one through hsell
+    dt, out = timed(lambda: alg.propagate(g, P))            # default route: panels of 4 columns on the hub-blocked form
     its = list(alg.convergence.iterations)
     calls = sum(i - 1 for i in its)
-    os.environ["PGB_PANEL"] = "1"                            # the 8-column panel kernel (pgb_affine_steps_batched)
-    alg.propagate(g, P[:, :8].contiguous())
-    dt_panel, out_panel = timed(lambda: alg.propagate(g, P))
-    panel_vs_default = rel_l1(out_panel[:, 1].cpu().numpy(), out[:, 1].cpu().numpy().astype(np.float64))
-    del out_panel
+    routes = {}
+    for route in ("0", "csr"):                              # column by column (single-vector hsell) / item-stream panels
+        os.environ["PGB_PANEL"] = route
+        alg.propagate(g, P[:, :8].contiguous())
+        dt_r, out_r = timed(lambda: alg.propagate(g, P))
+        routes[route] = (dt_r, rel_l1(out_r[:, 1].cpu().numpy(), out[:, 1].cpu().numpy().astype(np.float64)),
+                         list(alg.convergence.iterations))
+        del out_r
     os.environ.pop("PGB_PANEL")
+    # one panel, fixed step count: ms per panel iteration of the two kernels (gather + update) for 4 / 2 columns
+    panel_ms = {}
+    for dt_name, dtype_p, width in (("f32", torch.float32, 4), ("f64", torch.float64, 2)):
+        fixed = pgb.PageRank(0.85, error_type="iters", max_iters=41, dtype=dtype_p)
+        cols = P[:, :width].to(dtype_p).contiguous()
+        fixed.propagate(g, cols)
+        dtp, _ = timed(lambda: fixed.propagate(g, cols))
+        panel_ms[dt_name] = {"columns": width, "steps": 40, "ms_per_panel_step": dtp / 40 * 1e3,
+                             "edge_column_gteps": g.nnz * 40 * width / dtp / 1e9}
     one = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=torch.float32)
     one(g, P[:, 0].contiguous())
     dt1, r1 = timed(lambda: one(g, P[:, 0].contiguous()).np)
     c3 = {"graph": f"RMAT scale {scale} (n {n}, nnz {g.nnz})", "seed_sets": B, "propagate_s": dt,
-          "panel_kernel_s": dt_panel, "panel_edge_column_gteps": g.nnz * calls / dt_panel / 1e9,
-          "col1_rel_l1_panel_vs_default": panel_vs_default,
-          "column_iterations_min_max": [min(its), max(its)], "edge_column_gteps": g.nnz * calls / dt / 1e9,
+          "edge_column_gteps": g.nnz * calls / dt / 1e9, "route": "hsell panels (pgb_affine_steps_panel)",
+          "column_by_column_s": routes["0"][0], "column_by_column_edge_column_gteps": g.nnz * calls / routes["0"][0] / 1e9,
+          "csr_panel_s": routes["csr"][0], "csr_panel_edge_column_gteps": g.nnz * calls / routes["csr"][0] / 1e9,
+          "col1_rel_l1_vs_column_by_column": routes["0"][1], "col1_rel_l1_vs_csr_panel": routes["csr"][1],
+          "iterations_off_by_more_than_one_vs_column_by_column":
+              int(sum(abs(a - b) > 1 for a, b in zip(its, routes["0"][2]))),
+          "panel_step": panel_ms,
+          "column_iterations_min_max": [min(its), max(its)],
           "single_column_s": dt1, "single_column_gteps": g.nnz * (one.convergence.iteration - 1) / dt1 / 1e9,
           "col0_rel_l1_propagate_vs_single": rel_l1(out[:, 0].cpu().numpy(), r1.cpu().numpy().astype(np.float64))}
     del P, out
@@ -197,10 +214,22 @@ def main():
     algs[0](g, [int(v) for v in seeds])
     dt, _ = timed(lambda: [a(g, [int(v) for v in seeds]) for a in algs])
     calls = sum(a.convergence.iteration - 1 for a in algs)
+    sw = pgb.PageRank(0.85, tol=1e-9, max_iters=2000, dtype=torch.float32)
+    pvec = torch.zeros(n, dtype=torch.float32, device="cuda")
+    pvec[torch.as_tensor(np.asarray(seeds, dtype=np.int64), device="cuda")] = 1.0
+    sw.sweep(g, pvec, [float(a) for a in alphas[:4]])
+    dts, swept = timed(lambda: sw.sweep(g, pvec, [float(a) for a in alphas]))
+    sweep_its = list(sw.convergence.iterations)
+    last = algs[-1](g, [int(v) for v in seeds]).np
     ab = pgb.AbsorbingWalks(0.85, tol=1e-9, max_iters=2000, dtype=torch.float32)
     dta, _ = timed(lambda: ab(g, [int(v) for v in seeds]))
     report["C5"] = {"graph": f"BA-like n={n} m={m} (nnz {g.nnz})", "build_s": build, "sweep_32_alphas_s": dt,
                     "sweep_conv_calls": calls, "sweep_gteps": g.nnz * calls / dt / 1e9,
+                    "panel_sweep_32_alphas_s": dts, "panel_sweep_gteps": g.nnz * sum(i - 1 for i in sweep_its) / dts / 1e9,
+                    "panel_sweep_iterations_off_by_more_than_one":
+                        int(sum(abs(a.convergence.iteration - b) > 1 for a, b in zip(algs, sweep_its))),
+                    "panel_sweep_last_alpha_rel_l1_vs_single": rel_l1(swept[:, -1].cpu().numpy(),
+                                                                      last.cpu().numpy().astype(np.float64)),
                     "absorbing_iterations": ab.convergence.iteration, "absorbing_s": dta,
                     "absorbing_gteps": g.nnz * (ab.convergence.iteration - 1) / dta / 1e9}
     print("C5", report["C5"], flush=True)

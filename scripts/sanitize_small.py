@@ -44,9 +44,14 @@ x = B.to_array(p)
 num = B.conv(x, g) * 0.85 + x * 0.15
 nxt = num / B.sum(num)
 print("lazy", float(B.sum(B.abs(x - nxt)) / n), float(B.sum(nxt)))
-os.environ["PGB_PANEL"] = "1"
-out = pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=torch.float32).propagate(g, torch.stack([p, p * 2, p * 0], 1).float())
-print("panel", tuple(out.shape), float(out.sum()))
+for family in ("1", "csr"):          # hub-blocked panels (pgb_affine_steps_panel), item-stream panels
+    os.environ["PGB_PANEL"] = family
+    for dtype in (torch.float32, torch.float64):
+        feats = torch.stack([p, p * 2, p * 0, p + 1, p * 3], 1).to(dtype)
+        out = pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=dtype).propagate(g, feats)
+        print("panel", family, dtype, tuple(out.shape), float(out.sum()))
+del os.environ["PGB_PANEL"]
+print("sweep", float(pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=torch.float32).sweep(g, p.float(), [0.5, 0.7, 0.9]).sum()))
 C.check(C.lib().pgb_set_kernel_variant(3))
 a = pgb.PageRank(0.85, tol=1e-9, max_iters=200)
 print("item stream", a(g, p).np.sum().item(), a.convergence.iteration)

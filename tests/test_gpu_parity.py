@@ -251,16 +251,23 @@ def test_custom_absorption_and_propagate(pgb, torch_cuda, name):
 @pytest.mark.parametrize("run", ["ppr85", "ppr90_noq", "ppr85_col", "ppr85_l1", "ppr85_msq", "ppr85_tol6_mod3",
                                  "absorb85", "absorb85_col"])
 @pytest.mark.parametrize("relabel", ["hub", "degree", "none"])
-def test_batched_propagate_matches_golden(pgb, torch_cuda, monkeypatch, name, run, relabel):
-    """propagate() through the panel kernel (pgb_affine_steps_batched): every column must stop at the
-    reference's own iteration count and match its scores (signals.py:225-226 runs them one by one)."""
+@pytest.mark.parametrize("family", ["hsell", "csr"])
+def test_batched_propagate_matches_golden(pgb, torch_cuda, monkeypatch, name, run, relabel, family):
+    """propagate() through the panel kernels (hsell: pgb_affine_steps_panel on the hub-blocked form; csr:
+    pgb_affine_steps_batched on the item stream): every column must stop at the reference's own iteration count and
+    match its scores (signals.py:225-226 runs them one by one)."""
     torch = torch_cuda
-    monkeypatch.setenv("PGB_PANEL", "1")
+    monkeypatch.setenv("PGB_PANEL", "1" if family == "hsell" else "csr")
+    if family == "hsell":
+        monkeypatch.setenv("PGB_HSELL_BLOCK_COLS", "64")      # golden graphs are small: several hub blocks and a tail
+        monkeypatch.setenv("PGB_HSELL_BLOCKS", "5")
+        monkeypatch.setenv("PGB_HSELL_MIN_ENTRIES", "4")
     z, A, directed = load_golden(name)
     norm, make, _ = _runs(pgb)[run]
     g = _graph(pgb, A, directed, norm, relabel)
     P = z["P"]
     alg = make({"dtype": torch.float64})
+    assert alg._panel_family(g) == ("csr" if g.in_view.weighted else family)   # weighted graphs: item-stream panels
     out = alg.propagate(g, P).cpu().numpy()
     assert list(alg.convergence.iterations) == [int(v) for v in z[f"run_{run}_iters"]], (name, run)
     for c in range(P.shape[1]):
@@ -275,11 +282,14 @@ def test_batched_propagate_matches_golden(pgb, torch_cuda, monkeypatch, name, ru
 
 
 @pytest.mark.parametrize("dtype_name,tol", [("float64", 1e-12), ("float32", 2e-6)])
-def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, monkeypatch, dtype_name, tol):
-    """11 columns (one full panel + a ragged one), one all-zero column, columns that converge at
+@pytest.mark.parametrize("family", ["hsell", "hsell_small_blocks", "csr"])
+def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, monkeypatch, dtype_name, tol, family):
+    """11 columns (full panels + a ragged one), one all-zero column, columns that converge at
     different iterations; the batched result must equal the single-column fused path."""
     torch = torch_cuda
-    monkeypatch.setenv("PGB_PANEL", "1")
+    monkeypatch.setenv("PGB_PANEL", "csr" if family == "csr" else "1")
+    if family == "hsell_small_blocks":                           # 80 hub blocks of 256 nodes + a long tail
+        monkeypatch.setenv("PGB_HSELL_BLOCK_COLS", "256")
     from pygrank_b200 import synthetic, device_synthetic
     dtype = getattr(torch, dtype_name)
     scale = 17
@@ -308,6 +318,57 @@ def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, monkeypatch, dt
         assert rel_l1(out[:, c].cpu().numpy(), ref.cpu().numpy()) <= tol, c
     with pytest.raises(Exception, match="Could not converge within 4 iterations"):
         pgb.PageRank(0.99, tol=1e-14, max_iters=4, dtype=dtype).propagate(g, torch.from_numpy(P).cuda())
+
+
+@pytest.mark.parametrize("dtype_name,tol", [("float64", 1e-12), ("float32", 2e-6)])
+def test_alpha_sweep_as_panels_matches_single_solves(pgb, torch_cuda, dtype_name, tol):
+    """PageRank.sweep: the candidates of a parameter search (autotune/optimization.py:160-180 evaluates them one by
+    one) as columns of the hub-blocked panel kernel, every column with its own alpha, normaliser and stop decision."""
+    torch = torch_cuda
+    from pygrank_b200 import device_synthetic
+    dtype = getattr(torch, dtype_name)
+    scale = 16
+    n = 1 << scale
+    g = device_synthetic.rmat_graph_device(scale, 16, seed=9)
+    rng = np.random.default_rng(2)
+    p = np.zeros(n)
+    p[rng.choice(n, 50, replace=False)] = 1.0
+    alphas = [0.5, 0.6, 0.7, 0.8, 0.85, 0.9, 0.95]             # ragged: 7 columns
+    for quotient in (True, False):
+        alg = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=dtype, use_quotient=quotient)
+        out = alg.sweep(g, p, alphas)
+        its = list(alg.convergence.iterations)
+        assert out.shape == (n, len(alphas)) and its == sorted(its) and its[0] < its[-1]
+        for j, a in enumerate(alphas):
+            one = pgb.PageRank(a, tol=1e-9, max_iters=1000, dtype=dtype, use_quotient=quotient)
+            ref = one(g, p).np
+            assert abs(one.convergence.iteration - its[j]) <= (0 if dtype == torch.float64 else 1), (a, its)
+            assert rel_l1(out[:, j].cpu().numpy(), ref.cpu().numpy()) <= tol, a
+
+
+def test_panel_max_difference_matches_single_solves(pgb, torch_cuda, monkeypatch):
+    """error_type=MaxDifference through the hub-blocked panel kernel (a max reduction per column)."""
+    torch = torch_cuda
+    from pygrank_b200 import device_synthetic
+    monkeypatch.setenv("PGB_PANEL", "1")
+
+    class MaxDifference:
+        pass
+
+    n = 1 << 15
+    g = device_synthetic.rmat_graph_device(15, 16, seed=3)
+    rng = np.random.default_rng(1)
+    P = np.zeros((n, 5))
+    for c in range(5):
+        P[rng.choice(n, 10 ** (c % 3 + 1), replace=False), c] = 1.0
+    alg = pgb.PageRank(0.85, tol=1e-8, max_iters=1000, error_type=MaxDifference)
+    assert alg._panel_family(g) == "hsell"
+    out = alg.propagate(g, torch.from_numpy(P).cuda())
+    for c in range(5):
+        one = pgb.PageRank(0.85, tol=1e-8, max_iters=1000, error_type=MaxDifference)
+        ref = one(g, P[:, c]).np
+        assert one.convergence.iteration == alg.convergence.iterations[c]
+        assert rel_l1(out[:, c].cpu().numpy(), ref.cpu().numpy()) <= 1e-12
 
 
 @pytest.mark.parametrize("name", GOLDEN_GRAPHS)

@@ -157,3 +157,13 @@ def test_loop_invariant_cache_notices_in_place_writes(setup):
     p[3] = 100.0
     second = lazy._pure_value(expr(), lazy._pure_key(expr()))
     assert float(second[3]) == pytest.approx(15.0) and float(first[3]) != float(second[3])
+
+
+def test_scalar_division_by_zero_follows_numpy(setup):
+    """RMabs divides by sum|previous| (measures/supervised.py:114), zero on the first test of a closed-form filter: the
+    numpy backend gets inf and goes on; so must the deferred scalars."""
+    g, M, p, x = setup
+    zero = lazy.LazyScalar(("sum", p * 0.0))
+    one = lazy.LazyScalar(("sum", p * 0.0 + 1.0))
+    assert float(one / zero) == float("inf") and not ((one / zero) <= 1e-6)
+    assert np.isnan(float(zero / zero)) and not ((zero / zero) <= 1e-6)

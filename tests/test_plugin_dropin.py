@@ -201,6 +201,11 @@ def test_plugin_route_eager_fallbacks_stay_correct(pg):
         "gen3": lambda pre: pg.GenericGraphFilter([0.5, 0.25, 0.125], tol=1e-9, preprocessor=pre),
         "closed": lambda pre: pg.PageRankClosed(0.85, tol=1e-9, max_iters=1000, preprocessor=pre),
         "absorb_custom": lambda pre: pg.AbsorbingWalks(0.85, tol=1e-9, max_iters=1000, preprocessor=pre),
+        # measures a polynomial run does not keep on the device: consecutive results are read back and compared eagerly
+        "heat_rmabs": lambda pre: pg.HeatKernel(3, tol=1e-7, error_type=pg.RMabs, preprocessor=pre),
+        "heat_maxdiff": lambda pre: pg.HeatKernel(3, tol=1e-9, error_type=pg.MaxDifference, preprocessor=pre),
+        "heat_msq": lambda pre: pg.HeatKernel(3, tol=1e-16, error_type=pg.MSQ, preprocessor=pre),
+        "heat_modulo": lambda pre: pg.HeatKernel(3, tol=1e-9, end_modulo=2, preprocessor=pre),
     }
     results = {}
     for backend in ["numpy", "b200"]:
