@@ -153,6 +153,7 @@ enum { /* indices into state_f64[PGB_STATE_F64_LEN] */
     PGB_SF_LASTERR = 7,
     PGB_SF_NORM = 8,  /* sum|personalization| (abstract_filters.py:52)                   */
     PGB_SF_PSUM = 9,  /* sum(personalization)                                            */
+    PGB_SF_AMUL = 10, /* panel path: this column's multiplier of the gathered sum        */
     PGB_STATE_F64_LEN = 16
 };
 enum { /* indices into state_i32[PGB_STATE_I32_LEN] */
@@ -324,24 +325,54 @@ int pgb_affine_steps_batched(const pgb_csr *g, int dtype, double alpha, const vo
                              int32_t *state_i32, double *err_hist, int32_t hist_stride, pgb_span_ws ws,
                              int first_step, int num_launches, void *stream);
 
-/* K3 on the hub-blocked form — the fast path of NodeRanking.propagate (core/signals.py:225-226) and of alpha sweeps
- * (algorithms/autotune/optimization.py:160-180 evaluates one candidate after the other): PB =
- * pgb_hsell_panel_width(dtype) columns (4 x fp32 / 2 x fp64 = 16 bytes per node) advance together through a pgb_hsell
- * built with block_cols = pgb_hsell_panel_block_cols() (8192 nodes = 128 KB of [node][PB] per hub block; the builders
- * do not depend on the element type).  The gather kernel is the single-vector one instantiated on 16-byte elements:
- * one 16-bit hub index feeds one LDS.128, one tail index one 16-byte texel, a piece leaves as one 16-byte RED per
- * lane into yacc [(n_slices + 1) * 32][PB] (zero at the first launch; the update pass re-zeroes it).  Vectors z, q are
- * [n][PB] row-major, w / sq / c per row as in pgb_affine_steps (w = sq = NULL: derived from `indptr`).  alpha is a HOST
- * array of PB per-column multipliers.  state_f64 [PB][PGB_STATE_F64_LEN]; state_i32 [PB][PGB_STATE_I32_LEN] followed
- * by TWO shared words (ticket, panel stop word: set once every column has stopped, later launches are no-ops);
- * err_hist [PB][hist_stride].  Columns stop one by one exactly as in pgb_affine_steps_batched.  tail_queue: one zeroed
- * uint32 (pgb_span_ws.cnt).  Single-GPU forms only (n_segments == 1), accumulate mode, no in-kernel dropout. */
+/* K3 on the hub-blocked form — the fast path of NodeRanking.propagate (core/signals.py:225-226: one solve per feature
+ * column) and of alpha sweeps (algorithms/autotune/optimization.py:160-180 evaluates one candidate after the other).
+ * PB = pgb_hsell_panel_width(dtype) columns (4 x fp32 / 2 x fp64 = 16 bytes per node) advance together through a
+ * pgb_hsell built with block_cols = pgb_hsell_panel_block_cols() (8192 nodes = 128 KB of [node][PB] per hub block; the
+ * builders do not depend on the element type).  The gather kernel is the single-vector one instantiated on 16-byte
+ * elements: one 16-bit hub index feeds one LDS.128, one tail index one 16-byte texel, a piece leaves as one 16-byte RED
+ * per lane into yacc [(n_slices + 1) * 32][PB] (zero at the first launch; the update pass re-zeroes it).  Every column
+ * has its own multiplier (PGB_SF_AMUL), normaliser, error sum and stop decision.
+ *
+ * The PB columns are SLOTS of a job of n_cols seed columns, scheduled on the device: before every step a column that
+ * has stopped is written to `out` (scaled back by its norm when preserve_norm) with its iteration count, stop reason,
+ * step count and error history, and the next pending column is loaded into the free slot — the start of
+ * GraphFilter.rank, abstract_filters.py:52-56: norm = sum|col| ; pn = col/norm ; z = pn/sq ; q = coef*pn/sq ; state —
+ * while the other slots keep iterating.  The host enqueues steps in chunks and polls sched[1] (columns finished);
+ * launches after the last column has left are no-ops.  A column with a zero norm leaves with iteration 0 (:53-54). */
+typedef struct {
+    int32_t n_cols;           /* seed columns of the job                                                         */
+    int32_t hist_stride;      /* doubles per row of err_hist / col_err (>= max_iters + 2)                        */
+    const void *cols;         /* features, user order: element (i, j) at cols[i*row_stride + j*col_stride]       */
+    int64_t row_stride, col_stride;
+    void *out;                /* results: element (i, j) at out[i*out_row_stride + j*out_col_stride]             */
+    int64_t out_row_stride, out_col_stride;
+    const int32_t *perm;      /* internal row i is user node perm[i] (or NULL)                                   */
+    const void *sq;           /* per internal row (required)                                                     */
+    const void *coefvec;      /* per-row coefficient of the personalization (AbsorbingWalks) or NULL -> coef     */
+    const double *col_params; /* [n_cols][3] = (multiplier, alpha_s, coef) per column, or NULL -> the three below */
+    double alpha, alpha_s, coef;
+    double tol, mean;         /* PGB_SF_TOL, PGB_SF_MEAN of every column                                         */
+    int32_t max_iters, end_modulo, err_mode, quotient, preserve_norm;
+    int32_t *sched;           /* [4], zero at the start: next column to load, columns finished, spare, spare     */
+    int32_t *slot_col;        /* [PB], -1 at the start: column held by every slot                                */
+    int32_t *slot_plan;       /* [2*PB] scratch                                                                  */
+    double *plan_norm;        /* [PB] scratch                                                                    */
+    int32_t *col_result;      /* [n_cols][4]: iteration, stop reason, steps, norm > 0                            */
+    double *col_err;          /* [n_cols][hist_stride] error histories (entries 1..steps) or NULL                */
+} pgb_panel_job;
+
+/* Enqueues `num_launches` steps (step k reads buf[(k-1)&1], writes buf[k&1], k = first_step..).  z, q are [n][PB]
+ * row-major (zero at the start), w / c per row as in pgb_affine_steps (w = NULL: w and sq derived from `indptr`).
+ * state_f64 [PB][PGB_STATE_F64_LEN]; state_i32 [PB][PGB_STATE_I32_LEN] with STOP != RUNNING at the start, followed by
+ * FOUR shared words (ticket; panel stop word, != RUNNING at the start; steps executed; spare); err_hist
+ * [PB][hist_stride].  tail_queue: one zeroed uint32.  Single-GPU forms only, accumulate mode, no in-kernel dropout. */
 int pgb_hsell_panel_width(int dtype);
 int pgb_hsell_panel_block_cols(void);
-int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype, const double *alpha, const void *w,
-                           const void *sq, const void *c, const void *q, void *zbuf0, void *zbuf1, double *state_f64,
-                           int32_t *state_i32, double *err_hist, int32_t hist_stride, void *yacc, uint32_t *tail_queue,
-                           int first_step, int num_launches, void *stream);
+int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype, const pgb_panel_job *job, const void *w,
+                           const void *c, void *q, void *zbuf0, void *zbuf1, double *state_f64, int32_t *state_i32,
+                           double *err_hist, void *yacc, uint32_t *tail_queue, int first_step, int num_launches,
+                           void *stream);
 
 /* ---- row-partitioned multi-GPU: the exchange fused into the step (no reference counterpart) ----------
  * Every rank keeps the full gather vector (both buffers) and a slot array for the convergence sums in
@@ -404,6 +435,15 @@ int pgb_affine_init(int64_t n, int dtype, const void *p, const void *warm, const
                     double *state_f64, void *stream);
 /* invS for the first step from the accumulated T / BIAS (one thread). */
 int pgb_affine_init_finish(double *state_f64, int32_t *state_i32, void *stream);
+
+/* Staging of a panel job.  A slot loads / stores one column at a time; from a row-major [n][B] matrix in user order
+ * that is one 32-byte sector per value at random rows, so jobs run on column-major blocks in the engine's row order:
+ * direction 0: stage[j][i] = matrix[perm[i]*row_stride + (j0+j)*col_stride]   (j < n_cols; perm NULL = identity)
+ * direction 1: matrix[perm[i]*row_stride + (j0+j)] = stage[j][i]              (col_stride must be 1)
+ * (tiled transposes: both sides move in full lines).  The job then uses cols = stage, row_stride 1, col_stride n,
+ * perm NULL, and out = a second stage with out_row_stride 1, out_col_stride n. */
+int pgb_panel_stage(int64_t n, int dtype, int direction, void *matrix, int64_t row_stride, int64_t col_stride,
+                    const int32_t *perm, int64_t j0, int32_t n_cols, void *stage, void *stream);
 
 #ifdef __cplusplus
 }

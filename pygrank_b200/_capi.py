@@ -20,7 +20,7 @@ SCALE_ONE, SCALE_RECIP, SCALE_RSQRT = 0, 1, 2
 ERR_MABS, ERR_L1, ERR_MSQ, ERR_ITERS, ERR_MAX = 0, 1, 2, 3, 4
 RUNNING, CONVERGED, MAX_ITERS = 0, 1, 2
 # state_f64 / state_i32 slots
-SF_ALPHA, SF_BIAS, SF_INVS, SF_TACC, SF_EACC, SF_TOL, SF_MEAN, SF_LASTERR, SF_NORM, SF_PSUM = range(10)
+SF_ALPHA, SF_BIAS, SF_INVS, SF_TACC, SF_EACC, SF_TOL, SF_MEAN, SF_LASTERR, SF_NORM, SF_PSUM, SF_AMUL = range(11)
 SI_TICKET, SI_STEPS, SI_STOP, SI_ITERATION, SI_MAX_ITERS, SI_END_MODULO, SI_ERR_MODE, SI_QUOTIENT = range(8)
 STATE_LEN = 16
 ABI_VERSION = 3
@@ -33,6 +33,18 @@ class Csr(Structure):
     _fields_ = [("n", c_int64), ("nnz", c_int64), ("indptr", c_void_p), ("indices", c_void_p), ("values", c_void_p),
                 ("tile_row", c_void_p), ("n_tiles", c_int32), ("tile_items", c_int32), ("istream", c_void_p),
                 ("vstream", c_void_p), ("hsell", c_void_p)]
+
+
+class PanelJob(Structure):
+    """pgb_panel_job (include/pgb200.h): seed columns scheduled over the slots of a hub-blocked panel."""
+    _fields_ = [("n_cols", c_int32), ("hist_stride", c_int32), ("cols", c_void_p), ("row_stride", c_int64),
+                ("col_stride", c_int64), ("out", c_void_p), ("out_row_stride", c_int64), ("out_col_stride", c_int64),
+                ("perm", c_void_p),
+                ("sq", c_void_p), ("coefvec", c_void_p), ("col_params", c_void_p), ("alpha", c_double),
+                ("alpha_s", c_double), ("coef", c_double), ("tol", c_double), ("mean", c_double),
+                ("max_iters", c_int32), ("end_modulo", c_int32), ("err_mode", c_int32), ("quotient", c_int32),
+                ("preserve_norm", c_int32), ("sched", c_void_p), ("slot_col", c_void_p), ("slot_plan", c_void_p),
+                ("plan_norm", c_void_p), ("col_result", c_void_p), ("col_err", c_void_p)]
 
 
 class Hsell(Structure):
@@ -109,9 +121,11 @@ _SIGNATURES = {
                                          c_int, c_int, c_void_p]),
     "pgb_hsell_panel_width": (c_int, [c_int]),
     "pgb_hsell_panel_block_cols": (c_int, []),
-    "pgb_affine_steps_panel": (c_int, [POINTER(Hsell), c_void_p, c_int, POINTER(c_double), c_void_p, c_void_p, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
-                                       c_void_p, c_int, c_int, c_void_p]),
+    "pgb_affine_steps_panel": (c_int, [POINTER(Hsell), c_void_p, c_int, POINTER(PanelJob), c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                       c_int, c_void_p]),
+    "pgb_panel_stage": (c_int, [c_int64, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32, c_void_p,
+                                c_void_p]),
     "pgb_state_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgb_affine_step_peer": (c_int, [POINTER(Csr), c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, SpanWs, c_int, POINTER(Peers),

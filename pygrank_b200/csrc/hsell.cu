@@ -869,9 +869,8 @@ struct PanelStep {
     void *zout;              // [n][PB]
     const void *w, *sq, *c;  // per row
     void *y;                 // [(n_slices + 1) * 32][PB]
-    double alpha[4];         // per column
     double *sf;              // [PB][PGB_STATE_F64_LEN]
-    int32_t *si;             // [PB][PGB_STATE_I32_LEN], then the shared ticket and the panel stop word
+    int32_t *si;             // [PB][PGB_STATE_I32_LEN], then the shared ticket, the panel stop word, the step counter
     double *err_hist;        // [PB][hist_stride]
     int32_t hist_stride;
     uint32_t *tail_queue;
@@ -907,15 +906,16 @@ __global__ void __launch_bounds__(UPP_BLOCK) hsell_update_panel_kernel(const Pan
     bool active[PB];
     S invS[PB], alpha[PB];
     bool any = false;
+    int err_mode = PGB_ERR_MABS;   // one measure per panel: taken from a running column (empty slots hold no settings)
 #pragma unroll
     for (int c = 0; c < PB; ++c) {
         active[c] = P.si[c * PGB_STATE_I32_LEN + PGB_SI_STOP] == PGB_RUNNING;
         invS[c] = (S)P.sf[c * PGB_STATE_F64_LEN + PGB_SF_INVS];
-        alpha[c] = (S)P.alpha[c];
+        alpha[c] = (S)P.sf[c * PGB_STATE_F64_LEN + PGB_SF_AMUL];
+        if (active[c]) err_mode = P.si[c * PGB_STATE_I32_LEN + PGB_SI_ERR_MODE];
         any = any || active[c];
     }
     if (!any) return;   // run-ahead launch after every column has stopped
-    const int err_mode = P.si[PGB_SI_ERR_MODE];
     const bool is_max = err_mode == PGB_ERR_MAX;
     double err[PB], tsum[PB];
 #pragma unroll
@@ -1038,6 +1038,7 @@ __global__ void __launch_bounds__(UPP_BLOCK) hsell_update_panel_kernel(const Pan
             bool running = false;
             for (int c = 0; c < PB; ++c) running = running || vsi[c * PGB_STATE_I32_LEN + PGB_SI_STOP] == PGB_RUNNING;
             vsi[PB * PGB_STATE_I32_LEN + 1] = running ? PGB_RUNNING : PGB_CONVERGED;   // the gather's stop word
+            vsi[PB * PGB_STATE_I32_LEN + 2] = vsi[PB * PGB_STATE_I32_LEN + 2] + 1;     // steps the panel has executed
             vsi[PB * PGB_STATE_I32_LEN] = 0;
             __threadfence();
         }
@@ -1141,6 +1142,15 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool
     G.stop = stop;
     G.tail_queue = tail_queue;
     G.tail_warps = g_tail_warps;
+    if (sizeof(T) == 16) {   // panel elements: 8 tail warps measured best (5 -> 1.394, 8 -> 1.338, 12 -> 1.37 ms, RMAT-24 fp32x4)
+        static int panel_tail_warps = -1;
+        if (panel_tail_warps < 0) {
+            const char *e = getenv("PGB_HSELL_PANEL_TAIL_WARPS");
+            panel_tail_warps = e ? atoi(e) : 8;
+            if (panel_tail_warps < 0 || panel_tail_warps > HS_WARPS) panel_tail_warps = 8;
+        }
+        G.tail_warps = panel_tail_warps;
+    }
     static int debug_skip = -1;
     if (debug_skip < 0) {
         const char *e = getenv("PGB_HSELL_DEBUG_SKIP");
@@ -1181,9 +1191,200 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Slot scheduling of a panel job, on the device.  propagate() of B seed columns keeps the PB slots of the panel busy:
+// before every step four small launches look at the slots — a column that stopped is written out (its iteration
+// count, stop reason and error history recorded) and the next pending column is loaded into the free slot
+// (normalisation, scaled start vector, affine term, state: abstract_filters.py:52-56), while the other columns
+// keep iterating.  No host round trip: the host enqueues steps in chunks and only polls the count of finished
+// columns.  All four launches return at once when no slot changes hands.
+// ---------------------------------------------------------------------------------------------
+template <typename S, int PB>
+__global__ void panel_plan_kernel(const pgb_panel_job J, double *sf, int32_t *si, const double *err_hist) {
+    const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (s >= PB) return;
+    double *sfs = sf + s * PGB_STATE_F64_LEN;
+    int32_t *sis = si + s * PGB_STATE_I32_LEN;
+    int col = J.slot_col[s];
+    int harvest = -1, load = -1;
+    if (col >= 0 && sis[PGB_SI_STOP] != PGB_RUNNING) {
+        harvest = col;
+        const int steps = sis[PGB_SI_STEPS];
+        if (J.col_err)
+            for (int k = 1 + lane; k <= steps && k < J.hist_stride; k += 32)
+                J.col_err[(int64_t)col * J.hist_stride + k] = err_hist[(int64_t)s * J.hist_stride + k];
+        if (lane == 0) {
+            int32_t *r = J.col_result + 4 * (int64_t)col;
+            r[0] = sis[PGB_SI_ITERATION];
+            r[1] = sis[PGB_SI_STOP];
+            r[2] = steps;
+            r[3] = sfs[PGB_SF_NORM] > 0.0 ? 1 : 0;
+            J.plan_norm[s] = sfs[PGB_SF_NORM];
+            J.slot_col[s] = -1;
+            atomicAdd(&J.sched[1], 1);
+        }
+        col = -1;
+    }
+    __syncwarp();
+    if (col < 0) {
+        if (lane == 0) {
+            const int j = J.sched[0] < J.n_cols ? atomicAdd(&J.sched[0], 1) : J.n_cols;
+            if (j < J.n_cols) load = j;
+        }
+        load = __shfl_sync(0xffffffffu, load, 0);
+        if (load >= 0) {   // fresh state rows for the new column
+            if (lane < PGB_STATE_F64_LEN) sfs[lane] = 0.0;
+            if (lane < PGB_STATE_I32_LEN) sis[lane] = (lane == PGB_SI_STOP) ? PGB_CONVERGED : 0;
+        }
+    }
+    if (lane == 0) {
+        J.slot_plan[2 * s] = harvest;
+        J.slot_plan[2 * s + 1] = load;
+    }
+}
+
+template <typename S, int PB>
+__global__ void __launch_bounds__(256) panel_move_kernel(const pgb_panel_job J, int64_t n, const S *__restrict__ cur,
+                                                         const S *__restrict__ sq, double *sf) {
+    __shared__ double scratch[32];
+    int harvest[PB], load[PB];
+    bool any = false;
+#pragma unroll
+    for (int s = 0; s < PB; ++s) {
+        harvest[s] = J.slot_plan[2 * s];
+        load[s] = J.slot_plan[2 * s + 1];
+        any = any || harvest[s] >= 0 || load[s] >= 0;
+    }
+    if (!any) return;
+    const S *__restrict__ cols = (const S *)J.cols;
+    S *__restrict__ out = (S *)J.out;
+    double scale[PB], norm[PB];
+#pragma unroll
+    for (int s = 0; s < PB; ++s) {
+        scale[s] = (harvest[s] >= 0 && J.preserve_norm && J.plan_norm[s] > 0.0) ? J.plan_norm[s] : 1.0;
+        norm[s] = 0.0;
+    }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t user = J.perm ? (int64_t)J.perm[i] : i;
+        bool out_any = false;
+#pragma unroll
+        for (int s = 0; s < PB; ++s) out_any = out_any || harvest[s] >= 0;
+        if (out_any) {
+            const Pack<S, PB> z = ld_pack(cur + i * PB);
+            const S sqi = sq[i];
+#pragma unroll
+            for (int s = 0; s < PB; ++s)
+                if (harvest[s] >= 0) {
+                    S v = z.v[s] * sqi;
+                    if (scale[s] != 1.0) v = (S)(v * (S)scale[s]);
+                    out[user * J.out_row_stride + harvest[s] * J.out_col_stride] = v;
+                }
+        }
+#pragma unroll
+        for (int s = 0; s < PB; ++s)
+            if (load[s] >= 0) norm[s] += fabs((double)cols[user * J.row_stride + load[s] * J.col_stride]);
+    }
+#pragma unroll
+    for (int s = 0; s < PB; ++s)
+        if (load[s] >= 0) {   // uniform across the grid
+            const double t = block_sum(norm[s], scratch);
+            if (threadIdx.x == 0) atomicAdd(&sf[s * PGB_STATE_F64_LEN + PGB_SF_NORM], t);
+        }
+}
+
+template <typename S, int PB>
+__global__ void __launch_bounds__(256) panel_load_kernel(const pgb_panel_job J, int64_t n, S *__restrict__ cur,
+                                                         S *__restrict__ q, const S *__restrict__ sq,
+                                                         const S *__restrict__ c, double *sf) {
+    __shared__ double scratch[32];
+    int load[PB];
+    bool any = false;
+#pragma unroll
+    for (int s = 0; s < PB; ++s) {
+        load[s] = J.slot_plan[2 * s + 1];
+        any = any || load[s] >= 0;
+    }
+    if (!any) return;
+    const S *__restrict__ cols = (const S *)J.cols;
+    const S *__restrict__ coefvec = (const S *)J.coefvec;
+    double norm[PB], coef[PB], tacc[PB], bacc[PB];
+#pragma unroll
+    for (int s = 0; s < PB; ++s) {
+        norm[s] = load[s] >= 0 ? sf[s * PGB_STATE_F64_LEN + PGB_SF_NORM] : 0.0;
+        coef[s] = (load[s] >= 0 && J.col_params) ? J.col_params[3 * (int64_t)load[s] + 2] : J.coef;
+        tacc[s] = bacc[s] = 0.0;
+    }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t user = J.perm ? (int64_t)J.perm[i] : i;
+        const S sqi = sq[i], ci = c[i];
+        const double cv = coefvec ? (double)coefvec[i] : 0.0;
+#pragma unroll
+        for (int s = 0; s < PB; ++s)
+            if (load[s] >= 0) {
+                S zi = (S)0, qi = (S)0;
+                if (norm[s] > 0.0) {                                     // abstract_filters.py:53-55
+                    const S pn = (S)((double)cols[user * J.row_stride + load[s] * J.col_stride] / norm[s]);
+                    zi = pn / sqi;
+                    qi = (S)((coefvec ? cv : coef[s]) * (double)pn) / sqi;
+                    tacc[s] += (double)zi * (double)ci;
+                    bacc[s] += (double)qi * (double)sqi;
+                }
+                cur[i * PB + s] = zi;
+                q[i * PB + s] = qi;
+            }
+    }
+#pragma unroll
+    for (int s = 0; s < PB; ++s)
+        if (load[s] >= 0) {
+            const double t = block_sum(tacc[s], scratch);
+            const double b = block_sum(bacc[s], scratch);
+            if (threadIdx.x == 0) {
+                atomicAdd(&sf[s * PGB_STATE_F64_LEN + PGB_SF_TACC], t);
+                atomicAdd(&sf[s * PGB_STATE_F64_LEN + PGB_SF_BIAS], b);
+            }
+        }
+}
+
+template <int PB>
+__global__ void panel_finish_kernel(const pgb_panel_job J, double *sf, int32_t *si) {
+    const int s = threadIdx.x;
+    if (s < PB) {
+        const int load = J.slot_plan[2 * s + 1];
+        if (load >= 0) {
+            double *sfs = sf + s * PGB_STATE_F64_LEN;
+            int32_t *sis = si + s * PGB_STATE_I32_LEN;
+            const double amul = J.col_params ? J.col_params[3 * (int64_t)load] : J.alpha;
+            const double alpha_s = J.col_params ? J.col_params[3 * (int64_t)load + 1] : J.alpha_s;
+            const double t = sfs[PGB_SF_TACC];
+            const bool live = sfs[PGB_SF_NORM] > 0.0;
+            sfs[PGB_SF_TACC] = 0.0;
+            sfs[PGB_SF_EACC] = 0.0;
+            sfs[PGB_SF_ALPHA] = alpha_s;
+            sfs[PGB_SF_AMUL] = amul;
+            sfs[PGB_SF_TOL] = J.tol;
+            sfs[PGB_SF_MEAN] = J.mean;
+            sfs[PGB_SF_INVS] = (J.quotient && live) ? 1.0 / (alpha_s * t + sfs[PGB_SF_BIAS]) : 1.0;
+            sis[PGB_SI_STEPS] = 0;
+            sis[PGB_SI_ITERATION] = 0;
+            sis[PGB_SI_MAX_ITERS] = J.max_iters;
+            sis[PGB_SI_END_MODULO] = J.end_modulo;
+            sis[PGB_SI_ERR_MODE] = J.err_mode;
+            sis[PGB_SI_QUOTIENT] = J.quotient;
+            sis[PGB_SI_STOP] = live ? PGB_RUNNING : PGB_CONVERGED;   // a zero personalization never iterates (:53-54)
+            J.slot_col[s] = load;
+        }
+    }
+    __syncthreads();
+    if (s == 0) {
+        bool running = false;
+        for (int k = 0; k < PB; ++k) running = running || si[k * PGB_STATE_I32_LEN + PGB_SI_STOP] == PGB_RUNNING;
+        si[PB * PGB_STATE_I32_LEN + 1] = running ? PGB_RUNNING : PGB_CONVERGED;   // the gather's stop word
+    }
+}
+
 template <typename S, typename V, int PB>
-static int panel_steps(const pgb_hsell *h, const PanelStep &P0, void *zbuf0, void *zbuf1, int first_step, int num_launches,
-                       bool symdeg, cudaStream_t st) {
+static int panel_steps(const pgb_hsell *h, const PanelStep &P0, const pgb_panel_job &J, void *zbuf0, void *zbuf1,
+                       int first_step, int num_launches, bool symdeg, cudaStream_t st) {
     PanelStep P = P0;
     void *buf[2] = {zbuf0, zbuf1};
     const int32_t *stop = P.si + PB * PGB_STATE_I32_LEN + 1;
@@ -1204,6 +1405,14 @@ static int panel_steps(const pgb_hsell *h, const PanelStep &P0, void *zbuf0, voi
         const int k = first_step + j;
         P.zin = buf[(k - 1) & 1];
         P.zout = buf[k & 1];
+        // slots change hands on the buffer this step reads
+        const int mgrid = stride_grid(P.n, 256) < 1184 ? stride_grid(P.n, 256) : 1184;
+        panel_plan_kernel<S, PB><<<1, 32 * PB, 0, st>>>(J, P.sf, P.si, P.err_hist);
+        panel_move_kernel<S, PB><<<mgrid, 256, 0, st>>>(J, P.n, (const S *)P.zin, (const S *)J.sq, P.sf);
+        panel_load_kernel<S, PB><<<mgrid, 256, 0, st>>>(J, P.n, (S *)const_cast<void *>(P.zin), (S *)const_cast<void *>(P.q),
+                                                        (const S *)J.sq, (const S *)P.c, P.sf);
+        panel_finish_kernel<PB><<<1, 32, 0, st>>>(J, P.sf, P.si);
+        PGB_LAUNCH_OK("panel scheduling kernels");
         if (launch_gather<V>(h, P.zin, P.y, true, stop, P.tail_queue, k, st)) return 1;
         if (symdeg)
             hsell_update_panel_kernel<S, PB, true><<<(int)want, UPP_BLOCK, 0, st>>>(P);
@@ -1333,18 +1542,23 @@ int pgb_hsell_panel_width(int dtype) { return dtype == PGB_F32 ? 4 : (dtype == P
 
 int pgb_hsell_panel_block_cols(void) { return (128 * 1024) / 16; }
 
-int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype, const double *alpha, const void *w,
-                           const void *sq, const void *c, const void *q, void *zbuf0, void *zbuf1, double *state_f64,
-                           int32_t *state_i32, double *err_hist, int32_t hist_stride, void *yacc, uint32_t *tail_queue,
-                           int first_step, int num_launches, void *stream) {
+int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype, const pgb_panel_job *job, const void *w,
+                           const void *c, void *q, void *zbuf0, void *zbuf1, double *state_f64, int32_t *state_i32,
+                           double *err_hist, void *yacc, uint32_t *tail_queue, int first_step, int num_launches,
+                           void *stream) {
     if (!h) return fail("pgb_affine_steps_panel: null hsell form");
+    if (!job) return fail("pgb_affine_steps_panel: null job");
     if (h->n_segments != 1) return fail("pgb_affine_steps_panel: row-partitioned forms are not supported");
     if (!h->piece_slice) return fail("pgb_affine_steps_panel needs pgb_hsell.piece_slice");
-    if ((w == nullptr) != (sq == nullptr)) return fail("pgb_affine_steps_panel: w and sq must both be given or both be NULL");
     if (!w && !indptr) return fail("pgb_affine_steps_panel: degree-derived factors need the row pointers");
     if (first_step < 1) return fail("pgb_affine_steps_panel: first_step must be >= 1");
-    if (!alpha || !yacc || !tail_queue) return fail("pgb_affine_steps_panel: alpha, yacc and tail_queue are required");
-    if (h->n_rows == 0) return 0;
+    if (!yacc || !tail_queue || !q || !c || !state_f64 || !state_i32 || !err_hist)
+        return fail("pgb_affine_steps_panel: q, c, the state arrays, err_hist, yacc and tail_queue are required");
+    if (!job->cols || !job->out || !job->sq || !job->sched || !job->slot_col || !job->slot_plan || !job->plan_norm ||
+        !job->col_result)
+        return fail("pgb_affine_steps_panel: incomplete job (cols, out, sq, sched, slot_col, slot_plan, plan_norm, col_result)");
+    if (job->n_cols < 0 || job->hist_stride < 2) return fail("pgb_affine_steps_panel: bad n_cols / hist_stride");
+    if (h->n_rows == 0 || job->n_cols == 0) return 0;
     const int PB = pgb_hsell_panel_width(dtype);
     if (!PB) return fail("pgb_affine_steps_panel: unknown dtype %d", dtype);
     PanelStep P;
@@ -1353,18 +1567,18 @@ int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype,
     P.indptr = indptr;
     P.q = q;
     P.w = w;
-    P.sq = sq;
+    P.sq = w ? job->sq : nullptr;
     P.c = c;
     P.y = yacc;
-    for (int i = 0; i < PB; ++i) P.alpha[i] = alpha[i];
     P.sf = state_f64;
     P.si = state_i32;
     P.err_hist = err_hist;
-    P.hist_stride = hist_stride;
+    P.hist_stride = job->hist_stride;
     P.tail_queue = tail_queue;
     const bool symdeg = (w == nullptr);
-    if (dtype == PGB_F32) return panel_steps<float, f32x4, 4>(h, P, zbuf0, zbuf1, first_step, num_launches, symdeg, as_stream(stream));
-    return panel_steps<double, f64x2, 2>(h, P, zbuf0, zbuf1, first_step, num_launches, symdeg, as_stream(stream));
+    if (dtype == PGB_F32)
+        return panel_steps<float, f32x4, 4>(h, P, *job, zbuf0, zbuf1, first_step, num_launches, symdeg, as_stream(stream));
+    return panel_steps<double, f64x2, 2>(h, P, *job, zbuf0, zbuf1, first_step, num_launches, symdeg, as_stream(stream));
 }
 
 int pgb_hsell_set_dropout(double p, uint64_t seed) {

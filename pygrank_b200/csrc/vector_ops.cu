@@ -99,6 +99,57 @@ __global__ void affine_init_finish_kernel(double *sf, int32_t *si) {
     sf[PGB_SF_INVS] = si[PGB_SI_QUOTIENT] ? 1.0 / (sf[PGB_SF_ALPHA] * t + sf[PGB_SF_BIAS]) : 1.0;
 }
 
+// ---- staging of a panel job: features [n][B] in user order <-> column-major blocks in the engine's row order ----------
+// A slot of the panel loads / stores ONE column at a time; from a row-major [n][B] matrix in user order that is one
+// 32-byte sector per 4-byte value at random rows.  The job therefore runs on a staged copy, stage[j][i] =
+// cols[perm[i]][j0 + j], written by one tiled transpose (rows gathered through perm in full lines), and its results
+// go back the same way.
+template <typename T>
+__global__ void panel_stage_in_kernel(int64_t n, const T *__restrict__ cols, int64_t row_stride, int64_t col_stride,
+                                      const int32_t *__restrict__ perm, int64_t j0, int G, T *__restrict__ stage) {
+    __shared__ T tile[32][33];
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    const int jj0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t i = i0 + r;
+        const int j = jj0 + threadIdx.x;
+        T v = (T)0;
+        if (i < n && j < G) {
+            const int64_t src = perm ? (int64_t)perm[i] : i;
+            v = cols[src * row_stride + (j0 + j) * col_stride];
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = jj0 + r;
+        const int64_t i = i0 + threadIdx.x;
+        if (j < G && i < n) stage[(int64_t)j * n + i] = tile[threadIdx.x][r];
+    }
+}
+
+template <typename T>
+__global__ void panel_stage_out_kernel(int64_t n, const T *__restrict__ stage, const int32_t *__restrict__ perm,
+                                       int64_t j0, int G, T *__restrict__ out, int64_t out_row_stride) {
+    __shared__ T tile[32][33];
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    const int jj0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = jj0 + r;
+        const int64_t i = i0 + threadIdx.x;
+        tile[r][threadIdx.x] = (j < G && i < n) ? stage[(int64_t)j * n + i] : (T)0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t i = i0 + r;
+        const int j = jj0 + threadIdx.x;
+        if (i < n && j < G) {
+            const int64_t dst = perm ? (int64_t)perm[i] : i;
+            out[dst * out_row_stride + j0 + j] = tile[threadIdx.x][r];
+        }
+    }
+}
+
 }  // namespace pgb
 
 using namespace pgb;
@@ -196,6 +247,37 @@ int pgb_affine_init_peer(int64_t n, int dtype, const void *p, const void *warm, 
 int pgb_affine_init_finish(double *state_f64, int32_t *state_i32, void *stream) {
     affine_init_finish_kernel<<<1, 1, 0, as_stream(stream)>>>(state_f64, state_i32);
     PGB_LAUNCH_OK("affine_init_finish_kernel");
+    return 0;
+}
+
+int pgb_panel_stage(int64_t n, int dtype, int direction, void *matrix, int64_t row_stride, int64_t col_stride,
+                    const int32_t *perm, int64_t j0, int32_t n_cols, void *stage, void *stream) {
+    if (n <= 0 || n_cols <= 0) return 0;
+    if (!matrix || !stage) return fail("pgb_panel_stage: null matrix / stage");
+    if (n > 32ll * 2147483647ll || (n_cols + 31) / 32 > 65535) return fail("pgb_panel_stage: too many rows / columns");
+    const dim3 grid((unsigned)ceil_div(n, 32), (unsigned)((n_cols + 31) / 32)), block(32, 8);
+    cudaStream_t st = as_stream(stream);
+    if (direction == 0) {   // matrix (user order, any strides) -> stage [n_cols][n] (engine order)
+        if (dtype == PGB_F32)
+            panel_stage_in_kernel<float><<<grid, block, 0, st>>>(n, (const float *)matrix, row_stride, col_stride, perm, j0,
+                                                                 n_cols, (float *)stage);
+        else if (dtype == PGB_F64)
+            panel_stage_in_kernel<double><<<grid, block, 0, st>>>(n, (const double *)matrix, row_stride, col_stride, perm,
+                                                                  j0, n_cols, (double *)stage);
+        else
+            return fail("pgb_panel_stage: unknown dtype %d", dtype);
+    } else {                // stage -> matrix columns j0.. (row-major: col_stride must be 1)
+        if (col_stride != 1) return fail("pgb_panel_stage: the output matrix must have unit column stride");
+        if (dtype == PGB_F32)
+            panel_stage_out_kernel<float><<<grid, block, 0, st>>>(n, (const float *)stage, perm, j0, n_cols, (float *)matrix,
+                                                                  row_stride);
+        else if (dtype == PGB_F64)
+            panel_stage_out_kernel<double><<<grid, block, 0, st>>>(n, (const double *)stage, perm, j0, n_cols,
+                                                                   (double *)matrix, row_stride);
+        else
+            return fail("pgb_panel_stage: unknown dtype %d", dtype);
+    }
+    PGB_LAUNCH_OK("panel_stage_kernel");
     return 0;
 }
 

@@ -19,6 +19,7 @@ this engine through the backend plugin (pygrank_b200/backend.py); these classes 
 from __future__ import annotations
 
 import ctypes
+import os
 import time
 from typing import Optional, Sequence
 
@@ -321,7 +322,7 @@ class RecursiveGraphFilter(GraphFilter):
         if g.in_view.weighted or warm_start is not None or graph_dropout != 0 or g.pathological:
             return False
         family = self._panel_family(g)
-        if family is None:
+        if family is None or (family == "hsell" and self.convergence.max_iters <= 1):
             return False
         if family == "csr" and _error_code(self.convergence.error_type) == C.ERR_MAX:
             return False                                      # the item-stream panel kernel has no max reduction
@@ -333,6 +334,156 @@ class RecursiveGraphFilter(GraphFilter):
         return n_columns >= 2 or family == "csr"
 
     def _propagate_batched(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
+        kwargs.pop("n_columns", None)
+        if self._panel_family(g) == "hsell":
+            return self._propagate_panels(g, cols, **kwargs)
+        if self._column_alphas(int(cols.shape[1])) is not None:
+            raise Exception("per-column alpha needs the hub-blocked panel kernel (unweighted graph, PGB_HSELL=1)")
+        return self._propagate_batched_csr(g, cols, **kwargs)
+
+    def _propagate_panels(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
+        """All feature columns through ``pgb_affine_steps_panel``: the panel's ``pgb_hsell_panel_width`` columns are
+        SLOTS scheduled on the device — a column enters a free slot (normalisation, scaled start vector, affine term,
+        state: abstract_filters.py:52-56), iterates with its own alpha, normaliser, error and stop decision, and is
+        written out when it stops while the others keep going, so no slot waits for the slowest column of a fixed group
+        and the host only polls the number of finished columns.  Results and iteration counts equal the reference's
+        column-by-column loop (signals.py:225-226)."""
+        lib = C.lib()
+        dtype, code = self.dtype, dtype_code(self.dtype)
+        f64, i32 = torch.float64, torch.int32
+        dev, n = g.out_view.indptr.device, g.n
+        st = C.stream_ptr()
+        cm = self.convergence
+        B = int(cols.shape[1])
+        PB = lib.pgb_hsell_panel_width(code)
+        a = self._affine_args(g, **kwargs)
+        alpha, alpha_s, w_run, c_run, coef, coefvec = (a["alpha"], a["alpha_s"], a["w_run"], a["c_run"], a["coef"],
+                                                       a["coefvec"])
+        col_alphas = self._column_alphas(B)                   # per column (multiplier, alpha_s, coef) or None
+        sq = g.vec("sq", dtype)
+        c = c_run if c_run is not None else g.vec("c", dtype)
+        symdeg = g.symdeg and w_run is None
+        w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
+        view = g.in_view
+        form = view.hsell_panel()
+        err_code = _error_code(cm.error_type)
+        tol = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))
+        cols = cols.to(device=dev, dtype=dtype)               # [n, B] in user order, any strides
+        out = torch.empty((n, B), dtype=dtype, device=dev)
+        iterations, errors = [], []
+        if B == 0:
+            cm.iterations, cm.column_errors = [], []
+            return out
+        t0 = time.perf_counter()
+        esz = cols.element_size()
+        hist = cm.max_iters + 2
+        L = C.STATE_LEN
+        # working set of the panel (allocated once, reused by every group of columns)
+        yacc = torch.zeros((form.n_slices + 1) * 32 * PB, dtype=dtype, device=dev)
+        tail_queue = torch.zeros(1, dtype=i32, device=dev)
+        zbuf = [torch.zeros((n, PB), dtype=dtype, device=dev), torch.zeros((n, PB), dtype=dtype, device=dev)]
+        q = torch.zeros((n, PB), dtype=dtype, device=dev)
+        err_hist = torch.zeros((PB, hist), dtype=f64, device=dev)
+        si_host = np.zeros(PB * L + 4, dtype=np.int32)        # + ticket, panel stop word, executed steps, spare
+        si_host[:PB * L].reshape(PB, L)[:, C.SI_STOP] = C.CONVERGED          # empty slots never run
+        si_host[PB * L + 1] = C.CONVERGED
+        # Columns are staged in groups: column-major blocks in the engine's row order (pgb_panel_stage), so that a slot
+        # loads / stores its column as one contiguous stream instead of one sector per value at random rows.  A group is
+        # as large as memory comfortably allows (input + output stage).
+        free_bytes = torch.cuda.mem_get_info(dev)[0]
+        group = int(max(4 * PB, min(B, (free_bytes * 2 // 5) // max(2 * n * esz, 1))))
+        group = int(getattr(self, "panel_group", group))
+        stage_in = torch.empty((min(group, B), n), dtype=dtype, device=dev)
+        stage_out = torch.empty((min(group, B), n), dtype=dtype, device=dev)
+        chunk = max(int(getattr(self, "panel_chunk", 8)), 1)  # steps enqueued between polls of the finished count
+        polls = [torch.empty(4, dtype=i32).pin_memory() for _ in range(2)]
+        events = [torch.cuda.Event(), torch.cuda.Event()]
+        C.count_launches(1)
+        marks = [] if os.environ.get("PGB_PANEL_TIMING") else None
+
+        def mark(label):
+            if marks is not None:
+                torch.cuda.synchronize()
+                marks.append((label, time.perf_counter()))
+
+        mark("buffers")
+        for j0 in range(0, B, group):
+            G = min(group, B - j0)
+            C.check(lib.pgb_panel_stage(n, code, 0, cols.data_ptr(), int(cols.stride(0)), int(cols.stride(1)),
+                                        C.ptr(g.perm), j0, G, C.ptr(stage_in), st))
+            for t in (zbuf[0], zbuf[1], q, yacc, tail_queue):
+                t.zero_()
+            sf = torch.zeros((PB, L), dtype=f64, device=dev)
+            si = torch.from_numpy(si_host).to(dev)
+            sched = torch.zeros(4, dtype=i32, device=dev)
+            slot_col = torch.full((PB,), -1, dtype=i32, device=dev)
+            slot_plan = torch.full((2 * PB,), -1, dtype=i32, device=dev)
+            plan_norm = torch.zeros(PB, dtype=f64, device=dev)
+            col_result = torch.zeros((G, 4), dtype=i32, device=dev)
+            keep_hist = G * hist <= (1 << 24)                 # error histories of every column (128 MB at most)
+            col_err = torch.zeros((G, hist), dtype=f64, device=dev) if keep_hist else None
+            params = None
+            if col_alphas is not None:
+                params = torch.tensor([[float(v) for v in t] for t in col_alphas[j0:j0 + G]], dtype=f64,
+                                      device=dev).contiguous()
+            job = C.PanelJob(G, hist, stage_in.data_ptr(), 1, n, stage_out.data_ptr(), 1, n, None, C.ptr(sq),
+                             None if params is not None else C.ptr(coefvec), C.ptr(params), float(alpha),
+                             float(alpha_s), float(coef), tol, 1.0 if err_code in (C.ERR_L1, C.ERR_MAX) else float(n),
+                             int(cm.max_iters), max(int(cm.end_modulo), 1), err_code, int(self.use_quotient),
+                             int(self.preserve_norm), C.ptr(sched), C.ptr(slot_col), C.ptr(slot_plan),
+                             C.ptr(plan_norm), C.ptr(col_result), C.ptr(col_err))
+            budget = (cm.max_iters + 2) * (G // PB + 2) + chunk   # more steps than any schedule needs: guards a driver bug
+
+            # chunk i+1 is enqueued before the finished count after chunk i is looked at (pinned copy + event): the
+            # device never waits for the host; the launches enqueued past the end are no-ops
+            def enqueue(i):
+                C.check(lib.pgb_affine_steps_panel(ctypes.byref(form.struct), C.ptr(view.indptr), code,
+                                                   ctypes.byref(job), C.ptr(w), C.ptr(c), C.ptr(q), C.ptr(zbuf[0]),
+                                                   C.ptr(zbuf[1]), C.ptr(sf), C.ptr(si), C.ptr(err_hist), C.ptr(yacc),
+                                                   C.ptr(tail_queue), i * chunk + 1, chunk, st))
+                C.count_launches(6 * chunk)
+                polls[i & 1].copy_(sched, non_blocking=True)
+                events[i & 1].record()
+
+            mark("staged in")
+            enqueue(0)
+            i = 0
+            while True:
+                enqueue(i + 1)
+                events[i & 1].synchronize()
+                if int(polls[i & 1][1]) >= G:
+                    break
+                i += 1
+                if i * chunk > budget:
+                    raise Exception("pygrank_b200: panel scheduling did not terminate")
+            mark("job")
+            C.check(lib.pgb_panel_stage(n, code, 1, out.data_ptr(), B, 1, C.ptr(g.perm), j0, G, C.ptr(stage_out), st))
+            C.count_launches(2)
+            res = col_result.cpu().numpy()
+            mark("staged out")
+            for j in range(G):
+                it, stop, steps, live = (int(v) for v in res[j])
+                if not live:                                                    # abstract_filters.py:53-54
+                    iterations.append(0)
+                    errors.append(None)
+                    continue
+                iterations.append(it)
+                errors.append(col_err[j, 1:steps + 1] if col_err is not None else None)
+                if stop == C.MAX_ITERS and err_code != C.ERR_ITERS and cm.iter_exception is not None:
+                    raise cm.iter_exception("Could not converge within " + str(cm.max_iters) + " iterations")
+        if marks is not None:
+            prev = t0
+            for label, t in marks:
+                print(f"[panel] {label}: {(t - prev) * 1e3:.2f} ms", flush=True)
+                prev = t
+        cm.iterations = iterations
+        cm.iteration = iterations[-1] if iterations else 0
+        cm.errors = errors[-1] if errors else None
+        cm.column_errors = errors
+        cm.elapsed_time = time.perf_counter() - t0
+        return out
+
+    def _propagate_batched_csr(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
         """All feature columns through ``pgb_affine_steps_batched``: panels of ``pgb_panel_width``
         columns share one pass over the index stream per iteration; every column keeps its own
         normaliser, error and stop decision, so results and iteration counts equal the reference's
@@ -344,8 +495,7 @@ class RecursiveGraphFilter(GraphFilter):
         st = C.stream_ptr()
         cm = self.convergence
         B = int(cols.shape[1])
-        family = self._panel_family(g)
-        PB = lib.pgb_hsell_panel_width(code) if family == "hsell" else lib.pgb_panel_width(code)
+        PB = lib.pgb_panel_width(code)
         kwargs.pop("n_columns", None)
         a = self._affine_args(g, **kwargs)
         alpha, alpha_s, w_run, c_run, coef, coefvec = (a["alpha"], a["alpha_s"], a["w_run"], a["c_run"], a["coef"],
@@ -356,23 +506,14 @@ class RecursiveGraphFilter(GraphFilter):
         w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
         sq_arg = None if symdeg else sq
         view = g.in_view
-        if family == "hsell":
-            form = view.hsell_panel()
-            yacc = torch.zeros((form.n_slices + 1) * 32 * PB, dtype=dtype, device=dev)
-            tail_queue = torch.zeros(1, dtype=torch.int32, device=dev)
-            kernels_per_step = 2
-        else:
-            cs = view.cstruct(dtype, hsell=False)             # the item-stream panel kernel
-            kernels_per_step = 1
-        col_alphas = self._column_alphas(B)                   # per column (alpha, alpha_s, coef) or None
+        cs = view.cstruct(dtype, hsell=False)                 # the panel kernel reads the item stream
         err_code = _error_code(cm.error_type)
         tol = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))
         perm = None if g.perm is None else g.perm.long()
         out = torch.empty((n, B), dtype=dtype, device=dev)
-        if family == "csr":
-            acc = torch.zeros(max(view.n_tiles, 1) * PB, dtype=f64, device=dev)
-            cnt = torch.zeros(max(view.n_tiles, 1), dtype=torch.int32, device=dev)
-            ws = (acc, cnt)
+        acc = torch.zeros(max(view.n_tiles, 1) * PB, dtype=f64, device=dev)
+        cnt = torch.zeros(max(view.n_tiles, 1), dtype=torch.int32, device=dev)
+        ws = (acc, cnt)
         hist = cm.max_iters + 2
         budget = cm.max_iters - 1
         iterations, errors = [], []
@@ -389,23 +530,15 @@ class RecursiveGraphFilter(GraphFilter):
             zbuf = [torch.zeros((n, PB), dtype=dtype, device=dev), torch.zeros((n, PB), dtype=dtype, device=dev)]
             q = torch.zeros((n, PB), dtype=dtype, device=dev)
             zbuf[0][:, :nb] = pn / sq[:, None]
-            a_mul = np.full(PB, float(alpha))                 # multiplier of the gathered sum, per column
-            a_state = torch.full((PB,), float(alpha_s), dtype=f64, device=dev)
-            if col_alphas is not None:
-                trip = col_alphas[c0:c0 + nb]
-                a_mul[:nb] = [t[0] for t in trip]
-                a_state[:nb] = torch.tensor([t[1] for t in trip], dtype=f64, device=dev)
-                qc = torch.tensor([t[2] for t in trip], dtype=f64, device=dev)[None, :]
-            else:
-                qc = coefvec.to(f64)[:, None] if coefvec is not None else float(coef)
+            qc = coefvec.to(f64)[:, None] if coefvec is not None else float(coef)
             q[:, :nb] = (qc * pn.to(f64)).to(dtype) / sq[:, None]
             del pn
             tacc = (zbuf[0].to(f64) * c.to(f64)[:, None]).sum(dim=0)
             bias = (q.to(f64) * sq.to(f64)[:, None]).sum(dim=0)
             sf = torch.zeros((PB, C.STATE_LEN), dtype=f64, device=dev)
-            sf[:, C.SF_ALPHA] = a_state
+            sf[:, C.SF_ALPHA] = float(alpha_s)
             sf[:, C.SF_BIAS] = bias
-            sf[:, C.SF_INVS] = 1.0 / (a_state * tacc + bias) if self.use_quotient else 1.0
+            sf[:, C.SF_INVS] = 1.0 / (float(alpha_s) * tacc + bias) if self.use_quotient else 1.0
             sf[:, C.SF_TOL] = tol
             sf[:, C.SF_MEAN] = 1.0 if err_code == C.ERR_L1 else float(n)
             sf[:nb, C.SF_NORM] = norms
@@ -417,29 +550,17 @@ class RecursiveGraphFilter(GraphFilter):
             live_host = live.cpu().numpy()
             si_host[:, C.SI_STOP] = C.CONVERGED                                 # padding / zero columns never run
             si_host[:nb, C.SI_STOP] = np.where(live_host, C.RUNNING, C.CONVERGED)
-            # two shared words after the columns: the ticket, and the panel stop word of the hsell family
-            si = torch.from_numpy(np.concatenate([si_host.reshape(-1), np.zeros(2, np.int32)])).to(dev)
-            alpha_arr = (ctypes.c_double * PB)(*a_mul.tolist())
-            uniform_alpha = bool((a_mul == a_mul[0]).all())
+            si = torch.from_numpy(np.concatenate([si_host.reshape(-1), np.zeros(1, np.int32)])).to(dev)
             err_hist = torch.zeros((PB, hist), dtype=f64, device=dev)
             C.count_launches(1)
             done, chunk = 0, max(self.chunk, 1)
             host = si_host
             while done < budget and (host[:, C.SI_STOP] == C.RUNNING).any():
                 k = min(chunk, budget - done)
-                if family == "hsell":
-                    C.check(lib.pgb_affine_steps_panel(ctypes.byref(form.struct), C.ptr(view.indptr), code, alpha_arr,
-                                                       C.ptr(w), C.ptr(sq_arg), C.ptr(c), C.ptr(q), C.ptr(zbuf[0]),
-                                                       C.ptr(zbuf[1]), C.ptr(sf), C.ptr(si), C.ptr(err_hist), hist,
-                                                       C.ptr(yacc), C.ptr(tail_queue), done + 1, k, st))
-                else:
-                    if not uniform_alpha:
-                        raise Exception("per-column alpha needs the hub-blocked panel kernel (unweighted graph, PGB_HSELL=1)")
-                    C.check(lib.pgb_affine_steps_batched(ctypes.byref(cs), code, float(a_mul[0]), C.ptr(w), C.ptr(sq_arg),
-                                                         C.ptr(c), C.ptr(q), C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(sf),
-                                                         C.ptr(si), C.ptr(err_hist), hist, span_struct(ws), done + 1, k,
-                                                         st))
-                C.count_launches(k * kernels_per_step)
+                C.check(lib.pgb_affine_steps_batched(ctypes.byref(cs), code, float(alpha), C.ptr(w), C.ptr(sq_arg),
+                                                     C.ptr(c), C.ptr(q), C.ptr(zbuf[0]), C.ptr(zbuf[1]), 0, C.ptr(sf),
+                                                     C.ptr(si), C.ptr(err_hist), hist, span_struct(ws), done + 1, k, st))
+                C.count_launches(k)
                 done += k
                 host = si.cpu().numpy()[:PB * C.STATE_LEN].reshape(PB, C.STATE_LEN)
                 chunk = min(chunk * 2, 64)

@@ -129,7 +129,9 @@ def hsell_shape(dtype: torch.dtype, n_segments: int, seg_len: int, cfg: Optional
         # 16.8 M columns: 64 -> .685, 96 -> .670, 128 -> .70; fp64 (blocks half as wide): 64 -> 1.00, 128 -> .965;
         # fp32, 134 M columns on 8 ranks: 64 -> 1.40, 128 -> 1.28, 256 -> 1.19, 512 -> 1.36
         # round 2 (TEX tail + RED pieces, 16.8 M columns): 48 -> .562, 64 -> .531, 80 -> .522 ms: ~1/6.4 of the columns
-        max_blocks = max(64, min(_env_int("PGB_HSELL_BLOCKS_CAP", 256), (5 * n_segments * seg_len) // (32 * H)))
+        # panel forms (blocks of 8192 nodes): 192 -> 1.405, 256 -> 1.394, 384 -> 1.339 ms per 4-column step
+        cap_blocks = _env_int("PGB_HSELL_BLOCKS_CAP", 256 if elem_bytes is None else 384)
+        max_blocks = max(64, min(cap_blocks, (5 * n_segments * seg_len) // (32 * H)))
     K = max(min(max_blocks, -(-seg_len // Hs)), 0)
     if n_segments > 1 and K * Hs > seg_len:
         K = seg_len // Hs                            # multi-segment blocks must be full; the rest is tail

@@ -1,16 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-out=gpurun_out/panel_probe2.jsonl
-: > $out
-run() { env "$@" timeout 300 python scripts/panel_probe.py 2>&1 | tail -1 >> $out; }
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=2
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=3
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=4
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=6
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=4 PGB_HSELL_TAIL_WINDOW_MIN=64
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=4 PGB_HSELL_TAIL_WINDOW_MIN=16
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=4 PGB_HSELL_TAIL_WARPS=8
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=4 PGB_HSELL_MIN_ENTRIES=16
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=4 PGB_HSELL_MIN_ENTRIES=48
-run PGB_PANEL=1 PGB_HSELL_TAIL_WINDOWS=4 PROBE_DTYPE=f64
-cut -c1-60,330-480 $out
+PGB_PANEL_TIMING=1 timeout 300 python scripts/panel_e2e.py 2>&1 | tail -12
+PROBE_PANEL_CHUNK=4 timeout 300 python scripts/panel_e2e.py 2>&1 | tail -1
+PROBE_PANEL_CHUNK=16 timeout 300 python scripts/panel_e2e.py 2>&1 | tail -1
+PROBE_PANEL_GROUP=64 timeout 300 python scripts/panel_e2e.py 2>&1 | tail -1
+PGB_PANEL=1 timeout 300 python scripts/panel_probe.py 2>&1 | tail -1 | cut -c1-60,330-420

@@ -282,7 +282,7 @@ def test_batched_propagate_matches_golden(pgb, torch_cuda, monkeypatch, name, ru
 
 
 @pytest.mark.parametrize("dtype_name,tol", [("float64", 1e-12), ("float32", 2e-6)])
-@pytest.mark.parametrize("family", ["hsell", "hsell_small_blocks", "csr"])
+@pytest.mark.parametrize("family", ["hsell", "hsell_small_blocks", "hsell_groups", "csr"])
 def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, monkeypatch, dtype_name, tol, family):
     """11 columns (full panels + a ragged one), one all-zero column, columns that converge at
     different iterations; the batched result must equal the single-column fused path."""
@@ -307,6 +307,8 @@ def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, monkeypatch, dt
         k = [1, 10, 1000, n // 2][c % 4]
         P[rng.choice(n, k, replace=False), c] = rng.uniform(0.5, 2.0, k)
     alg = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=dtype)
+    if family == "hsell_groups":
+        alg.panel_group, alg.panel_chunk = 5, 3             # columns staged in three groups, polled every 3 steps
     out = alg.propagate(g, torch.from_numpy(P).cuda())
     its = list(alg.convergence.iterations)
     assert out.shape == (n, B) and its[4] == 0 and not bool(out[:, 4].any())

@@ -88,7 +88,7 @@ def test_hsell_shape_and_config_defaults(monkeypatch):
     H, K = graph.hsell_shape(torch.float32, 2, 5000)            # multi-segment blocks must be full
     assert K == 0
     H, K = graph.hsell_shape(None, 1, 1 << 24, elem_bytes=graph.PANEL_ELEM_BYTES)   # panel form: 16 bytes per node
-    assert H == 8192 and K == 256
+    assert H == 8192 and K == 320
     monkeypatch.setenv("PGB_HSELL_BLOCK_COLS", "1000000")        # clamped to what shared memory holds
     assert graph.hsell_shape(None, 1, 1 << 24, elem_bytes=16)[0] == ((232448 - 64) // 16 - 1) & ~63
     H, _ = graph.hsell_shape(torch.float32, 1, 1 << 24)
