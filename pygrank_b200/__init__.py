@@ -21,7 +21,7 @@ from ._capi import build, lib
 
 __all__ = ["build", "lib", "install", "configure", "preprocessor", "DeviceGraph", "PageRank", "PageRankClosed",
            "HeatKernel", "GenericGraphFilter", "AbsorbingWalks", "ConvergenceManager", "RankResult", "Normalize", "Ordinals",
-           "Top", "Threshold", "import_snap_format_dataset", "from_fastgraph"]
+           "Top", "Threshold", "import_snap_format_dataset", "from_fastgraph", "AlphaSweep"]
 
 BACKEND_NAME = "b200"
 
@@ -41,6 +41,9 @@ def __getattr__(name):
     if name in ("import_snap_format_dataset", "from_fastgraph", "read_pairs", "graph_from_pairs"):
         from . import ingest
         return getattr(ingest, name)
+    if name == "AlphaSweep":
+        from . import tuning
+        return tuning.AlphaSweep
     if name == "configure":
         from . import backend
         return backend.configure

@@ -245,3 +245,37 @@ def test_parameter_tuner_runs_unchanged_on_b200(pg):
     pg.load_backend("numpy")
     assert found["numpy"][0] == pytest.approx(found["b200"][0], abs=1e-9)
     assert rel_l1(found["b200"][1], found["numpy"][1]) <= 1e-9
+
+
+def test_parameter_tuner_candidates_run_as_panels(pg):
+    """pg.ParameterTuner, unmodified, with pygrank_b200.AlphaSweep as its ranker generator and optimizer: every round's
+    candidates are columns of one panel sweep (pgb_affine_steps_panel, per-column alpha), and the tuner lands on the
+    parameters and scores the stock numpy run finds."""
+    import pygrank_b200
+    z, A, directed = load_golden("ba2000")
+    rng = np.random.default_rng(0)
+    n = A.shape[0]
+    members = rng.choice(n, 200, replace=False)
+    args = dict(max_vals=[0.99], min_vals=[0.5], measure=pg.AUC, deviation_tol=0.01)
+    pg.load_backend("numpy")
+    graph = pg.AdjacencyWrapper(A, directed=directed)
+    pre = pg.preprocessor(normalization="symmetric", assume_immutability=True)
+    stock = pg.ParameterTuner(lambda params: pg.PageRank(params[0], preprocessor=pre, tol=1e-9, max_iters=1000),
+                              tuning_backend="numpy", **args)
+    ref = stock(graph, pg.to_signal(graph, {int(v): 1.0 for v in members}))
+    ref_scores = np.asarray(ref.np, dtype=np.float64)
+    pg.load_backend("b200")
+    try:
+        sweep = pygrank_b200.AlphaSweep(tol=1e-9, max_iters=1000, normalization="symmetric")
+        tuner = pg.ParameterTuner(sweep.ranker, optimizer=sweep.optimizer, tuning_backend="b200", **args)
+        graph = pg.AdjacencyWrapper(A, directed=directed)
+        got = tuner(graph, pg.to_signal(graph, {int(v): 1.0 for v in members}))
+        got_scores = got.np.cpu().numpy()
+    finally:
+        pg.load_backend("numpy")
+    assert list(tuner.last_params) == pytest.approx(list(stock.last_params), abs=1e-9)
+    assert rel_l1(got_scores, ref_scores) <= 1e-9
+    # 5 candidates per round (the stock default): one sweep per round carries the round's new candidates (those of an
+    # earlier round are served from the cache), plus one single-column solve for the final ranking
+    assert sweep.stats["sweeps"] >= 2 and sweep.stats["columns"] >= 5 + (sweep.stats["sweeps"] - 1)
+    assert sweep.stats["served"] >= 2 * 5 + 1 > sweep.stats["sweeps"]
