@@ -166,7 +166,7 @@ def main():
         fixed = pgb.PageRank(0.85, error_type="iters", max_iters=41, dtype=dtype_p)
         cols = P[:, :width].to(dtype_p).contiguous()
         fixed.propagate(g, cols)
-        dtp, _ = timed(lambda: fixed.propagate(g, cols))
+        dtp = min(timed(lambda: fixed.propagate(g, cols))[0] for _ in range(3))
         panel_ms[dt_name] = {"columns": width, "steps": 40, "ms_per_panel_step": dtp / 40 * 1e3,
                              "edge_column_gteps": g.nnz * 40 * width / dtp / 1e9}
     one = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=torch.float32)
