@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PGB_ABI_VERSION 3
+#define PGB_ABI_VERSION 4
 
 enum { PGB_F32 = 0, PGB_F64 = 1 };
 
@@ -78,7 +78,7 @@ typedef struct pgb_csr {
     const struct pgb_hsell *hsell; /* hub-blocked sliced-ELL form (HOST pointer to the struct) or NULL     */
 } pgb_csr;
 
-/* Hub-blocked sliced-ELL form of an UNWEIGHTED pull CSR whose nodes are ranked by degree (built once
+/* Hub-blocked sliced-ELL form of a pull CSR (unweighted, or weighted: hub_vals / tail_vals) whose nodes are ranked by degree (built once
  * per graph and vector dtype with pgb_hsell_count + pgb_hsell_fill).  Rows are cut into slices of 32
  * (one lane per row); columns into n_blocks "hub blocks" of block_cols columns — what one SM keeps of
  * the gather vector in shared memory — and a tail.  The entries of (slice, block) form a UNIT of
@@ -125,6 +125,9 @@ typedef struct pgb_hsell {
     const int32_t *cta_hub_begin;     /* [n_ctas+1]                                                 */
     const int32_t *cta_tail_begin;    /* [n_ctas+1]                                                 */
     const int32_t *piece_slice;       /* [pieces] slice of each piece (n_slices for padding pieces): accumulate mode */
+    const void *hub_vals;             /* weighted graphs: [n_hub_chunks*CHUNK*32][2] edge values of the two halves of
+                                         every hub word, in the dtype of the form (0 in padding slots); NULL: all 1 */
+    const void *tail_vals;            /* weighted graphs: [n_tail_chunks*CHUNK*32] edge values of the tail entries   */
 } pgb_hsell;
 
 /* Cross-tile workspace of one running filter: rows that straddle merge-path tiles are
@@ -248,13 +251,16 @@ int pgb_hsell_count(int64_t n, const int32_t *indptr, const int32_t *indices, in
  * with the dump row.  scratch (int32[nnz], or NULL) enables the bank-aware slot order:
  * within a unit, entry position p of lane l gets a column of shared-memory bank (l + p) mod banks
  * when the row has one (banks = 32 for fp32, 16 for fp64 vectors), which removes most bank conflicts
- * of the gather kernel; the order of a row's entries has no other meaning. */
+ * of the gather kernel; the order of a row's entries has no other meaning.
+ * WEIGHTED graphs: `values` ([nnz], `dtype`, the CSR's edge values) are written next to the indices — hub_vals
+ * [words][2] (the values of the two halves of every hub word), tail_vals [tail words] — both zero-filled by the caller
+ * (padding slots multiply the zero padding entry of the gather vector).  values = NULL: unweighted form. */
 int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int32_t block_cols, int32_t n_blocks,
                    int32_t n_segments, int64_t seg_len, const int32_t *hub_rounds, const int32_t *tail_rounds,
                    const int64_t *hub_round_base, const int64_t *hub_part_base, const int64_t *tail_round_base,
                    const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
                    int32_t *piece_row, int32_t *scratch, int32_t banks, int32_t n_windows, int64_t window_len,
-                   void *stream);
+                   int dtype, const void *values, void *hub_vals, void *tail_vals, void *stream);
 /* K8 — graph_dropout inside the gather kernel of the hsell form (torch backends' semantics,
  * /root/reference/pygrank/core/backend/pytorch.py:34-38; called once per iteration, abstract_filters.py:59-62): while
  * p > 0 every stored entry is dropped with probability p by a counter-based hash of (seed, gather launches since this

@@ -23,7 +23,7 @@ RUNNING, CONVERGED, MAX_ITERS = 0, 1, 2
 SF_ALPHA, SF_BIAS, SF_INVS, SF_TACC, SF_EACC, SF_TOL, SF_MEAN, SF_LASTERR, SF_NORM, SF_PSUM, SF_AMUL = range(11)
 SI_TICKET, SI_STEPS, SI_STOP, SI_ITERATION, SI_MAX_ITERS, SI_END_MODULO, SI_ERR_MODE, SI_QUOTIENT = range(8)
 STATE_LEN = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 SIGNATURE_WORDS = 8
 HSELL_MAX_WINDOWS = 16
 HSELL_CHUNK = 32   # PGB_HSELL_CHUNK: rounds per chunk of the hsell streams
@@ -48,7 +48,7 @@ class PanelJob(Structure):
 
 
 class Hsell(Structure):
-    """pgb_hsell (include/pgb200.h): hub-blocked sliced-ELL form of an unweighted pull CSR."""
+    """pgb_hsell (include/pgb200.h): hub-blocked sliced-ELL form of a pull CSR (edge values optional)."""
     _fields_ = [("n_rows", c_int64), ("n_slices", c_int64), ("n_partials", c_int64), ("seg_len", c_int64),
                 ("n_segments", c_int32), ("block_cols", c_int32), ("n_blocks", c_int32), ("n_ctas", c_int32),
                 ("n_hub_chunks", c_int32), ("n_tail_chunks", c_int32), ("n_heavy", c_int32), ("heavy_parts", c_int32),
@@ -57,7 +57,7 @@ class Hsell(Structure):
                 ("piece_row", c_void_p), ("upd_rows", c_void_p), ("heavy_slices", c_void_p),
                 ("reduce_items", c_void_p),
                 ("block_chunk_begin", c_void_p), ("cta_hub_begin", c_void_p), ("cta_tail_begin", c_void_p),
-                ("piece_slice", c_void_p)]
+                ("piece_slice", c_void_p), ("hub_vals", c_void_p), ("tail_vals", c_void_p)]
 
 
 MAX_PEERS = 16
@@ -86,7 +86,7 @@ _SIGNATURES = {
                                 c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "pgb_hsell_fill": (c_int, [c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_int32, c_int32, c_int64, c_void_p]),
+                               c_void_p, c_int32, c_int32, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgb_build_item_stream": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "pgb_gather_probe": (c_int, [POINTER(Csr), c_int, c_void_p, c_void_p, c_void_p]),

@@ -158,8 +158,11 @@ constexpr int FILL_GROUP = 8;   // hub blocks per work item of the fill kernel
 // the last part the slice's tail (entries of the blocks without a unit, then the columns past the hub
 // blocks).  Splitting the slices matters for the hub rows: the top slice alone holds ~1 % of all entries
 // and used to be the critical path of the whole build.
+template <typename VT, bool WEIGHTED>
 __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__restrict__ indptr,
-                                  const int32_t *__restrict__ indices, int H, int K, int N, int64_t seg_len,
+                                  const int32_t *__restrict__ indices, const VT *__restrict__ values,
+                                  VT *__restrict__ hub_vals, VT *__restrict__ tail_vals, int H, int K, int N,
+                                  int64_t seg_len,
                                   const int32_t *__restrict__ hub_rounds, const int32_t *__restrict__ tail_rounds,
                                   const int64_t *__restrict__ hub_round_base, const int64_t *__restrict__ hub_part_base,
                                   const int64_t *__restrict__ tail_round_base,
@@ -202,12 +205,18 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                 const int64_t g0 = hub_round_base[(int64_t)blk * n_slices + s];
                 const int64_t wb = g0 * 32;
                 const int base = blk * H;
+                // WEIGHTED: the value of the entry in half hh of word (round j, lane) sits at hub_vals[2*word + hh]
+                // (a lane reads both halves' values of a round as one 8- or 16-byte load); padding slots keep 0
                 if (scratch == nullptr || len < 2) {
                     for (int j = 0; j < R; ++j) {
                         const int i0 = 2 * j, i1 = 2 * j + 1;
                         const uint32_t lo = (i0 < len) ? (uint32_t)(indices[pos + i0] - base) : (uint32_t)H;
                         const uint32_t hi = (i1 < len) ? (uint32_t)(indices[pos + i1] - base) : (uint32_t)H;
                         hub_words[wb + (int64_t)j * 32 + lane] = lo | (hi << 16);
+                        if (WEIGHTED) {
+                            if (i0 < len) hub_vals[2 * (wb + (int64_t)j * 32 + lane)] = values[pos + i0];
+                            if (i1 < len) hub_vals[2 * (wb + (int64_t)j * 32 + lane) + 1] = values[pos + i1];
+                        }
                     }
                 } else {
                     // Bank-aware slot order.  The 32 lanes of a round read shared memory together; with the
@@ -225,9 +234,9 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                         cur[q] = run;
                         run += cnt[q];
                     }
-                    for (int i = 0; i < len; ++i) {
+                    for (int i = 0; i < len; ++i) {   // scratch: the row's entries (offsets from pos) bucketed by bank
                         const int c = indices[pos + i] - base;
-                        scratch[pos + cur[c & (banks - 1)]++] = c;
+                        scratch[pos + cur[c & (banks - 1)]++] = i;
                     }
                     // cur[q] is now the END of bucket q; the bucket starts cnt[q] earlier
                     for (int q = 0; q < banks; ++q) cur[q] -= cnt[q];
@@ -241,7 +250,9 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                             } else {
                                 const int tb = (lane + pp) & (banks - 1);
                                 if (cnt[tb] > 0) {
-                                    half[hh] = (uint32_t)scratch[pos + cur[tb]++];
+                                    const int src = scratch[pos + cur[tb]++];
+                                    half[hh] = (uint32_t)(indices[pos + src] - base);
+                                    if (WEIGHTED) hub_vals[2 * (wb + (int64_t)j * 32 + lane) + hh] = values[pos + src];
                                     --cnt[tb];
                                 } else {
                                     half[hh] = HOLE;
@@ -258,7 +269,9 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                         for (int hh = 0; hh < 2; ++hh) {
                             if (((w >> (16 * hh)) & 0xffffu) == HOLE) {
                                 while (cnt[bb] == 0) ++bb;
-                                const uint32_t v = (uint32_t)scratch[pos + cur[bb]++];
+                                const int src = scratch[pos + cur[bb]++];
+                                const uint32_t v = (uint32_t)(indices[pos + src] - base);
+                                if (WEIGHTED) hub_vals[2 * (wb + (int64_t)j * 32 + lane) + hh] = values[pos + src];
                                 --cnt[bb];
                                 w = (w & ~(0xffffu << (16 * hh))) | (v << (16 * hh));
                                 changed = true;
@@ -294,6 +307,7 @@ __global__ void hsell_fill_kernel(int64_t n, int64_t n_slices, const int32_t *__
                     if (q == w) tw = t[q]++;
                 const int64_t base = tail_round_base[(int64_t)w * n_slices + s] * 32;
                 tail_cols[base + (int64_t)tw * 32 + lane] = hsell_real_col(v, H, K, N, seg_len);
+                if (WEIGHTED) tail_vals[base + (int64_t)tw * 32 + lane] = values[i];
             }
         };
         int pos = b;
@@ -394,6 +408,27 @@ __device__ __forceinline__ void red_add(f64x2 *p, const f64x2 &v) {
     atomicAdd(reinterpret_cast<double *>(p) + 1, v.v.y);
 }
 
+// the two values of a weighted hub word (halves 0 and 1) as one streaming load
+__device__ __forceinline__ void ld_pair(const float *p, float &a, float &b) {
+    const float2 v = __ldcs(reinterpret_cast<const float2 *>(p));
+    a = v.x;
+    b = v.y;
+}
+__device__ __forceinline__ void ld_pair(const double *p, double &a, double &b) {
+    const double2 v = __ldcs(reinterpret_cast<const double2 *>(p));
+    a = v.x;
+    b = v.y;
+}
+template <typename T>
+__device__ __forceinline__ void ld_pair(const T *p, T &a, T &b) {   // panel elements: weighted forms are not built
+    a = ld_ro(p);
+    b = ld_ro(p + 1);
+}
+__device__ __forceinline__ float ld_val(const float *p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_val(const double *p) { return __ldcs(p); }
+template <typename T>
+__device__ __forceinline__ T ld_val(const T *p) { return ld_ro(p); }
+
 struct GatherParams {
     pgb_hsell h;
     const void *z;
@@ -427,42 +462,61 @@ static_assert(CH == 32 && CH % BATCH == 0, "the end mask of a chunk is one 32-bi
 // registers a 1024-thread CTA leaves each thread
 template <typename T> struct BatchOf { static constexpr int value = sizeof(T) > 8 ? 4 : BATCH; };
 
-// One chunk of the hub stream: 32 rounds, two shared-memory gathers per lane and round.
-template <typename T, bool ACCUM, bool DROP>
-__device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, int64_t chunk, uint32_t p_first,
-                                          uint32_t endmask, const int32_t *__restrict__ piece_row, const T *s_z,
-                                          T *__restrict__ partials, int lane, const DropParams &D) {
+// One chunk of the hub stream: 32 rounds, two shared-memory gathers per lane and round.  WEIGHTED: every entry is
+// multiplied by its edge value (one 8- / 16-byte load per lane and round next to the index word; 4 rounds in flight
+// instead of 8 to stay inside the 64 registers of a 1024-thread CTA).
+template <typename T, bool ACCUM, bool DROP, bool WEIGHTED>
+__device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, const T *__restrict__ vals, int64_t chunk,
+                                          uint32_t p_first, uint32_t endmask, const int32_t *__restrict__ piece_row,
+                                          const T *s_z, T *__restrict__ partials, int lane, const DropParams &D) {
+    constexpr int HB = WEIGHTED ? 4 : BATCH;
     const T dscale = DROP ? (T)D.scale : (T)1;
     const uint64_t slot0 = ((uint64_t)chunk * (CH * 32) + (uint64_t)lane) * 2;   // + round * 64 + half
     const uint32_t *d = words + chunk * (CH * 32) + lane;
+    const T *dv = WEIGHTED ? vals + 2 * (chunk * (CH * 32) + lane) : nullptr;      // + round * 64
     endmask |= 0x80000000u;   // the chunk end closes the last piece
     // a chunk has at most 32 pieces: lane j fetches the partial row of piece j
     const int my_row = (lane < __popc(endmask)) ? __ldg(piece_row + p_first + lane) : 0;
-    uint32_t w[BATCH], nx[BATCH];
+    uint32_t w[HB], nx[HB];
+    T v0[WEIGHTED ? HB : 1], v1[WEIGHTED ? HB : 1], n0[WEIGHTED ? HB : 1], n1[WEIGHTED ? HB : 1];
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) w[u] = ld_stream_u32(d + u * 32);
+    for (int u = 0; u < HB; ++u) {
+        w[u] = ld_stream_u32(d + u * 32);
+        if (WEIGHTED) ld_pair(dv + u * 64, v0[u], v1[u]);
+    }
     T a0 = (T)0, a1 = (T)0;
     int p = 0;
 #pragma unroll
-    for (int bt = 0; bt < CH / BATCH; ++bt) {
-        if (bt + 1 < CH / BATCH) {
+    for (int bt = 0; bt < CH / HB; ++bt) {
+        if (bt + 1 < CH / HB) {
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) nx[u] = ld_stream_u32(d + ((bt + 1) * BATCH + u) * 32);
+            for (int u = 0; u < HB; ++u) {
+                nx[u] = ld_stream_u32(d + ((bt + 1) * HB + u) * 32);
+                if (WEIGHTED) ld_pair(dv + ((bt + 1) * HB + u) * 64, n0[u], n1[u]);
+            }
         }
-        const uint32_t m8 = (endmask >> (bt * BATCH)) & 0xffu;
+        const uint32_t m8 = (endmask >> (bt * HB)) & ((1u << HB) - 1u);
         if (m8 == 0u) {
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const uint64_t sl = slot0 + (uint64_t)(bt * BATCH + u) * 64;
-                const T x0 = s_z[w[u] & 0xffffu], x1 = s_z[w[u] >> 16];
+            for (int u = 0; u < HB; ++u) {
+                const uint64_t sl = slot0 + (uint64_t)(bt * HB + u) * 64;
+                T x0 = s_z[w[u] & 0xffffu], x1 = s_z[w[u] >> 16];
+                if (WEIGHTED) {
+                    x0 = x0 * v0[u];
+                    x1 = x1 * v1[u];
+                }
                 a0 += kept<DROP>(D, sl) ? x0 : (T)0;
                 a1 += kept<DROP>(D, sl + 1) ? x1 : (T)0;
             }
         } else {
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const uint64_t sl = slot0 + (uint64_t)(bt * BATCH + u) * 64;
-                const T x0 = s_z[w[u] & 0xffffu], x1 = s_z[w[u] >> 16];
+            for (int u = 0; u < HB; ++u) {
+                const uint64_t sl = slot0 + (uint64_t)(bt * HB + u) * 64;
+                T x0 = s_z[w[u] & 0xffffu], x1 = s_z[w[u] >> 16];
+                if (WEIGHTED) {
+                    x0 = x0 * v0[u];
+                    x1 = x1 * v1[u];
+                }
                 a0 += kept<DROP>(D, sl) ? x0 : (T)0;
                 a1 += kept<DROP>(D, sl + 1) ? x1 : (T)0;
                 if ((m8 >> u) & 1u) {
@@ -473,7 +527,13 @@ __device__ __forceinline__ void hub_chunk(const uint32_t *__restrict__ words, in
             }
         }
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) w[u] = nx[u];
+        for (int u = 0; u < HB; ++u) {
+            w[u] = nx[u];
+            if (WEIGHTED) {
+                v0[u] = n0[u];
+                v1[u] = n1[u];
+            }
+        }
     }
 }
 
@@ -495,12 +555,12 @@ __device__ __forceinline__ f64x2 tex_fetch(cudaTextureObject_t t, int c, const f
 }
 
 // One chunk of the tail stream: 32 rounds, one L2 gather per lane and round (padding lanes are off).
-template <typename T, bool TEX, bool ACCUM, bool DROP>
-__device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int64_t chunk, uint32_t p_first,
-                                           uint32_t endmask, const int32_t *__restrict__ piece_row,
+template <typename T, bool TEX, bool ACCUM, bool DROP, bool WEIGHTED>
+__device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, const T *__restrict__ vals, int64_t chunk,
+                                           uint32_t p_first, uint32_t endmask, const int32_t *__restrict__ piece_row,
                                            const T *__restrict__ z, cudaTextureObject_t ztex,
                                            T *__restrict__ partials, int lane, const DropParams &D) {
-    constexpr int B = BatchOf<T>::value;
+    constexpr int B = (WEIGHTED && sizeof(T) == 8) ? 4 : BatchOf<T>::value;
     const T dscale = DROP ? (T)D.scale : (T)1;
     const uint64_t tslot0 = (1ull << 62) + (uint64_t)chunk * (CH * 32) + (uint64_t)lane;   // + round * 32
     const int32_t *d = cols + chunk * (CH * 32) + lane;
@@ -521,6 +581,7 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
                 x[u] = on ? tex_fetch(ztex, c[u], T()) : (T)0;
             else
                 x[u] = on ? ld_ro(z + c[u]) : (T)0;
+            if (WEIGHTED) x[u] = x[u] * ld_val(vals + chunk * (CH * 32) + lane + (bt * B + u) * 32);   // padding: 0 * 0
         }
         if (bt + 1 < CH / B) {
 #pragma unroll
@@ -549,7 +610,7 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, int
     }
 }
 
-template <typename T, bool TEX, bool ACCUM, bool DROP>
+template <typename T, bool TEX, bool ACCUM, bool DROP, bool WEIGHTED = false>
 __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const GatherParams G) {
     extern __shared__ __align__(16) unsigned char hs_smem[];
     T *s_z = reinterpret_cast<T *>(hs_smem);   // [block_cols + 1]; the last entry is the padding target (0)
@@ -579,7 +640,8 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
         const int u1 = (u0 + TB < tail_hi) ? u0 + TB : tail_hi;
         for (int u = u0; u < u1; ++u) {
             const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.tail_chunks) + u);
-            tail_chunk<T, TEX, ACCUM, DROP>(h.tail_cols, u, d.x, d.y, piece_dst, z, G.ztex, partials, lane, G.drop);
+            tail_chunk<T, TEX, ACCUM, DROP, WEIGHTED>(h.tail_cols, (const T *)h.tail_vals, u, d.x, d.y, piece_dst, z, G.ztex,
+                                                      partials, lane, G.drop);
         }
     };
 
@@ -638,7 +700,8 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
             if (kind == 1) {
                 if (!(G.debug_skip & 1)) {
                     const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.hub_chunks) + u);
-                    hub_chunk<T, ACCUM, DROP>(h.hub_words, u, d.x, d.y, piece_dst, s_z, partials, lane, G.drop);
+                    hub_chunk<T, ACCUM, DROP, WEIGHTED>(h.hub_words, (const T *)h.hub_vals, u, d.x, d.y, piece_dst, s_z,
+                                                        partials, lane, G.drop);
                 }
             } else {
                 run_tail(u);
@@ -1116,16 +1179,16 @@ static double g_drop_p = 0.0;
 static uint64_t g_drop_seed = 0;
 static uint64_t g_drop_launch = 0;   // gather launches since pgb_hsell_set_dropout: every launch draws a new mask
 
-template <typename T, bool TEX, bool ACCUM, bool DROP>
+template <typename T, bool TEX, bool ACCUM, bool DROP, bool WEIGHTED = false>
 static int launch_gather_variant(const GatherParams &G, int n_ctas, size_t smem, cudaStream_t st) {
     static PerDeviceInt configured_on;
     int &configured = configured_on.here();
     if (!configured) {
-        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, TEX, ACCUM, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         HS_SMEM_LIMIT - 64));
+        PGB_CUDA_OK(cudaFuncSetAttribute(hsell_gather_kernel<T, TEX, ACCUM, DROP, WEIGHTED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM_LIMIT - 64));
         configured = 1;
     }
-    hsell_gather_kernel<T, TEX, ACCUM, DROP><<<n_ctas, HS_THREADS, smem, st>>>(G);
+    hsell_gather_kernel<T, TEX, ACCUM, DROP, WEIGHTED><<<n_ctas, HS_THREADS, smem, st>>>(G);
     PGB_LAUNCH_OK("hsell_gather_kernel");
     return 0;
 }
@@ -1177,6 +1240,12 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool
         return G.ztex ? launch_gather_variant<T, true, true, false>(G, n, smem, st)
                       : launch_gather_variant<T, false, true, false>(G, n, smem, st);
     } else {
+        if (h->hub_vals || h->tail_vals) {   // weighted form: accumulate mode, no in-kernel dropout
+            if (!h->hub_vals || !h->tail_vals) return fail("hsell: a weighted form needs both hub_vals and tail_vals");
+            if (!accum || drop) return fail("hsell: weighted forms run in accumulate mode without in-kernel dropout");
+            return G.ztex ? launch_gather_variant<T, true, true, false, true>(G, n, smem, st)
+                          : launch_gather_variant<T, false, true, false, true>(G, n, smem, st);
+        }
         const int sel = (G.ztex ? 4 : 0) | (accum ? 2 : 0) | (drop ? 1 : 0);
         switch (sel) {
             case 0: return launch_gather_variant<T, false, false, false>(G, n, smem, st);
@@ -1620,19 +1689,29 @@ int pgb_hsell_fill(int64_t n, const int32_t *indptr, const int32_t *indices, int
                    const int64_t *hub_round_base, const int64_t *hub_part_base, const int64_t *tail_round_base,
                    const int64_t *tail_part_base, const int32_t *slice_ptr, uint32_t *hub_words, int32_t *tail_cols,
                    int32_t *piece_row, int32_t *scratch, int32_t banks, int32_t n_windows, int64_t window_len,
-                   void *stream) {
+                   int dtype, const void *values, void *hub_vals, void *tail_vals, void *stream) {
     if (n <= 0) return 0;
     if (scratch && (banks < 1 || banks > 32 || (banks & (banks - 1)))) return fail("pgb_hsell_fill: banks must be a power of two <= 32");
     if (scratch && block_cols >= 0xffff) return fail("pgb_hsell_fill: bank-aware ordering needs block_cols < 65535");
     if (n_segments < 1 || block_cols % n_segments) return fail("pgb_hsell_fill: block_cols must be a multiple of n_segments");
     if (n_windows < 1 || n_windows > HS_MAX_WINDOWS || (n_windows > 1 && window_len < 1))
         return fail("pgb_hsell_fill: n_windows must be in 1..%d with a positive window_len", HS_MAX_WINDOWS);
+    if (values && (!hub_vals || !tail_vals)) return fail("pgb_hsell_fill: a weighted form needs hub_vals and tail_vals");
+    if (values && dtype != PGB_F32 && dtype != PGB_F64) return fail("pgb_hsell_fill: unknown dtype %d", dtype);
     const int64_t n_slices = ceil_div(n, 32);
     const int grid = stride_grid(n_slices * 32 * ((n_blocks + FILL_GROUP - 1) / FILL_GROUP + 1), 256);
-    hsell_fill_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, n_slices, indptr, indices, block_cols, n_blocks, n_segments,
-                                                           seg_len, hub_rounds, tail_rounds, hub_round_base, hub_part_base,
-                                                           tail_round_base, tail_part_base, slice_ptr, hub_words,
-                                                           tail_cols, piece_row, scratch, banks, n_windows, window_len);
+    cudaStream_t st = as_stream(stream);
+#define PGB_FILL_ARGS(VT)                                                                                           \
+    n, n_slices, indptr, indices, (const VT *)values, (VT *)hub_vals, (VT *)tail_vals, block_cols, n_blocks,       \
+        n_segments, seg_len, hub_rounds, tail_rounds, hub_round_base, hub_part_base, tail_round_base,              \
+        tail_part_base, slice_ptr, hub_words, tail_cols, piece_row, scratch, banks, n_windows, window_len
+    if (!values)
+        hsell_fill_kernel<float, false><<<grid, 256, 0, st>>>(PGB_FILL_ARGS(float));
+    else if (dtype == PGB_F32)
+        hsell_fill_kernel<float, true><<<grid, 256, 0, st>>>(PGB_FILL_ARGS(float));
+    else
+        hsell_fill_kernel<double, true><<<grid, 256, 0, st>>>(PGB_FILL_ARGS(double));
+#undef PGB_FILL_ARGS
     PGB_LAUNCH_OK("hsell_fill_kernel");
     return 0;
 }

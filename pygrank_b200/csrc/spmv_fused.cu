@@ -371,7 +371,8 @@ template <int MODE>
 static int dispatch(const StepParams &P, int dtype, bool symdeg, cudaStream_t st) {
     const bool weighted = P.values != nullptr;
     if (P.hsell && g_kernel_variant >= 4) {
-        if (weighted) return fail("the hsell form is for unweighted graphs");
+        if (weighted != (P.hsell->hub_vals != nullptr))
+            return fail("the hsell form and the graph disagree about edge values (weighted graph: build the form with values)");
         return hsell_step<MODE>(P, P.hsell, P.partials, dtype, symdeg, st);
     }
     if (dtype == PGB_F32) {

@@ -99,6 +99,8 @@ def hsell_config() -> dict:
         # 1: pieces are RED.ADDed into one accumulator row per slice and the update pass streams it (fast path);
         # 0: partial rows added in a fixed order (bit-reproducible runs; PGB_DETERMINISTIC=1 selects it too)
         "accumulate": _env_int("PGB_HSELL_ACCUM", 1) != 0 and _env_int("PGB_DETERMINISTIC", 0) == 0,
+        # weighted graphs on the hub-blocked form (edge values next to the indices); 0: item-stream kernels
+        "weighted": _env_int("PGB_HSELL_WEIGHTED", 1) != 0,
     }
 
 
@@ -277,7 +279,7 @@ class HsellForm:
     """Device arrays of one pgb_hsell (kept alive here; the C struct holds raw pointers)."""
 
     def __init__(self, view: "CsrView", dtype: Optional[torch.dtype], n_segments: int = 1, seg_len: Optional[int] = None,
-                 cfg: Optional[dict] = None, elem_bytes: Optional[int] = None):
+                 cfg: Optional[dict] = None, elem_bytes: Optional[int] = None, values: Optional[torch.Tensor] = None):
         lib = C.lib()
         cfg = dict(hsell_config(), **(cfg or {}))
         st = C.stream_ptr()
@@ -325,11 +327,20 @@ class HsellForm:
         self.tail_cols = torch.full((max(n_tail_words, 1),), -1, dtype=torch.int32, device=dev)
         self.piece_row = torch.full((max(n_pieces, 1),), lay["dump_row"], dtype=torch.int32, device=dev)
         scratch = torch.empty(max(view.nnz, 1), dtype=torch.int32, device=dev) if cfg["bank_order"] else None
+        # weighted graphs: the edge values travel next to the indices (zero in padding slots)
+        self.hub_vals = self.tail_vals = None
+        if values is not None:
+            if values.dtype != dtype or values.numel() != view.nnz:
+                raise Exception("hsell: edge values must have the form's dtype and one entry per stored edge")
+            self.hub_vals = torch.zeros(max(2 * n_hub_words, 1), dtype=dtype, device=dev)
+            self.tail_vals = torch.zeros(max(n_tail_words, 1), dtype=dtype, device=dev)
         C.check(lib.pgb_hsell_fill(n, C.ptr(view.indptr), C.ptr(view.indices), H, K, n_segments, seg_len,
                                    C.ptr(hub_rounds), C.ptr(tail_rounds), C.ptr(hub_g0), C.ptr(hub_p0),
                                    C.ptr(tail_g0), C.ptr(tail_p0), C.ptr(self.slice_ptr), C.ptr(self.hub_words),
                                    C.ptr(self.tail_cols), C.ptr(self.piece_row), C.ptr(scratch),
-                                   128 // eb, W, window_len, st))      # shared-memory banks per element
+                                   128 // eb, W, window_len,             # shared-memory banks per element
+                                   dtype_code(dtype) if values is not None else C.PGB_F32, C.ptr(values),
+                                   C.ptr(self.hub_vals), C.ptr(self.tail_vals), st))
         del scratch
         # slice of every piece (accumulate mode): first-level rows are slice-major, padding pieces -> row n_slices
         ps = torch.searchsorted(lay["slice_ptr"].to(i64), self.piece_row.to(i64), right=True) - 1
@@ -361,12 +372,14 @@ class HsellForm:
                               C.ptr(self.hub_words), C.ptr(self.tail_cols), C.ptr(self.piece_row),
                               C.ptr(self.upd_rows), C.ptr(self.heavy_slices), C.ptr(self.reduce_items),
                               C.ptr(self.block_chunk_begin),
-                              C.ptr(self.cta_hub_begin), C.ptr(self.cta_tail_begin), C.ptr(self.piece_slice))
+                              C.ptr(self.cta_hub_begin), C.ptr(self.cta_tail_begin), C.ptr(self.piece_slice),
+                              C.ptr(self.hub_vals), C.ptr(self.tail_vals))
 
     def nbytes(self) -> int:
         return sum(int(t.numel()) * t.element_size() for t in (self.hub_chunks, self.tail_chunks, self.hub_words,
                                                                self.tail_cols, self.slice_ptr, self.piece_row,
-                                                               self.upd_rows))
+                                                               self.upd_rows, self.hub_vals, self.tail_vals)
+                   if t is not None)
 
 
 class CsrView:
@@ -388,15 +401,23 @@ class CsrView:
         self._istream = None
         self._vstream = {}
         self._hsell = {}
+        self.transient_values = False # with_values(): values replaced per call
         self.n_cols = self.n          # length of the gather vector (larger than n for a row-partitioned slice)
         self.hsell_segments = (1, None)
 
     def hsell(self, dtype: torch.dtype) -> Optional[HsellForm]:
-        """Hub-blocked sliced-ELL form for this dtype (unweighted graphs; None when disabled)."""
-        if self.weighted or self.nnz == 0 or not hsell_config()["enabled"]:
+        """Hub-blocked sliced-ELL form for this dtype (None when disabled).  Weighted graphs carry their edge values
+        in the form (accumulate mode, single-GPU views); views whose values change per call (``with_values``: the
+        plugin route's dropout masks) stay on the item stream — a form per call would cost more than it saves."""
+        cfg = hsell_config()
+        if self.nnz == 0 or not cfg["enabled"]:
+            return None
+        if self.weighted and (self.transient_values or not cfg["accumulate"] or not cfg["weighted"]
+                              or self.hsell_segments[0] != 1):
             return None
         if dtype not in self._hsell:
-            self._hsell[dtype] = HsellForm(self, dtype, self.hsell_segments[0], self.hsell_segments[1])
+            self._hsell[dtype] = HsellForm(self, dtype, self.hsell_segments[0], self.hsell_segments[1],
+                                           values=self.values(dtype) if self.weighted else None)
         return self._hsell[dtype]
 
     def hsell_panel(self) -> Optional[HsellForm]:
@@ -486,6 +507,7 @@ class CsrView:
         other._ws = None
         other._vstream = {}
         other._hsell = {}
+        other.transient_values = True
         return other
 
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), f"{name} declared in pgb200.h but not exported"
     assert sorted(_capi.EXPORTED_SYMBOLS) == declared, "ctypes signatures out of sync with the header"
     handle.pgb_abi_version.restype = ctypes.c_int
-    assert handle.pgb_abi_version() == _capi.ABI_VERSION == 3
+    assert handle.pgb_abi_version() == _capi.ABI_VERSION == 4
     handle.pgb_tile_items.restype = ctypes.c_int
     assert handle.pgb_tile_items() % 2 == 0 and (handle.pgb_tile_items() // 256) % 2 == 1   # odd items/thread
 

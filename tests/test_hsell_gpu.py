@@ -265,3 +265,73 @@ def test_in_kernel_graph_dropout(pgb, monkeypatch, shape):
     assert np.isfinite(out).all() and out.sum() > 0
     with pytest.raises(Exception, match="use_quotient"):
         pgb.PageRank(0.85)(g, p, graph_dropout=0.1)
+
+
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], SHAPES[3], SHAPES[5]])
+@pytest.mark.parametrize("normalization", ["symmetric", "col"])
+def test_weighted_hsell_equals_item_stream_kernel(pgb, monkeypatch, shape, normalization):
+    """Weighted graphs on the hub-blocked form (edge values next to the indices: pgb_hsell.hub_vals / tail_vals) against
+    the item-stream kernel (the round-1 path of every weighted graph): same conv, same PPR / heat-kernel iterates, on
+    forced small blocks (hub units cut into pieces, bank-ordered slots, a real tail, tail windows) and the default shape."""
+    import torch
+    from pygrank_b200 import _capi as C
+    from pygrank_b200 import device_synthetic
+    _set_shape(monkeypatch, shape)
+    scale = 15
+    n = 1 << scale
+    src, dst = device_synthetic.rmat_edges_device(scale, 16, seed=6)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    wts = torch.rand(src.numel(), dtype=torch.float64, device="cuda", generator=gen) * 4 + 0.25
+    g = pgb.DeviceGraph.from_edges(n, src, dst, weights=wts, directed=False, drop_self_loops=True,
+                                   normalization=normalization)
+    assert g.in_view.weighted
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen)
+    p = torch.zeros(n, dtype=torch.float64, device="cuda")
+    p[torch.randint(0, n, (10,), device="cuda", generator=gen)] = 1.0
+    lib = C.lib()
+    out = {}
+    try:
+        for variant in (4, 3):
+            C.check(lib.pgb_set_kernel_variant(variant))
+            res = {}
+            for dtype in (torch.float64, torch.float32):
+                a = pgb.PageRank(0.85, tol=1e-9, max_iters=1000, dtype=dtype)
+                h = pgb.HeatKernel(3, tol=1e-9, dtype=dtype)
+                res[dtype] = (g.conv(x.to(dtype)), a(g, p.to(dtype)).np, a.convergence.iteration,
+                              h(g, p.to(dtype)).np, h.convergence.iteration)
+            out[variant] = res
+    finally:
+        C.check(lib.pgb_set_kernel_variant(4))
+    form = g.in_view.hsell(torch.float64)
+    assert form is not None and form.hub_vals is not None and form.struct.hub_vals
+    if shape[0]:
+        assert form.n_tail_chunks > 0 and form.n_hub_chunks > 0
+    for dtype, tol, slack in ((torch.float64, 1e-13, 0), (torch.float32, 2e-6, 1)):
+        y4, r4, i4, h4, hi4 = out[4][dtype]
+        y3, r3, i3, h3, hi3 = out[3][dtype]
+        assert float((y4 - y3).abs().sum()) <= tol * float(y3.abs().sum())
+        assert abs(i4 - i3) <= slack and abs(hi4 - hi3) <= slack
+        assert float((r4 - r3).abs().sum()) <= 10 * tol * float(r3.abs().sum())
+        assert float((h4 - h3).abs().sum()) <= 10 * tol * float(h3.abs().sum())
+
+
+def test_weighted_forms_stay_off_transient_and_deterministic_views(pgb, monkeypatch):
+    """Views whose values change per call (the plugin route's dropout masks) and the deterministic mode keep weighted
+    graphs on the item stream; PGB_HSELL_WEIGHTED=0 switches the weighted forms off."""
+    import torch
+    from pygrank_b200 import device_synthetic
+    src, dst = device_synthetic.rmat_edges_device(12, 8, seed=1)
+    wts = torch.rand(src.numel(), dtype=torch.float64, device="cuda") + 0.5
+    g = pgb.DeviceGraph.from_edges(1 << 12, src, dst, weights=wts, normalization="symmetric")
+    view = g.in_view
+    assert view.hsell(torch.float32) is not None
+    assert view.with_values(view.values(torch.float64) * 2).hsell(torch.float32) is None
+    monkeypatch.setenv("PGB_HSELL_WEIGHTED", "0")
+    g2 = pgb.DeviceGraph.from_edges(1 << 12, src, dst, weights=wts, normalization="symmetric")
+    assert g2.in_view.hsell(torch.float32) is None
+    monkeypatch.delenv("PGB_HSELL_WEIGHTED")
+    monkeypatch.setenv("PGB_DETERMINISTIC", "1")
+    g3 = pgb.DeviceGraph.from_edges(1 << 12, src, dst, weights=wts, normalization="symmetric")
+    assert g3.in_view.hsell(torch.float32) is None
+    x = torch.rand(1 << 12, dtype=torch.float64, device="cuda")
+    assert torch.allclose(g3.conv(x), g.conv(x), rtol=1e-12, atol=0)
