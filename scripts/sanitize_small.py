@@ -52,7 +52,7 @@ for family in ("1", "csr"):          # hub-blocked panels (pgb_affine_steps_pane
         print("panel", family, dtype, tuple(out.shape), float(out.sum()))
 del os.environ["PGB_PANEL"]
 print("sweep", float(pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=torch.float32).sweep(g, p.float(), [0.5, 0.7, 0.9]).sum()))
-wts = torch.rand(g.nnz, dtype=torch.float64, device="cuda") + 0.5   # weighted graph on the hub-blocked form
+# weighted graph on the hub-blocked form (edge values in the form)
 src, dst = device_synthetic.rmat_edges_device(scale, 16, seed=5)
 gw = pgb.DeviceGraph.from_edges(n, src, dst, weights=torch.rand(src.numel(), dtype=torch.float64, device="cuda") + 0.5,
                                 normalization="symmetric")
