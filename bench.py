@@ -321,6 +321,53 @@ def plugin_leg(args, g, seeds, alpha, dtype, n_warm, total):
         return {"value": None, "error": repr(exc)[:300]}
 
 
+def propagate_leg(args, g, dtype, alpha, columns=32):
+    """NodeRanking.propagate (core/signals.py:225-226) of `columns` seed sets on the bench graph through the hub-blocked
+    panel path (pgb_affine_steps_panel: 4 fp32 / 2 fp64 columns per gather, columns scheduled over the panel's slots on the
+    device), checked column by column against single solves of the same engine."""
+    import torch
+
+    import pygrank_b200 as pgb
+    from pygrank_b200 import synthetic
+    try:
+        dev = g.out_view.indptr.device
+        n = g.n
+        P = torch.zeros((n, columns), dtype=dtype, device=dev)
+        for c, sset in enumerate(synthetic.seed_sets(n, columns, 10, seed=7)):
+            P[torch.from_numpy(sset).to(dev), c] = 1.0
+        alg = pgb.PageRank(alpha, tol=TOL, max_iters=MAX_ITERS, dtype=dtype)
+        alg.propagate(g, P[:, :8])
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t0 = time.perf_counter()
+        out = alg.propagate(g, P)
+        ev1.record()
+        torch.cuda.synchronize()
+        secs = max(ev0.elapsed_time(ev1) * 1e-3, time.perf_counter() - t0)
+        its = list(alg.convergence.iterations)
+        calls = sum(i - 1 for i in its)
+        one = pgb.PageRank(alpha, tol=TOL, max_iters=MAX_ITERS, dtype=dtype)
+        worst, its_off = 0.0, 0
+        t1 = time.perf_counter()
+        for c in range(columns):
+            ref = one(g, P[:, c].contiguous()).np
+            worst = max(worst, float((out[:, c] - ref).abs().sum(dtype=torch.float64) / ref.abs().sum(dtype=torch.float64)))
+            its_off = max(its_off, abs(one.convergence.iteration - its[c]))
+        torch.cuda.synchronize()
+        seq = time.perf_counter() - t1
+        tol = 1e-5 if dtype == torch.float32 else 1e-10
+        return {"columns": columns, "seconds": secs, "edge_column_gteps": g.nnz * calls / secs / 1e9,
+                "column_iterations_min_max": [min(its), max(its)],
+                "route": "pgb_affine_steps_panel (hub-blocked panel kernel, device-scheduled slots)"
+                         if alg._panel_family(g) == "hsell" else "item-stream panel kernel",
+                "column_by_column_seconds_incl_check": seq,
+                "parity": {"vs": "single solves of the same engine, every column", "worst_rel_l1": worst, "tol": tol,
+                           "iterations_max_abs_diff": its_off, "ok": bool(worst <= tol and its_off <= (1 if dtype == torch.float32 else 0))}}
+    except Exception as exc:   # reported, never fatal for the bench line
+        return {"edge_column_gteps": None, "error": repr(exc)[:300]}
+
+
 def run_single(args):
     import torch
 
@@ -407,6 +454,8 @@ def run_single(args):
 
     e2e_plugin = plugin_leg(args, g, seeds, alpha, dtype, min(args.warmup, 2), total) if not args.no_plugin else None
 
+    panel = propagate_leg(args, g, dtype, alpha) if not args.no_panel else None
+
     cpu = parity = None
     if not args.no_cpu:
         ref = CpuReference(CPU_SAMPLE_SCALE, alpha)
@@ -442,6 +491,7 @@ def run_single(args):
         "e2e": {"value": e2e_value, "unit": "GTEPS", "h2d_bytes_per_step": 10 * 8 + 10 * 8,
                 "d2h_bytes_per_step": n * w + 64 * 2},
         "e2e_plugin": e2e_plugin,
+        "propagate": panel,
         "gpu_launches": launches,
         "roofline": r_main,
         "value_" + oname: o_value, "roofline_" + oname: roof(kern_o, oname),
@@ -554,6 +604,7 @@ def main():
     ap.add_argument("--relabel", default="hub", choices=["hub", "degree", "none"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline + parity legs")
     ap.add_argument("--no-plugin", action="store_true", help="skip the e2e_plugin leg")
+    ap.add_argument("--no-panel", action="store_true", help="skip the propagate (panel kernel) leg")
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the pre-timing parity solves")
     ap.add_argument("--kernel-only", action="store_true",
                     help="experiments: time only the fused step (no solves, no e2e, no CPU leg) and print a short line")
