@@ -438,6 +438,7 @@ struct GatherParams {
     int tail_warps;
     int tail_batch;        // tail chunks taken per grab of the global queue
     int debug_skip;        // timing experiments only (PGB_HSELL_DEBUG_SKIP): 1 = skip hub chunks, 2 = skip tail chunks
+    int bulk;              // hub blocks arrive by cp.async.bulk (TMA unit) + mbarrier instead of LDG -> STS by every thread
     cudaTextureObject_t ztex;   // linear texture over z (TEX kernels): tail gathers go through the TEX pipe
     DropParams drop;            // DROP kernels: in-kernel graph_dropout
 };
@@ -610,11 +611,41 @@ __device__ __forceinline__ void tail_chunk(const int32_t *__restrict__ cols, con
     }
 }
 
+// Bulk copy of a hub block: one thread hands the 128 KB to the TMA unit (cp.async.bulk, SASS UBLKCP) and arms an
+// mbarrier with the byte count; warps that gather from the block wait on the barrier, warps with tail work do not —
+// the block load no longer occupies 1024 threads' LDG -> STS slots and overlaps the tail chunks.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_global, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
 template <typename T, bool TEX, bool ACCUM, bool DROP, bool WEIGHTED = false>
 __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const GatherParams G) {
     extern __shared__ __align__(16) unsigned char hs_smem[];
     T *s_z = reinterpret_cast<T *>(hs_smem);   // [block_cols + 1]; the last entry is the padding target (0)
     __shared__ int s_hub_next;
+    __shared__ __align__(8) uint64_t s_bar;    // completion of the bulk copy of the current hub block
 
     if (G.stop && *G.stop != PGB_RUNNING) return;
     const pgb_hsell &h = G.h;
@@ -632,7 +663,11 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
     const bool tail_pref = warp < G.tail_warps;
     const int H = h.block_cols, N = h.n_segments;
     const int Hs = H / N;
-    if (tid == 0) s_z[H] = (T)0;
+    if (tid == 0) {
+        s_z[H] = (T)0;
+        if (G.bulk) mbar_init(&s_bar, 1);
+    }
+    uint32_t bar_parity = 0;   // phase of s_bar the next bulk-loaded block completes (same in every thread)
 
     const int TB = G.tail_batch;
     auto run_tail = [&](int u0) {   // a grab of the global queue: TB consecutive tail chunks
@@ -653,15 +688,31 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
         const int blk_end = h.block_chunk_begin[blk + 1];
         const int seg_end = blk_end < hub_hi ? blk_end : hub_hi;
         __syncthreads();   // every warp is done with the previous block
+        // bulk path: every segment part 16-byte aligned on both sides and a multiple of 16 bytes long
+        constexpr int V = 16 / sizeof(T);
+        bool use_bulk = G.bulk != 0;
+        uint32_t bulk_bytes = 0;
+        for (int sgm = 0; sgm < N && use_bulk; ++sgm) {
+            const int64_t first = (int64_t)sgm * h.seg_len + (int64_t)blk * Hs;
+            int64_t avail = h.seg_len - (int64_t)blk * Hs;
+            const int cnt = (int)(avail < Hs ? (avail < 0 ? 0 : avail) : Hs);
+            if ((first % V) || ((sgm * Hs) % V) || (cnt % V) || (((uintptr_t)z) & 15u)) use_bulk = false;
+            bulk_bytes += (uint32_t)cnt * (uint32_t)sizeof(T);
+        }
+        if (bulk_bytes == 0) use_bulk = false;
+        if (use_bulk && tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of s_z before the async writes
+            mbar_expect_tx(&s_bar, bulk_bytes);
+        }
         for (int sgm = 0; sgm < N; ++sgm) {
             const int64_t first = (int64_t)sgm * h.seg_len + (int64_t)blk * Hs;
             int64_t avail = h.seg_len - (int64_t)blk * Hs;
             const int cnt = (int)(avail < Hs ? (avail < 0 ? 0 : avail) : Hs);
             T *dst = s_z + sgm * Hs;
             const T *src = z + first;
-            // vector part when both sides are 16-byte aligned, scalar otherwise
-            constexpr int V = 16 / sizeof(T);
-            if (((first % V) == 0) && (((sgm * Hs) % V) == 0)) {
+            if (use_bulk) {
+                if (tid == 0 && cnt > 0) bulk_g2s(dst, src, (uint32_t)cnt * (uint32_t)sizeof(T), &s_bar);
+            } else if (((first % V) == 0) && (((sgm * Hs) % V) == 0)) {   // vector part when both sides are 16-byte aligned
                 const int nv = cnt / V;
                 const float4 *s4 = reinterpret_cast<const float4 *>(src);
                 float4 *d4 = reinterpret_cast<float4 *>(dst);
@@ -672,6 +723,9 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
             }
             for (int i = cnt + tid; i < Hs; i += HS_THREADS) dst[i] = (T)0;
         }
+        bool block_ready = !use_bulk;   // bulk: the first hub chunk of every warp waits for the copy
+        const uint32_t wait_parity = bar_parity;
+        if (use_bulk) bar_parity ^= 1u;
         if (tid == 0) s_hub_next = cur;
         __syncthreads();
         // the id of the NEXT chunk is requested (lane 0) before the current one is processed, so the atomic's
@@ -698,6 +752,10 @@ __global__ void __launch_bounds__(HS_THREADS, 1) hsell_gather_kernel(const Gathe
             int nkind, nu;
             grab(nkind, nu);
             if (kind == 1) {
+                if (!block_ready) {
+                    mbar_wait(&s_bar, wait_parity);
+                    block_ready = true;
+                }
                 if (!(G.debug_skip & 1)) {
                     const uint2 d = __ldg(reinterpret_cast<const uint2 *>(h.hub_chunks) + u);
                     hub_chunk<T, ACCUM, DROP, WEIGHTED>(h.hub_words, (const T *)h.hub_vals, u, d.x, d.y, piece_dst, s_z,
@@ -1220,6 +1278,12 @@ static int launch_gather(const pgb_hsell *h, const void *z, void *partials, bool
         debug_skip = e ? atoi(e) : 0;
     }
     G.debug_skip = debug_skip;
+    static int bulk = -1;
+    if (bulk < 0) {
+        const char *e = getenv("PGB_HSELL_BULK");
+        bulk = e ? atoi(e) : 1;
+    }
+    G.bulk = bulk;
     static int tail_batch = -1;
     if (tail_batch < 0) {
         const char *e = getenv("PGB_HSELL_TAIL_BATCH");
