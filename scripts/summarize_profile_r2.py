@@ -92,7 +92,7 @@ lib = os.path.join(ROOT, "pygrank_b200", "lib", "libpgb200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 with open(os.path.join(OUT, f"sass_{tag}.md"), "w") as f:
     f.write(f"# SASS opcode histograms ({tag}): `cuobjdump -sass pygrank_b200/lib/libpgb200.so`, sm_100a\n\n")
-    for want in ("hsell_gather_kernelIfLb1ELb1E", "hsell_update_accum_kernelIfLi1ELb1E"):
+    for want in ("hsell_gather_kernelIfLb1ELb1ELb0ELb0E", "hsell_gather_kernelINS_5f32x4ELb1ELb1ELb0ELb0E", "hsell_gather_kernelIfLb1ELb1ELb0ELb1E", "hsell_update_accum_kernelIfLi1ELb1E", "hsell_update_panel_kernelIfLi4ELb1E"):
         m = re.search(r"Function : (\S*" + want + r"\S*)(.*?)(?=Function : |\Z)", sass, re.S)
         if not m:
             continue
@@ -102,7 +102,7 @@ with open(os.path.join(OUT, f"sass_{tag}.md"), "w") as f:
             fam[op.split(".")[0]] += c
         f.write(f"## `{m.group(1)[:100]}`\n\n{sum(ops.values())} instructions.  Memory / special opcodes in full, the rest by family.\n\n| opcode | count |\n|---|---:|\n")
         for op, c in sorted(ops.items(), key=lambda kv: -kv[1]):
-            if re.match(r"(LD|ST|TLD|TEX|RED|ATOM|SHFL|BAR|UBLK|UTMA|CCTL|MEMBAR|LDS|STS|LDSM|ERRBAR)", op):
+            if re.match(r"(LD|ST|TLD|TEX|RED|ATOM|SHFL|BAR|UBLK|UTMA|SYNCS|FENCE|CCTL|MEMBAR|LDS|STS|LDSM|ERRBAR)", op):
                 f.write(f"| `{op}` | {c} |\n")
         f.write("\n| family | count |\n|---|---:|\n")
         for op, c in fam.most_common(14):
