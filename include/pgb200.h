@@ -366,6 +366,11 @@ typedef struct {
     double *plan_norm;        /* [PB] scratch                                                                    */
     int32_t *col_result;      /* [n_cols][4]: iteration, stop reason, steps, norm > 0                            */
     double *col_err;          /* [n_cols][hist_stride] error histories (entries 1..steps) or NULL                */
+    /* polynomial (closed-form) filters, ClosedFormGraphFilter._step (abstract_filters.py:225-256): every slot accumulates
+     * ranks[:, slot] += coef_table[k] * power_k (k = the slot's own step) while its power advances, and leaves with ranks */
+    int32_t poly, reserved0;  /* 0: affine recursion; 1: polynomial accumulation (quotient must be 0)            */
+    void *ranks;              /* poly: [n][PB] accumulated results (any content: a loaded slot starts from 0)   */
+    const double *coef_table; /* poly: device table, coefficient of step k at coef_table[k], k = 1..max_iters    */
 } pgb_panel_job;
 
 /* Enqueues `num_launches` steps (step k reads buf[(k-1)&1], writes buf[k&1], k = first_step..).  z, q are [n][PB]

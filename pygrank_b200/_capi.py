@@ -44,7 +44,8 @@ class PanelJob(Structure):
                 ("alpha_s", c_double), ("coef", c_double), ("tol", c_double), ("mean", c_double),
                 ("max_iters", c_int32), ("end_modulo", c_int32), ("err_mode", c_int32), ("quotient", c_int32),
                 ("preserve_norm", c_int32), ("sched", c_void_p), ("slot_col", c_void_p), ("slot_plan", c_void_p),
-                ("plan_norm", c_void_p), ("col_result", c_void_p), ("col_err", c_void_p)]
+                ("plan_norm", c_void_p), ("col_result", c_void_p), ("col_err", c_void_p), ("poly", c_int32),
+                ("reserved0", c_int32), ("ranks", c_void_p), ("coef_table", c_void_p)]
 
 
 class Hsell(Structure):

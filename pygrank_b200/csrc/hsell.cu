@@ -995,9 +995,23 @@ struct PanelStep {
     double *err_hist;        // [PB][hist_stride]
     int32_t hist_stride;
     uint32_t *tail_queue;
+    void *ranks;             // MODE_POLY: accumulated results [n][PB]
+    const double *coef;      // MODE_POLY: coefficient of step k at coef[k]
 };
 
 template <typename S, int PB> struct alignas(16) Pack { S v[PB]; };
+__device__ __forceinline__ Pack<float, 4> ld_pack_rw(const float *p) {
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    Pack<float, 4> r;
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    return r;
+}
+__device__ __forceinline__ Pack<double, 2> ld_pack_rw(const double *p) {
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    Pack<double, 2> r;
+    r.v[0] = t.x; r.v[1] = t.y;
+    return r;
+}
 __device__ __forceinline__ Pack<float, 4> ld_pack(const float *p) {
     const float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
     Pack<float, 4> r;
@@ -1019,7 +1033,7 @@ __device__ __forceinline__ void st_pack(double *p, const Pack<double, 2> &r) {
 
 constexpr int UPP_BLOCK = 256;
 constexpr int UPP_ROWS = 2;
-template <typename S, int PB, bool SYMDEG>
+template <typename S, int PB, bool SYMDEG, int MODE>
 __global__ void __launch_bounds__(UPP_BLOCK) hsell_update_panel_kernel(const PanelStep P) {
     __shared__ double s_red[2][UPP_BLOCK / 32][PB];
     __shared__ int s_last;
@@ -1037,6 +1051,11 @@ __global__ void __launch_bounds__(UPP_BLOCK) hsell_update_panel_kernel(const Pan
         any = any || active[c];
     }
     if (!any) return;   // run-ahead launch after every column has stopped
+    S coef[PB];         // MODE_POLY: every column is at its own step of the coefficient table
+#pragma unroll
+    for (int c = 0; c < PB; ++c)
+        coef[c] = (MODE == MODE_POLY && active[c]) ? (S)P.coef[P.si[c * PGB_STATE_I32_LEN + PGB_SI_STEPS] + 1] : (S)0;
+    S *__restrict__ ranks = (S *)P.ranks;
     const bool is_max = err_mode == PGB_ERR_MAX;
     double err[PB], tsum[PB];
 #pragma unroll
@@ -1059,8 +1078,12 @@ __global__ void __launch_bounds__(UPP_BLOCK) hsell_update_panel_kernel(const Pan
             if (row < n) {
                 acc[k] = ld_pack(y + row * PB);
                 zi[k] = ld_pack(zin + row * PB);
-                qi[k] = ld_pack(qv + row * PB);
-                ci[k] = ld_stream((const S *)P.c + row);
+                if (MODE == MODE_AFFINE) {
+                    qi[k] = ld_pack(qv + row * PB);
+                    ci[k] = ld_stream((const S *)P.c + row);
+                } else {
+                    qi[k] = ld_pack_rw(ranks + row * PB);   // the accumulated result (read-modify-write)
+                }
                 if (SYMDEG) {
                     ip0[k] = P.indptr[row];
                     ip1[k] = P.indptr[row + 1];
@@ -1082,12 +1105,15 @@ __global__ void __launch_bounds__(UPP_BLOCK) hsell_update_panel_kernel(const Pan
                     wi[k] = deg > 0 ? RowMath<S>::inv((S)deg) : (S)0;
                     sqi[k] = deg > 0 ? RowMath<S>::root((S)deg) : (S)1;
                 }
-                Pack<S, PB> zn, zero;
+                Pack<S, PB> zn, zero, rk;
+                bool rk_dirty = false;
 #pragma unroll
                 for (int c = 0; c < PB; ++c) {
                     zero.v[c] = (S)0;
                     zn.v[c] = zi[k].v[c];
-                    if (active[c]) {
+                    rk.v[c] = qi[k].v[c];
+                    if (!active[c]) continue;
+                    if (MODE == MODE_AFFINE) {
                         const S znew = (alpha[c] * wi[k] * acc[k].v[c] + qi[k].v[c]) * invS[c];
                         zn.v[c] = znew;
                         S d = znew - zi[k].v[c];
@@ -1097,10 +1123,26 @@ __global__ void __launch_bounds__(UPP_BLOCK) hsell_update_panel_kernel(const Pan
                         else
                             berr[c] += (err_mode == PGB_ERR_MSQ) ? d * d : d;
                         bt[c] += znew * ci[k];
+                    } else {   // ClosedFormGraphFilter._step (abstract_filters.py:225-228, 248-256), as RowUpdate MODE_POLY
+                        const S pw = sqi[k] * zi[k].v[c];
+                        if (coef[c] != (S)0) {
+                            const S prev = qi[k].v[c];
+                            const S cur = prev + pw * coef[c];
+                            rk.v[c] = cur;
+                            rk_dirty = true;
+                            S d = (sizeof(S) == 8) ? prev - cur : coef[c] * pw;
+                            d = d < (S)0 ? -d : d;
+                            if (is_max)
+                                berr[c] = berr[c] > d ? berr[c] : d;
+                            else
+                                berr[c] += (err_mode == PGB_ERR_MSQ) ? d * d : d;
+                        }
+                        zn.v[c] = wi[k] * acc[k].v[c];
                     }
                 }
                 st_pack(y + row * PB, zero);
                 st_pack(zout + row * PB, zn);
+                if (MODE == MODE_POLY && rk_dirty) st_pack(ranks + row * PB, rk);
             }
         }
 #pragma unroll
@@ -1377,8 +1419,10 @@ __global__ void panel_plan_kernel(const pgb_panel_job J, double *sf, int32_t *si
 }
 
 template <typename S, int PB>
-__global__ void __launch_bounds__(256) panel_move_kernel(const pgb_panel_job J, int64_t n, const S *__restrict__ cur,
+__global__ void __launch_bounds__(256) panel_move_kernel(const pgb_panel_job J, int64_t n, const S *__restrict__ cur_z,
                                                          const S *__restrict__ sq, double *sf) {
+    // what a finished column leaves with: its iterate z * sq (affine recursion) or its accumulated result (polynomial)
+    const S *__restrict__ cur = J.poly ? (const S *)J.ranks : cur_z;
     __shared__ double scratch[32];
     int harvest[PB], load[PB];
     bool any = false;
@@ -1403,8 +1447,8 @@ __global__ void __launch_bounds__(256) panel_move_kernel(const pgb_panel_job J, 
 #pragma unroll
         for (int s = 0; s < PB; ++s) out_any = out_any || harvest[s] >= 0;
         if (out_any) {
-            const Pack<S, PB> z = ld_pack(cur + i * PB);
-            const S sqi = sq[i];
+            const Pack<S, PB> z = ld_pack_rw(cur + i * PB);
+            const S sqi = J.poly ? (S)1 : sq[i];
 #pragma unroll
             for (int s = 0; s < PB; ++s)
                 if (harvest[s] >= 0) {
@@ -1449,7 +1493,7 @@ __global__ void __launch_bounds__(256) panel_load_kernel(const pgb_panel_job J, 
     }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t user = J.perm ? (int64_t)J.perm[i] : i;
-        const S sqi = sq[i], ci = c[i];
+        const S sqi = sq[i], ci = J.poly ? (S)0 : c[i];
         const double cv = coefvec ? (double)coefvec[i] : 0.0;
 #pragma unroll
         for (int s = 0; s < PB; ++s)
@@ -1458,12 +1502,17 @@ __global__ void __launch_bounds__(256) panel_load_kernel(const pgb_panel_job J, 
                 if (norm[s] > 0.0) {                                     // abstract_filters.py:53-55
                     const S pn = (S)((double)cols[user * J.row_stride + load[s] * J.col_stride] / norm[s]);
                     zi = pn / sqi;
-                    qi = (S)((coefvec ? cv : coef[s]) * (double)pn) / sqi;
-                    tacc[s] += (double)zi * (double)ci;
-                    bacc[s] += (double)qi * (double)sqi;
+                    if (!J.poly) {
+                        qi = (S)((coefvec ? cv : coef[s]) * (double)pn) / sqi;
+                        tacc[s] += (double)zi * (double)ci;
+                        bacc[s] += (double)qi * (double)sqi;
+                    }
                 }
                 cur[i * PB + s] = zi;
-                q[i * PB + s] = qi;
+                if (J.poly)
+                    ((S *)J.ranks)[i * PB + s] = (S)0;                   // abstract_filters.py:213
+                else
+                    q[i * PB + s] = qi;
             }
     }
 #pragma unroll
@@ -1526,10 +1575,11 @@ static int panel_steps(const pgb_hsell *h, const PanelStep &P0, const pgb_panel_
     if (ctas == 0) {
         int v = 0;
         const cudaError_t e = symdeg
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_panel_kernel<S, PB, true>, UPP_BLOCK, 0)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_panel_kernel<S, PB, false>, UPP_BLOCK, 0);
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_panel_kernel<S, PB, true, MODE_AFFINE>, UPP_BLOCK, 0)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, hsell_update_panel_kernel<S, PB, false, MODE_AFFINE>, UPP_BLOCK, 0);
         ctas = (e == cudaSuccess && v >= 1) ? v : 4;
     }
+    const bool poly = J.poly != 0;
     int64_t want = ceil_div(P.n, (int64_t)UPP_BLOCK * UPP_ROWS);
     const int64_t cap = (int64_t)sm_count() * ctas;
     if (want > cap) want = cap;
@@ -1547,10 +1597,14 @@ static int panel_steps(const pgb_hsell *h, const PanelStep &P0, const pgb_panel_
         panel_finish_kernel<PB><<<1, 32, 0, st>>>(J, P.sf, P.si);
         PGB_LAUNCH_OK("panel scheduling kernels");
         if (launch_gather<V>(h, P.zin, P.y, true, stop, P.tail_queue, k, st)) return 1;
-        if (symdeg)
-            hsell_update_panel_kernel<S, PB, true><<<(int)want, UPP_BLOCK, 0, st>>>(P);
+        if (symdeg && !poly)
+            hsell_update_panel_kernel<S, PB, true, MODE_AFFINE><<<(int)want, UPP_BLOCK, 0, st>>>(P);
+        else if (!poly)
+            hsell_update_panel_kernel<S, PB, false, MODE_AFFINE><<<(int)want, UPP_BLOCK, 0, st>>>(P);
+        else if (symdeg)
+            hsell_update_panel_kernel<S, PB, true, MODE_POLY><<<(int)want, UPP_BLOCK, 0, st>>>(P);
         else
-            hsell_update_panel_kernel<S, PB, false><<<(int)want, UPP_BLOCK, 0, st>>>(P);
+            hsell_update_panel_kernel<S, PB, false, MODE_POLY><<<(int)want, UPP_BLOCK, 0, st>>>(P);
         PGB_LAUNCH_OK("hsell_update_panel_kernel");
     }
     return 0;
@@ -1685,8 +1739,11 @@ int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype,
     if (!h->piece_slice) return fail("pgb_affine_steps_panel needs pgb_hsell.piece_slice");
     if (!w && !indptr) return fail("pgb_affine_steps_panel: degree-derived factors need the row pointers");
     if (first_step < 1) return fail("pgb_affine_steps_panel: first_step must be >= 1");
-    if (!yacc || !tail_queue || !q || !c || !state_f64 || !state_i32 || !err_hist)
-        return fail("pgb_affine_steps_panel: q, c, the state arrays, err_hist, yacc and tail_queue are required");
+    if (!yacc || !tail_queue || !state_f64 || !state_i32 || !err_hist)
+        return fail("pgb_affine_steps_panel: the state arrays, err_hist, yacc and tail_queue are required");
+    if (!job->poly && (!q || !c)) return fail("pgb_affine_steps_panel: the affine recursion needs q and c");
+    if (job->poly && (!job->ranks || !job->coef_table)) return fail("pgb_affine_steps_panel: a polynomial job needs ranks and coef_table");
+    if (job->poly && job->quotient) return fail("pgb_affine_steps_panel: polynomial filters have no quotient");
     if (!job->cols || !job->out || !job->sq || !job->sched || !job->slot_col || !job->slot_plan || !job->plan_norm ||
         !job->col_result)
         return fail("pgb_affine_steps_panel: incomplete job (cols, out, sq, sched, slot_col, slot_plan, plan_norm, col_result)");
@@ -1708,6 +1765,8 @@ int pgb_affine_steps_panel(const pgb_hsell *h, const int32_t *indptr, int dtype,
     P.err_hist = err_hist;
     P.hist_stride = job->hist_stride;
     P.tail_queue = tail_queue;
+    P.ranks = job->ranks;
+    P.coef = job->coef_table;
     const bool symdeg = (w == nullptr);
     if (dtype == PGB_F32)
         return panel_steps<float, f32x4, 4>(h, P, *job, zbuf0, zbuf1, first_step, num_launches, symdeg, as_stream(stream));

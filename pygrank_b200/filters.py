@@ -183,6 +183,171 @@ class GraphFilter:
     def _can_batch(self, g, *args, n_columns: int = 2, **kwargs) -> bool:
         return False
 
+    def _panel_family(self, g) -> Optional[str]:
+        """Which batched kernel propagate() uses: "hsell" = panels of 4 fp32 / 2 fp64 columns through the hub-blocked
+        form (pgb_affine_steps_panel: 16-byte shared-memory / texture gathers, the index streams read once per panel);
+        "csr" = panels of 8 / 4 columns through the item-stream kernel (pgb_affine_steps_batched); None = column by
+        column.  PGB_PANEL: 0 = never, csr = the item-stream panel, anything else = batch with the best family."""
+        import os
+        forced = os.environ.get("PGB_PANEL")
+        if forced == "0":
+            return None
+        if forced == "csr":
+            return "csr"
+        return "hsell" if g.in_view.hsell_panel() is not None else "csr"
+
+    def _propagate_panels(self, g: DeviceGraph, cols: torch.Tensor, poly_coefs=None, **kwargs) -> torch.Tensor:
+        """All feature columns through ``pgb_affine_steps_panel``: the panel's ``pgb_hsell_panel_width`` columns are
+        SLOTS scheduled on the device — a column enters a free slot (normalisation, scaled start vector, affine term,
+        state: abstract_filters.py:52-56), iterates with its own alpha, normaliser, error and stop decision, and is
+        written out when it stops while the others keep going, so no slot waits for the slowest column of a fixed group
+        and the host only polls the number of finished columns.  Results and iteration counts equal the reference's
+        column-by-column loop (signals.py:225-226).  ``poly_coefs`` (closed-form filters): the coefficient of step k at
+        index k — every slot accumulates ``ranks += coef[k] * power_k`` at its own step while its power advances
+        (abstract_filters.py:225-256) and leaves with the accumulated result."""
+        lib = C.lib()
+        dtype, code = self.dtype, dtype_code(self.dtype)
+        f64, i32 = torch.float64, torch.int32
+        dev, n = g.out_view.indptr.device, g.n
+        st = C.stream_ptr()
+        cm = self.convergence
+        B = int(cols.shape[1])
+        PB = lib.pgb_hsell_panel_width(code)
+        poly = poly_coefs is not None
+        if poly:
+            alpha, alpha_s, w_run, c_run, coef, coefvec, col_alphas, quotient = 1.0, 1.0, None, None, 0.0, None, None, False
+        else:
+            a = self._affine_args(g, **kwargs)
+            alpha, alpha_s, w_run, c_run, coef, coefvec = (a["alpha"], a["alpha_s"], a["w_run"], a["c_run"], a["coef"],
+                                                           a["coefvec"])
+            col_alphas = self._column_alphas(B)               # per column (multiplier, alpha_s, coef) or None
+            quotient = bool(self.use_quotient)
+        sq = g.vec("sq", dtype)
+        c = None if poly else (c_run if c_run is not None else g.vec("c", dtype))
+        symdeg = g.symdeg and w_run is None
+        w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
+        view = g.in_view
+        form = view.hsell_panel()
+        err_code = _error_code(cm.error_type)
+        tol = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))
+        cols = cols.to(device=dev, dtype=dtype)               # [n, B] in user order, any strides
+        out = torch.empty((n, B), dtype=dtype, device=dev)
+        iterations, errors = [], []
+        if B == 0:
+            cm.iterations, cm.column_errors = [], []
+            return out
+        t0 = time.perf_counter()
+        esz = cols.element_size()
+        hist = cm.max_iters + 2
+        L = C.STATE_LEN
+        # working set of the panel (allocated once, reused by every group of columns)
+        yacc = torch.zeros((form.n_slices + 1) * 32 * PB, dtype=dtype, device=dev)
+        tail_queue = torch.zeros(1, dtype=i32, device=dev)
+        zbuf = [torch.zeros((n, PB), dtype=dtype, device=dev), torch.zeros((n, PB), dtype=dtype, device=dev)]
+        q = torch.zeros((n, PB), dtype=dtype, device=dev)     # affine: the constant term; polynomial: the accumulated results
+        coef_dev = torch.tensor([float(v) for v in poly_coefs], dtype=f64, device=dev) if poly else None
+        err_hist = torch.zeros((PB, hist), dtype=f64, device=dev)
+        si_host = np.zeros(PB * L + 4, dtype=np.int32)        # + ticket, panel stop word, executed steps, spare
+        si_host[:PB * L].reshape(PB, L)[:, C.SI_STOP] = C.CONVERGED          # empty slots never run
+        si_host[PB * L + 1] = C.CONVERGED
+        # Columns are staged in groups: column-major blocks in the engine's row order (pgb_panel_stage), so that a slot
+        # loads / stores its column as one contiguous stream instead of one sector per value at random rows.  A group is
+        # as large as memory comfortably allows (input + output stage).
+        free_bytes = torch.cuda.mem_get_info(dev)[0]
+        group = int(max(4 * PB, min(B, (free_bytes * 2 // 5) // max(2 * n * esz, 1))))
+        group = int(getattr(self, "panel_group", group))
+        stage_in = torch.empty((min(group, B), n), dtype=dtype, device=dev)
+        stage_out = torch.empty((min(group, B), n), dtype=dtype, device=dev)
+        chunk = max(int(getattr(self, "panel_chunk", 8)), 1)  # steps enqueued between polls of the finished count
+        polls = [torch.empty(4, dtype=i32).pin_memory() for _ in range(2)]
+        events = [torch.cuda.Event(), torch.cuda.Event()]
+        C.count_launches(1)
+        marks = [] if os.environ.get("PGB_PANEL_TIMING") else None
+
+        def mark(label):
+            if marks is not None:
+                torch.cuda.synchronize()
+                marks.append((label, time.perf_counter()))
+
+        mark("buffers")
+        for j0 in range(0, B, group):
+            G = min(group, B - j0)
+            C.check(lib.pgb_panel_stage(n, code, 0, cols.data_ptr(), int(cols.stride(0)), int(cols.stride(1)),
+                                        C.ptr(g.perm), j0, G, C.ptr(stage_in), st))
+            for t in (zbuf[0], zbuf[1], q, yacc, tail_queue):
+                t.zero_()
+            sf = torch.zeros((PB, L), dtype=f64, device=dev)
+            si = torch.from_numpy(si_host).to(dev)
+            sched = torch.zeros(4, dtype=i32, device=dev)
+            slot_col = torch.full((PB,), -1, dtype=i32, device=dev)
+            slot_plan = torch.full((2 * PB,), -1, dtype=i32, device=dev)
+            plan_norm = torch.zeros(PB, dtype=f64, device=dev)
+            col_result = torch.zeros((G, 4), dtype=i32, device=dev)
+            keep_hist = G * hist <= (1 << 24)                 # error histories of every column (128 MB at most)
+            col_err = torch.zeros((G, hist), dtype=f64, device=dev) if keep_hist else None
+            params = None
+            if col_alphas is not None:
+                params = torch.tensor([[float(v) for v in t] for t in col_alphas[j0:j0 + G]], dtype=f64,
+                                      device=dev).contiguous()
+            job = C.PanelJob(G, hist, stage_in.data_ptr(), 1, n, stage_out.data_ptr(), 1, n, None, C.ptr(sq),
+                             None if params is not None else C.ptr(coefvec), C.ptr(params), float(alpha),
+                             float(alpha_s), float(coef), tol, 1.0 if err_code in (C.ERR_L1, C.ERR_MAX) else float(n),
+                             int(cm.max_iters), max(int(cm.end_modulo), 1), err_code, int(quotient),
+                             int(self.preserve_norm), C.ptr(sched), C.ptr(slot_col), C.ptr(slot_plan),
+                             C.ptr(plan_norm), C.ptr(col_result), C.ptr(col_err), int(poly), 0,
+                             C.ptr(q) if poly else None, C.ptr(coef_dev))
+            budget = (cm.max_iters + 2) * (G // PB + 2) + chunk   # more steps than any schedule needs: guards a driver bug
+
+            # chunk i+1 is enqueued before the finished count after chunk i is looked at (pinned copy + event): the
+            # device never waits for the host; the launches enqueued past the end are no-ops
+            def enqueue(i):
+                C.check(lib.pgb_affine_steps_panel(ctypes.byref(form.struct), C.ptr(view.indptr), code,
+                                                   ctypes.byref(job), C.ptr(w), C.ptr(c), None if poly else C.ptr(q),
+                                                   C.ptr(zbuf[0]),
+                                                   C.ptr(zbuf[1]), C.ptr(sf), C.ptr(si), C.ptr(err_hist), C.ptr(yacc),
+                                                   C.ptr(tail_queue), i * chunk + 1, chunk, st))
+                C.count_launches(6 * chunk)
+                polls[i & 1].copy_(sched, non_blocking=True)
+                events[i & 1].record()
+
+            mark("staged in")
+            enqueue(0)
+            i = 0
+            while True:
+                enqueue(i + 1)
+                events[i & 1].synchronize()
+                if int(polls[i & 1][1]) >= G:
+                    break
+                i += 1
+                if i * chunk > budget:
+                    raise Exception("pygrank_b200: panel scheduling did not terminate")
+            mark("job")
+            C.check(lib.pgb_panel_stage(n, code, 1, out.data_ptr(), B, 1, C.ptr(g.perm), j0, G, C.ptr(stage_out), st))
+            C.count_launches(2)
+            res = col_result.cpu().numpy()
+            mark("staged out")
+            for j in range(G):
+                it, stop, steps, live = (int(v) for v in res[j])
+                if not live:                                                    # abstract_filters.py:53-54
+                    iterations.append(0)
+                    errors.append(None)
+                    continue
+                iterations.append(it)
+                errors.append(col_err[j, 1:steps + 1] if col_err is not None else None)
+                if stop == C.MAX_ITERS and err_code != C.ERR_ITERS and cm.iter_exception is not None:
+                    raise cm.iter_exception("Could not converge within " + str(cm.max_iters) + " iterations")
+        if marks is not None:
+            prev = t0
+            for label, t in marks:
+                print(f"[panel] {label}: {(t - prev) * 1e3:.2f} ms", flush=True)
+                prev = t
+        cm.iterations = iterations
+        cm.iteration = iterations[-1] if iterations else 0
+        cm.errors = errors[-1] if errors else None
+        cm.column_errors = errors
+        cm.elapsed_time = time.perf_counter() - t0
+        return out
+
     def _check_dropout(self, g: DeviceGraph):
         """graph_dropout (abstract_filters.py:59-62) is drawn inside the gather kernel of the hub-blocked form."""
         if g.in_view.hsell(self.dtype) is None:
@@ -304,19 +469,6 @@ class RecursiveGraphFilter(GraphFilter):
         (set by sweep())."""
         return getattr(self, "_sweep", None)
 
-    def _panel_family(self, g) -> Optional[str]:
-        """Which batched kernel propagate() uses: "hsell" = panels of 4 fp32 / 2 fp64 columns through the hub-blocked
-        form (pgb_affine_steps_panel: 16-byte shared-memory / texture gathers, the index streams read once per panel);
-        "csr" = panels of 8 / 4 columns through the item-stream kernel (pgb_affine_steps_batched); None = column by
-        column.  PGB_PANEL: 0 = never, csr = the item-stream panel, anything else = batch with the best family."""
-        import os
-        forced = os.environ.get("PGB_PANEL")
-        if forced == "0":
-            return None
-        if forced == "csr":
-            return "csr"
-        return "hsell" if g.in_view.hsell_panel() is not None else "csr"
-
     def _can_batch(self, g, warm_start=None, graph_dropout: float = 0, n_columns: int = 2, **kwargs) -> bool:
         # Both panel kernels stream no edge values (every BASELINE config is unweighted).
         if g.in_view.weighted or warm_start is not None or graph_dropout != 0 or g.pathological:
@@ -340,148 +492,6 @@ class RecursiveGraphFilter(GraphFilter):
         if self._column_alphas(int(cols.shape[1])) is not None:
             raise Exception("per-column alpha needs the hub-blocked panel kernel (unweighted graph, PGB_HSELL=1)")
         return self._propagate_batched_csr(g, cols, **kwargs)
-
-    def _propagate_panels(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
-        """All feature columns through ``pgb_affine_steps_panel``: the panel's ``pgb_hsell_panel_width`` columns are
-        SLOTS scheduled on the device — a column enters a free slot (normalisation, scaled start vector, affine term,
-        state: abstract_filters.py:52-56), iterates with its own alpha, normaliser, error and stop decision, and is
-        written out when it stops while the others keep going, so no slot waits for the slowest column of a fixed group
-        and the host only polls the number of finished columns.  Results and iteration counts equal the reference's
-        column-by-column loop (signals.py:225-226)."""
-        lib = C.lib()
-        dtype, code = self.dtype, dtype_code(self.dtype)
-        f64, i32 = torch.float64, torch.int32
-        dev, n = g.out_view.indptr.device, g.n
-        st = C.stream_ptr()
-        cm = self.convergence
-        B = int(cols.shape[1])
-        PB = lib.pgb_hsell_panel_width(code)
-        a = self._affine_args(g, **kwargs)
-        alpha, alpha_s, w_run, c_run, coef, coefvec = (a["alpha"], a["alpha_s"], a["w_run"], a["c_run"], a["coef"],
-                                                       a["coefvec"])
-        col_alphas = self._column_alphas(B)                   # per column (multiplier, alpha_s, coef) or None
-        sq = g.vec("sq", dtype)
-        c = c_run if c_run is not None else g.vec("c", dtype)
-        symdeg = g.symdeg and w_run is None
-        w = None if symdeg else (w_run if w_run is not None else g.vec("w", dtype))
-        view = g.in_view
-        form = view.hsell_panel()
-        err_code = _error_code(cm.error_type)
-        tol = 0.0 if cm.tol is None else max(float(cm.tol), float(np.finfo(float).eps))
-        cols = cols.to(device=dev, dtype=dtype)               # [n, B] in user order, any strides
-        out = torch.empty((n, B), dtype=dtype, device=dev)
-        iterations, errors = [], []
-        if B == 0:
-            cm.iterations, cm.column_errors = [], []
-            return out
-        t0 = time.perf_counter()
-        esz = cols.element_size()
-        hist = cm.max_iters + 2
-        L = C.STATE_LEN
-        # working set of the panel (allocated once, reused by every group of columns)
-        yacc = torch.zeros((form.n_slices + 1) * 32 * PB, dtype=dtype, device=dev)
-        tail_queue = torch.zeros(1, dtype=i32, device=dev)
-        zbuf = [torch.zeros((n, PB), dtype=dtype, device=dev), torch.zeros((n, PB), dtype=dtype, device=dev)]
-        q = torch.zeros((n, PB), dtype=dtype, device=dev)
-        err_hist = torch.zeros((PB, hist), dtype=f64, device=dev)
-        si_host = np.zeros(PB * L + 4, dtype=np.int32)        # + ticket, panel stop word, executed steps, spare
-        si_host[:PB * L].reshape(PB, L)[:, C.SI_STOP] = C.CONVERGED          # empty slots never run
-        si_host[PB * L + 1] = C.CONVERGED
-        # Columns are staged in groups: column-major blocks in the engine's row order (pgb_panel_stage), so that a slot
-        # loads / stores its column as one contiguous stream instead of one sector per value at random rows.  A group is
-        # as large as memory comfortably allows (input + output stage).
-        free_bytes = torch.cuda.mem_get_info(dev)[0]
-        group = int(max(4 * PB, min(B, (free_bytes * 2 // 5) // max(2 * n * esz, 1))))
-        group = int(getattr(self, "panel_group", group))
-        stage_in = torch.empty((min(group, B), n), dtype=dtype, device=dev)
-        stage_out = torch.empty((min(group, B), n), dtype=dtype, device=dev)
-        chunk = max(int(getattr(self, "panel_chunk", 8)), 1)  # steps enqueued between polls of the finished count
-        polls = [torch.empty(4, dtype=i32).pin_memory() for _ in range(2)]
-        events = [torch.cuda.Event(), torch.cuda.Event()]
-        C.count_launches(1)
-        marks = [] if os.environ.get("PGB_PANEL_TIMING") else None
-
-        def mark(label):
-            if marks is not None:
-                torch.cuda.synchronize()
-                marks.append((label, time.perf_counter()))
-
-        mark("buffers")
-        for j0 in range(0, B, group):
-            G = min(group, B - j0)
-            C.check(lib.pgb_panel_stage(n, code, 0, cols.data_ptr(), int(cols.stride(0)), int(cols.stride(1)),
-                                        C.ptr(g.perm), j0, G, C.ptr(stage_in), st))
-            for t in (zbuf[0], zbuf[1], q, yacc, tail_queue):
-                t.zero_()
-            sf = torch.zeros((PB, L), dtype=f64, device=dev)
-            si = torch.from_numpy(si_host).to(dev)
-            sched = torch.zeros(4, dtype=i32, device=dev)
-            slot_col = torch.full((PB,), -1, dtype=i32, device=dev)
-            slot_plan = torch.full((2 * PB,), -1, dtype=i32, device=dev)
-            plan_norm = torch.zeros(PB, dtype=f64, device=dev)
-            col_result = torch.zeros((G, 4), dtype=i32, device=dev)
-            keep_hist = G * hist <= (1 << 24)                 # error histories of every column (128 MB at most)
-            col_err = torch.zeros((G, hist), dtype=f64, device=dev) if keep_hist else None
-            params = None
-            if col_alphas is not None:
-                params = torch.tensor([[float(v) for v in t] for t in col_alphas[j0:j0 + G]], dtype=f64,
-                                      device=dev).contiguous()
-            job = C.PanelJob(G, hist, stage_in.data_ptr(), 1, n, stage_out.data_ptr(), 1, n, None, C.ptr(sq),
-                             None if params is not None else C.ptr(coefvec), C.ptr(params), float(alpha),
-                             float(alpha_s), float(coef), tol, 1.0 if err_code in (C.ERR_L1, C.ERR_MAX) else float(n),
-                             int(cm.max_iters), max(int(cm.end_modulo), 1), err_code, int(self.use_quotient),
-                             int(self.preserve_norm), C.ptr(sched), C.ptr(slot_col), C.ptr(slot_plan),
-                             C.ptr(plan_norm), C.ptr(col_result), C.ptr(col_err))
-            budget = (cm.max_iters + 2) * (G // PB + 2) + chunk   # more steps than any schedule needs: guards a driver bug
-
-            # chunk i+1 is enqueued before the finished count after chunk i is looked at (pinned copy + event): the
-            # device never waits for the host; the launches enqueued past the end are no-ops
-            def enqueue(i):
-                C.check(lib.pgb_affine_steps_panel(ctypes.byref(form.struct), C.ptr(view.indptr), code,
-                                                   ctypes.byref(job), C.ptr(w), C.ptr(c), C.ptr(q), C.ptr(zbuf[0]),
-                                                   C.ptr(zbuf[1]), C.ptr(sf), C.ptr(si), C.ptr(err_hist), C.ptr(yacc),
-                                                   C.ptr(tail_queue), i * chunk + 1, chunk, st))
-                C.count_launches(6 * chunk)
-                polls[i & 1].copy_(sched, non_blocking=True)
-                events[i & 1].record()
-
-            mark("staged in")
-            enqueue(0)
-            i = 0
-            while True:
-                enqueue(i + 1)
-                events[i & 1].synchronize()
-                if int(polls[i & 1][1]) >= G:
-                    break
-                i += 1
-                if i * chunk > budget:
-                    raise Exception("pygrank_b200: panel scheduling did not terminate")
-            mark("job")
-            C.check(lib.pgb_panel_stage(n, code, 1, out.data_ptr(), B, 1, C.ptr(g.perm), j0, G, C.ptr(stage_out), st))
-            C.count_launches(2)
-            res = col_result.cpu().numpy()
-            mark("staged out")
-            for j in range(G):
-                it, stop, steps, live = (int(v) for v in res[j])
-                if not live:                                                    # abstract_filters.py:53-54
-                    iterations.append(0)
-                    errors.append(None)
-                    continue
-                iterations.append(it)
-                errors.append(col_err[j, 1:steps + 1] if col_err is not None else None)
-                if stop == C.MAX_ITERS and err_code != C.ERR_ITERS and cm.iter_exception is not None:
-                    raise cm.iter_exception("Could not converge within " + str(cm.max_iters) + " iterations")
-        if marks is not None:
-            prev = t0
-            for label, t in marks:
-                print(f"[panel] {label}: {(t - prev) * 1e3:.2f} ms", flush=True)
-                prev = t
-        cm.iterations = iterations
-        cm.iteration = iterations[-1] if iterations else 0
-        cm.errors = errors[-1] if errors else None
-        cm.column_errors = errors
-        cm.elapsed_time = time.perf_counter() - t0
-        return out
 
     def _propagate_batched_csr(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
         """All feature columns through ``pgb_affine_steps_batched``: panels of ``pgb_panel_width``
@@ -859,6 +869,26 @@ class ClosedFormGraphFilter(GraphFilter):
                 x = g.conv(x)
         return max(errors)
 
+    def _coefficient_table(self):
+        """coef[k] = the coefficient step k applies (step k runs with convergence.iteration == k); coef[0] unused."""
+        coefs, prev = [0.0], None
+        for k in range(1, max(self.convergence.max_iters, 1) + 1):
+            prev = self._coefficient(prev, k)
+            coefs.append(float(prev))
+        return coefs
+
+    def _can_batch(self, g, warm_start=None, graph_dropout: float = 0, n_columns: int = 2, **kwargs) -> bool:
+        # taylor filters in the node space: columns as slots of the hub-blocked panel kernel (polynomial mode)
+        if not self._fusable() or g.in_view.weighted or warm_start is not None or graph_dropout != 0 or g.pathological:
+            return False
+        if self._panel_family(g) != "hsell" or self.convergence.max_iters <= 1:
+            return False
+        return n_columns >= 2 or os.environ.get("PGB_PANEL") not in (None, "")
+
+    def _propagate_batched(self, g: DeviceGraph, cols: torch.Tensor, **kwargs) -> torch.Tensor:
+        kwargs.pop("n_columns", None)
+        return self._propagate_panels(g, cols, poly_coefs=self._coefficient_table(), **kwargs)
+
     def _coefficient(self, previous_coefficient, iteration: int) -> float:
         raise Exception("Use a derived class of ClosedFormGraphFilter that implements the _coefficient method")
 
@@ -870,11 +900,7 @@ class ClosedFormGraphFilter(GraphFilter):
         dev, n = p.device, g.n
         st = C.stream_ptr()
         cm = self.convergence
-        coefs, prev = [0.0], None
-        for k in range(1, max(cm.max_iters, 1) + 1):          # step k runs with convergence.iteration == k
-            prev = self._coefficient(prev, k)
-            coefs.append(float(prev))
-        coef_dev = torch.tensor(coefs, dtype=torch.float64, device=dev)
+        coef_dev = torch.tensor(self._coefficient_table(), dtype=torch.float64, device=dev)
         state_f64, state_i32, err_hist = self._new_state(g, norm, 1.0, False)
         sq = g.vec("sq", dtype)
         zbuf = [torch.empty(n, dtype=dtype, device=dev), torch.empty(n, dtype=dtype, device=dev)]

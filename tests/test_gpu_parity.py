@@ -281,6 +281,34 @@ def test_batched_propagate_matches_golden(pgb, torch_cuda, monkeypatch, name, ru
         assert rel_l1(out32[:, c], z[f"run_{run}_scores"][:, c]) <= FP32_TOL, (name, run, c)
 
 
+@pytest.mark.parametrize("name", GOLDEN_GRAPHS)
+@pytest.mark.parametrize("run", ["heat3", "heat3_tol9", "heat5_sym", "gen40", "gen3_tol", "pprclosed"])
+@pytest.mark.parametrize("relabel", ["hub", "none"])
+def test_closed_form_propagate_as_panels_matches_golden(pgb, torch_cuda, monkeypatch, name, run, relabel):
+    """propagate() of the closed-form filters through the polynomial mode of the hub-blocked panel kernel: every slot
+    accumulates coef[k] * power_k at its own step (abstract_filters.py:225-256); golden iteration counts and scores per
+    column.  Weighted graphs (no panel form) run column by column and must give the same."""
+    torch = torch_cuda
+    monkeypatch.setenv("PGB_HSELL_BLOCK_COLS", "64")          # several hub blocks and a tail on the small golden graphs
+    monkeypatch.setenv("PGB_HSELL_BLOCKS", "5")
+    monkeypatch.setenv("PGB_HSELL_MIN_ENTRIES", "4")
+    z, A, directed = load_golden(name)
+    norm, make, _ = _runs(pgb)[run]
+    g = _graph(pgb, A, directed, norm, relabel)
+    P = z["P"]
+    alg = make({"dtype": torch.float64})
+    assert alg._can_batch(g, n_columns=P.shape[1]) == (not g.in_view.weighted)
+    out = alg.propagate(g, P).cpu().numpy()
+    assert list(alg.convergence.iterations) == [int(v) for v in z[f"run_{run}_iters"]], (name, run)
+    for c in range(P.shape[1]):
+        assert rel_l1(out[:, c], z[f"run_{run}_scores"][:, c]) <= FP64_TOL, (name, run, c)
+    alg32 = make({"dtype": torch.float32})
+    out32 = alg32.propagate(g, P).cpu().numpy()
+    for c in range(P.shape[1]):
+        assert abs(alg32.convergence.iterations[c] - int(z[f"run_{run}_iters"][c])) <= 1
+        assert rel_l1(out32[:, c], z[f"run_{run}_scores"][:, c]) <= FP32_TOL, (name, run, c)
+
+
 @pytest.mark.parametrize("dtype_name,tol", [("float64", 1e-12), ("float32", 2e-6)])
 @pytest.mark.parametrize("family", ["hsell", "hsell_small_blocks", "hsell_groups", "csr"])
 def test_batched_propagate_ragged_panels_rmat17(pgb, torch_cuda, monkeypatch, dtype_name, tol, family):
