@@ -33,7 +33,8 @@ import torch
 from . import _capi as C
 
 FUSE = True      # False: never start a fused run (every node evaluates eagerly); debugging / CPU tests of the eager path
-STATS = {"eager_ops": 0, "eager_convs": 0, "fused_steps": 0, "runs": 0, "recomputed_runs": 0, "syncs": 0}
+STATS = {"eager_ops": 0, "eager_convs": 0, "fused_steps": 0, "runs": 0, "recomputed_runs": 0, "syncs": 0,
+         "step_waits": 0}   # syncs: full stream synchronisations; step_waits: waits for the event of ONE step
 
 
 def reset_stats():
@@ -742,9 +743,24 @@ def _check_finite(host_hist):
                         "RecursiveGraphFilter's quotient, or non-finite input)")
 
 
+_SNAP_ROWS = 1024
+_snap_pool: list = []      # pinned (state_f64 rows, state_i32 rows) snapshot buffers, reused across runs
+
+
+def _take_snapshots():
+    if _snap_pool:
+        return _snap_pool.pop()
+    return (torch.empty((_SNAP_ROWS, C.STATE_LEN), dtype=torch.float64).pin_memory(),
+            torch.empty((_SNAP_ROWS, C.STATE_LEN), dtype=torch.int32).pin_memory())
+
+
 class AffineRun:
     """x_k = (A o conv(x_{k-1}, M) + B) [/ sum] on pgb_affine_steps: resumable, and — once the driver's first convergence
-    test has shown its measure and threshold — ahead of the driver with the stop decision on the device."""
+    test has shown its measure and threshold — ahead of the driver with the stop decision on the device.
+
+    The driver's test of iteration k only needs step k: after every step the device state (error of the step, stop
+    flag) is copied to pinned host memory behind an event, and a test waits for THAT event, not for the steps enqueued
+    after it — the driver's own Python work of iteration k+1 overlaps the device's step k+1."""
 
     def __init__(self, g, f: _Affine, x0: torch.Tensor, quotient: bool, x0_node):
         from .graph import dtype_code
@@ -805,6 +821,7 @@ class AffineRun:
         self.known = 0                # steps whose error is on the host
         self.host_err = np.zeros(1)
         self.stopped_at = None        # step at which the device-side rule stopped the run
+        self.events = {}              # step -> event recorded after its state snapshot
 
     # -- matching ---------------------------------------------------------------------------------------------------
     @staticmethod
@@ -837,13 +854,60 @@ class AffineRun:
                                 device=self.err_hist.device)
             grown[:self.err_hist.numel()] = self.err_hist
             self.err_hist = grown
-        C.check(lib.pgb_affine_steps(ctypes.byref(self.cs), self.code, self.alpha, C.ptr(self.w_arg), C.ptr(self.sq_arg),
-                                     C.ptr(self.c), C.ptr(self.q), C.ptr(self.zbuf[0]), C.ptr(self.zbuf[1]), 0,
-                                     C.ptr(self.state_f64), C.ptr(self.state_i32), C.ptr(self.err_hist),
-                                     span_struct(self.ws), self.done + 1, count, 1, C.stream_ptr()))
+        if getattr(self, "snap", None) is None:
+            self.snap = _take_snapshots()
+        st = C.stream_ptr()
+        ws = span_struct(self.ws)
+        for _ in range(count):
+            C.check(lib.pgb_affine_steps(ctypes.byref(self.cs), self.code, self.alpha, C.ptr(self.w_arg),
+                                         C.ptr(self.sq_arg), C.ptr(self.c), C.ptr(self.q), C.ptr(self.zbuf[0]),
+                                         C.ptr(self.zbuf[1]), 0, C.ptr(self.state_f64), C.ptr(self.state_i32),
+                                         C.ptr(self.err_hist), ws, self.done + 1, 1, 1, st))
+            self.done += 1
+            if self.done < _SNAP_ROWS:                       # state after this step -> pinned host row, behind an event
+                self.snap[0][self.done].copy_(self.state_f64, non_blocking=True)
+                self.snap[1][self.done].copy_(self.state_i32, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self.events[self.done] = ev
         C.count_launches(count * self.view.kernels_per_step(self.dtype))
         STATS["fused_steps"] += count
-        self.done += count
+
+    def __del__(self):
+        snap = getattr(self, "snap", None)
+        if snap is not None and len(_snap_pool) < 8:
+            try:
+                for ev in getattr(self, "events", {}).values():   # nothing may still be writing into the rows
+                    ev.synchronize()
+                _snap_pool.append(snap)
+            except Exception:
+                pass
+
+    def _advance(self, k) -> bool:
+        """Learn the outcome of steps known+1 .. k from their snapshots, waiting only for the events of those steps.
+        False when a step has no snapshot (very long runs): the caller falls back to a full read."""
+        while self.known < k and self.known < self.done:
+            j = self.known + 1
+            ev = self.events.get(j)
+            if ev is None:
+                return False
+            ev.synchronize()
+            STATS["step_waits"] += 1
+            steps, stop = int(self.snap[1][j][C.SI_STEPS]), int(self.snap[1][j][C.SI_STOP])
+            if steps < j:                                    # the device had already stopped: launch j was a no-op
+                self.stopped_at, self.done = steps, steps
+                return True
+            if j >= self.host_err.shape[0]:
+                grown = np.zeros(max(2 * self.host_err.shape[0], j + 8))
+                grown[:self.host_err.shape[0]] = self.host_err
+                self.host_err = grown
+            self.host_err[j] = float(self.snap[0][j][C.SF_LASTERR])
+            _check_finite(self.host_err[j:j + 1])
+            self.known = j
+            if stop != C.RUNNING:
+                self.stopped_at, self.done = j, j            # launches enqueued after the stop were no-ops
+                return True
+        return True
 
     def _configure(self, mode, divisor, threshold):
         """Device-side measure and stop rule = the driver's test (convergence.py:97-101), adopted when its first test
@@ -891,7 +955,8 @@ class AffineRun:
                 self._launch(max(k - self.done, self.chunk if self.threshold is not None else 1))
                 if self.threshold is not None:
                     self.chunk = min(self.chunk * 2, 64)
-            self._read()
+            if not self._advance(k):
+                self._read()
         scale = self.mean / float(divisor) if _KIND[mode] != 2 else 1.0
         return float(self.host_err[k]) * scale
 
@@ -899,7 +964,8 @@ class AffineRun:
         """x_k * scale in the user's node order (one read-out kernel)."""
         k = handle.args[1]
         if self.threshold is not None and self.stopped_at is None and self.done > self.known:
-            self._read()
+            if not self._advance(self.done):
+                self._read()
         final = self.stopped_at if self.stopped_at is not None else self.done
         if final > k:
             # the device went past the iterate the driver ends on (its stop rule was not the assumed one): redo k steps
