@@ -188,7 +188,6 @@ class GraphFilter:
         form (pgb_affine_steps_panel: 16-byte shared-memory / texture gathers, the index streams read once per panel);
         "csr" = panels of 8 / 4 columns through the item-stream kernel (pgb_affine_steps_batched); None = column by
         column.  PGB_PANEL: 0 = never, csr = the item-stream panel, anything else = batch with the best family."""
-        import os
         forced = os.environ.get("PGB_PANEL")
         if forced == "0":
             return None
@@ -478,7 +477,6 @@ class RecursiveGraphFilter(GraphFilter):
             return False
         if family == "csr" and _error_code(self.convergence.error_type) == C.ERR_MAX:
             return False                                      # the item-stream panel kernel has no max reduction
-        import os
         if os.environ.get("PGB_PANEL") not in (None, ""):
             return True
         # default: a single column is cheaper through the single-vector kernel (a panel would carry padding columns);

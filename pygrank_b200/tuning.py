@@ -22,8 +22,6 @@ PageRank's alpha that is ``partitions`` full solves on the same personalization 
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Optional
-
 import torch
 
 from .filters import PageRank
