@@ -21,9 +21,22 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """(header, units, values) of the one profiled launch: from the CSV exported on the GPU box (gpu_profile_r2.sh) or
+    from the .ncu-rep itself."""
+    csv_path = rep[:-len(".ncu-rep")] + ".raw.csv"
+    if os.path.exists(csv_path):
+        out = open(csv_path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2]
+
+
+def hot(rep):
+    txt = rep[:-len(".ncu-rep")] + ".hot.txt"
+    if os.path.exists(txt):
+        return open(txt).read()
+    return subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_hot.py"), rep, "14"], capture_output=True, text=True).stdout
 
 
 def to_bytes(v, unit):
@@ -32,19 +45,24 @@ def to_bytes(v, unit):
 
 
 traffic = {}
-for suffix, dt in (("gather", "f32"), ("update", "f32"), ("gather_f64", "f64"), ("update_f64", "f64")):
+NOTES = {"gather": "RMAT scale 24 fp32, one launch of `bench.py --kernel-only`",
+         "update": "RMAT scale 24 fp32, one launch of `bench.py --kernel-only`",
+         "panel_gather": "panel path, RMAT scale 24, 4 x fp32 columns per node (f32x4 elements), one launch of `scripts/panel_probe.py`",
+         "panel_update": "panel path, RMAT scale 24, 4 x fp32 columns, one launch of `scripts/panel_probe.py`"}
+for suffix, dt in (("gather", "f32"), ("update", "f32"), ("gather_f64", "f64"), ("update_f64", "f64"),
+                   ("panel_gather", "f32x4"), ("panel_update", "f32x4")):
     rep = os.path.join(GO, f"prof_{tag}_{suffix}.ncu-rep")
-    if not os.path.exists(rep):
+    if not os.path.exists(rep) and not os.path.exists(rep[:-len(".ncu-rep")] + ".raw.csv"):
         continue
     hdr, units, vals = raw(rep)
     name = vals[hdr.index("Kernel Name")]
     rd = to_bytes(vals[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
     wr = to_bytes(vals[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
     traffic.setdefault(dt, {"bytes_per_launch": {}})["bytes_per_launch"][name.split("(")[0]] = rd + wr
-    if dt != "f32":
+    if dt == "f64":
         continue
     with open(os.path.join(OUT, f"kernel_{tag}_{suffix}.md"), "w") as f:
-        f.write(f"# `{name[:90]}` — ncu --set full --clock-control none ({tag}), RMAT scale 24 fp32, one launch of `bench.py --kernel-only`\n\n")
+        f.write(f"# `{name[:90]}` — ncu --set full --clock-control none ({tag}), {NOTES[suffix]}\n\n")
         f.write("Cold-cache, serialised profiler run: durations are indicative, counters are per launch.\n\n| metric | value | unit |\n|---|---:|---|\n")
         for i, h in enumerate(hdr):
             if h in WANT:
@@ -54,9 +72,8 @@ for suffix, dt in (("gather", "f32"), ("update", "f32"), ("gather_f64", "f64"), 
         f.write("\nTop warp stall reasons (warps per issue-active cycle):\n\n| reason | value |\n|---|---:|\n")
         for v, h in sorted(st, reverse=True)[:7]:
             f.write("| %s | %.2f |\n" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
-        if suffix == "gather":
-            hot = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_hot.py"), rep, "14"], capture_output=True, text=True).stdout
-            f.write("\nMost-sampled SASS instructions (source page):\n\n```\n" + hot + "```\n")
+        if suffix in ("gather", "panel_gather"):
+            f.write("\nMost-sampled SASS instructions (source page):\n\n```\n" + hot(rep) + "```\n")
 with open(os.path.join(OUT, f"traffic_{tag}.json"), "w") as f:
     json.dump(dict(traffic, source="ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, bench.py --kernel-only "
                                    "(RMAT scale 24), gather + update kernels of one fused step"), f, indent=1)
