@@ -56,3 +56,63 @@ def test_unsupported_strategies_are_refused():
             sweep.optimizer(lambda p: 0.0, max_vals=[1], **kw)
     with pytest.raises(Exception, match="divide_range"):
         sweep.optimizer(lambda p: 0.0, max_vals=[1], divide_range=1)
+
+
+class _Signal:
+    """The three attributes of a pg.GraphSignal the sweep's rankers touch (core/signals.py:38-60)."""
+
+    def __init__(self, graph, obj, node2id=None):
+        self.graph, self.np, self.node2id = graph, obj, node2id
+
+
+class _Filter:
+    def __init__(self):
+        import torch
+        self.dtype = torch.float64
+        self.calls = []
+
+    def _device_graph(self, graph):
+        return graph
+
+    def sweep(self, g, p, alphas, **kwargs):
+        import torch
+        self.calls.append(list(alphas))
+        return p[:, None] * torch.tensor(alphas, dtype=p.dtype)[None, :]
+
+
+def test_candidates_of_a_round_share_one_sweep():
+    """Announced candidates are evaluated by ONE sweep on the first miss and served from the cache afterwards; a new
+    personalization, or an in-place write to the old one, starts over; the final single-alpha ranking is its own solve."""
+    import torch
+    from pygrank_b200.lazy import LazyVec
+    from pygrank_b200.tuning import AlphaSweep
+    sweep = AlphaSweep.__new__(AlphaSweep)
+    sweep.filter, sweep._announced, sweep.stats = _Filter(), [], {"sweeps": 0, "columns": 0, "served": 0}
+    from collections import OrderedDict
+    sweep._cache = OrderedDict()
+    graph = object()
+    p = torch.arange(1.0, 6.0, dtype=torch.float64)
+    sig = _Signal(graph, LazyVec.wrap(p), {"a": 0})
+    grid = [[0.5], [0.6], [0.7]]
+    sweep.announce(grid)
+    outs = [sweep.ranker(c).rank(sig) for c in grid]
+    assert sweep.filter.calls == [[0.5, 0.6, 0.7]] and sweep.stats == {"sweeps": 1, "columns": 3, "served": 3}
+    for c, o in zip(grid, outs):
+        assert isinstance(o, _Signal) and o.graph is graph and o.node2id == {"a": 0}
+        assert torch.equal(o.np.materialize(), p * c[0])
+    # next round: two old candidates, two new ones -> one sweep with the new ones only (the missed one first)
+    sweep.announce([[0.6], [0.65], [0.7], [0.75]])
+    sweep.ranker([0.6]).rank(sig)
+    sweep.ranker([0.65]).rank(sig)
+    assert sweep.filter.calls[-1] == [0.65, 0.75] and sweep.stats["sweeps"] == 2
+    # the tuner's final ranking: a parameter nobody announced
+    sweep.announce([])
+    sweep.ranker([0.9]).rank(graph, sig)
+    assert sweep.filter.calls[-1] == [0.9]
+    # an in-place write to the personalization invalidates what was cached for it
+    p[0] = 100.0
+    sweep.announce([[0.5]])
+    out = sweep.ranker([0.5]).rank(sig)
+    assert sweep.filter.calls[-1] == [0.5] and float(out.np.materialize()[0]) == 50.0
+    with pytest.raises(Exception, match="graph signal"):
+        sweep.ranker([0.5]).rank(graph, [1.0, 2.0])
