@@ -50,6 +50,10 @@ for family in ("1", "csr"):          # hub-blocked panels (pgb_affine_steps_pane
         feats = torch.stack([p, p * 2, p * 0, p + 1, p * 3], 1).to(dtype)
         out = pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=dtype).propagate(g, feats)
         print("panel", family, dtype, tuple(out.shape), float(out.sum()))
+    if family == "1":                # polynomial mode of the panel kernel (closed-form filters)
+        feats = torch.stack([p, p * 2, p * 0, p + 1, p * 3], 1)
+        print("poly panel", float(pgb.HeatKernel(3, tol=1e-9).propagate(g, feats).sum()),
+              float(pgb.GenericGraphFilter([0.5, 0.3, 0.2], tol=1e-9, dtype=torch.float32).propagate(g, feats.float()).sum()))
 del os.environ["PGB_PANEL"]
 print("sweep", float(pgb.PageRank(0.85, tol=1e-9, max_iters=200, dtype=torch.float32).sweep(g, p.float(), [0.5, 0.7, 0.9]).sum()))
 # weighted graph on the hub-blocked form (edge values in the form)
