@@ -1,7 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
-PGB_PANEL_TIMING=1 timeout 300 python scripts/panel_e2e.py 2>&1 | tail -12
-PROBE_PANEL_CHUNK=4 timeout 300 python scripts/panel_e2e.py 2>&1 | tail -1
-PROBE_PANEL_CHUNK=16 timeout 300 python scripts/panel_e2e.py 2>&1 | tail -1
-PROBE_PANEL_GROUP=64 timeout 300 python scripts/panel_e2e.py 2>&1 | tail -1
-PGB_PANEL=1 timeout 300 python scripts/panel_probe.py 2>&1 | tail -1 | cut -c1-60,330-420
+out=gpurun_out/panel_probe4.jsonl
+: > $out
+run() { env "$@" timeout 300 python scripts/panel_probe.py 2>&1 | tail -1 >> $out; }
+run PGB_PANEL=1
+run PGB_PANEL=1 PGB_HSELL_BLOCKS=448
+run PGB_PANEL=1 PGB_HSELL_BLOCKS=512
+run PGB_PANEL=1 PGB_HSELL_PANEL_TAIL_WARPS=6
+run PGB_PANEL=1 PGB_HSELL_PANEL_TAIL_WARPS=10
+python - <<'PY'
+import json
+for l in open('gpurun_out/panel_probe4.jsonl'):
+    try: d=json.loads(l)
+    except Exception: print('bad', l[:200]); continue
+    e=d['env']; e.pop('PGB_PANEL',None)
+    print(f"{d['ms_per_panel_step']:.3f} ms K {d['K']} pieces {d['pieces']/1e6:.2f}M hub_slots {d['hub_slots']/1e6:.0f}M tail_entries {d['tail_entries']/1e6:.0f}M", e)
+PY
